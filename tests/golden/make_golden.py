@@ -1,0 +1,243 @@
+"""Generate tests/golden/*.npz by executing the REFERENCE's own GNN_model code.
+
+Runs only in the build container (needs /root/reference); the fixtures it writes are committed and
+are what the GPU box and the CPU suite read.  The reference's TeacherGNN path imports ``dgl`` (absent
+here), so this script installs a minimal stand-in for exactly the DGL surface GCN.py touches
+(SURVEY 8b "lower seam"): ``dgl.graph``, ``.to``, ``.local_scope``, ``.in_degrees``, ``.out_degrees``,
+``.number_of_edges``, ``.srcdata/.dstdata/.edata``, ``.update_all(copy_src|u_mul_e, sum)``,
+``dgl.utils.expand_as_pair``, ``dgl.base.DGLError``.  The stand-in's ``update_all`` is a sequential
+``index_add_`` over the COO edge list (multigraph semantics).  Everything else that executes -- layer
+construction, parameter init order, the forward loop, residual tricks, norm no-op rule, the wrappers --
+is the reference's unmodified code.
+
+    python tests/golden/make_golden.py        # rewrites tests/golden/ref_*.npz
+"""
+import contextlib
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+REF = '/root/reference'
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---------------------------------------------------------------- DGL stand-in
+class _FakeGraph:
+    def __init__(self, pair):
+        self.src = torch.as_tensor(pair[0], dtype=torch.long)
+        self.dst = torch.as_tensor(pair[1], dtype=torch.long)
+        self.n = int(max(self.src.max(), self.dst.max())) + 1
+        self.srcdata, self.edata = {}, {}
+        self.dstdata = self.srcdata            # homogeneous graph: one node frame
+
+    def to(self, device):
+        return self
+
+    @contextlib.contextmanager
+    def local_scope(self):
+        saved = dict(self.srcdata), dict(self.edata)
+        try:
+            yield
+        finally:
+            self.srcdata.clear(); self.srcdata.update(saved[0])
+            self.edata.clear(); self.edata.update(saved[1])
+
+    def in_degrees(self):
+        return torch.bincount(self.dst, minlength=self.n)
+
+    def out_degrees(self):
+        return torch.bincount(self.src, minlength=self.n)
+
+    def number_of_edges(self):
+        return self.src.numel()
+
+    def update_all(self, msg, red):
+        kind, field = msg[0], msg[1]
+        m = self.srcdata[field][self.src]
+        if kind == 'u_mul_e':
+            m = m * self.edata[msg[2]].reshape(-1, *([1] * (m.dim() - 1)))
+        out = torch.zeros((self.n,) + tuple(m.shape[1:]), dtype=m.dtype)
+        self.dstdata[red[2]] = out.index_add_(0, self.dst, m)
+
+
+def _install_shims():
+    dgl = types.ModuleType('dgl')
+    dgl.graph = lambda pair: _FakeGraph(pair)
+    fn = types.ModuleType('dgl.function')
+    fn.copy_src = lambda src, out: ('copy_src', src, out)
+    fn.u_mul_e = lambda u, e, out: ('u_mul_e', u, e, out)
+    fn.sum = lambda msg, out: ('sum', msg, out)
+    base = types.ModuleType('dgl.base')
+
+    class DGLError(Exception):
+        pass
+    base.DGLError = DGLError
+    dutils = types.ModuleType('dgl.utils')
+    dutils.expand_as_pair = lambda feat, g=None: (feat, feat)
+    dgl.function, dgl.base, dgl.utils = fn, base, dutils
+    sys.modules.update({'dgl': dgl, 'dgl.function': fn, 'dgl.base': base, 'dgl.utils': dutils})
+
+    # drop_tricks.py imports these at module top; none of them runs on the default (no graph-dropout) path
+    def _unused(*a, **k):
+        raise RuntimeError('not reachable on the TeacherGNN default path')
+    for name, attrs in {
+        'torch_scatter': {'scatter_add': _unused},
+        'torch_geometric': {},
+        'torch_geometric.nn': {},
+        'torch_geometric.nn.conv': {},
+        'torch_geometric.nn.conv.gcn_conv': {'gcn_norm': _unused},
+        'torch_geometric.utils': {'dropout_adj': _unused, 'subgraph': _unused},
+        'torch_geometric.utils.num_nodes': {'maybe_num_nodes': _unused},
+    }.items():
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+
+    # GNN_normalizations.py does ``from utils import D`` (a bare attribute bag, utils.py:857)
+    u = types.ModuleType('utils')
+
+    class D:
+        pass
+    u.D = D
+    sys.modules['utils'] = u
+
+
+def _args(**kw):
+    d = dict(type_trick='NoRes', type_model='GCN', num_layers=2, dim_hidden=16, num_feats=12, num_classes=5,
+             dropout=0.0, res_alpha=0.1, layer_agg='concat', transductive=True, N_nodes=0, device='cpu',
+             dataset='Cora', dim_learnable_input=0, lamda=0.5, num_groups=None, skip_weight=None,
+             graph_dropout=0.0, layerwise_dropout=False, dim_commonEmb=None)
+    se = kw.pop('whetherHasSE', '000')
+    d.update(kw)
+    a = SimpleNamespace(**d)
+    a.TeacherGNN = SimpleNamespace(whetherHasSE=[int(c) for c in se], change_to_featureless=False)
+    if a.dim_commonEmb is None:
+        a.dim_commonEmb = a.num_classes
+    return a
+
+
+def _graph(n, m, seed):
+    """Small symmetric multigraph-free graph with self loops (what the trainer hands the model)."""
+    g = torch.Generator().manual_seed(seed)
+    w = torch.arange(1, n + 1, dtype=torch.float64).pow(-0.7)
+    a = torch.multinomial(w, m, replacement=True, generator=g)
+    b = torch.multinomial(w, m, replacement=True, generator=g)
+    perm = torch.randperm(n, generator=g)
+    a, b = perm[a], perm[b]
+    keep = a != b
+    key = torch.unique(torch.cat([a[keep] * n + b[keep], b[keep] * n + a[keep]]))
+    loops = torch.arange(n)
+    ei = torch.stack([torch.cat([key // n, loops]), torch.cat([key % n, loops])])
+    return ei[:, torch.randperm(ei.shape[1], generator=g)]     # unsorted edge list
+
+
+CASES = {
+    # name: (args overrides, N, undirected draws, seed, eval_mode)
+    'nores_se000_L2':        (dict(type_trick='NoResNodeNorm', whetherHasSE='000', num_layers=2), 48, 120, 1),
+    'nores_se111_L3':        (dict(type_trick='NoRes', whetherHasSE='111', num_layers=3), 40, 100, 2),
+    'nores_se100_L4':        (dict(type_trick='NoResGroupNorm', whetherHasSE='100', num_layers=4,
+                                   dataset='Citeseer'), 36, 90, 3),
+    'initial_se111_L2':      (dict(type_trick='InitialBatchNorm', whetherHasSE='111', num_layers=2,
+                                   dataset='Pubmed'), 56, 150, 4),
+    'initial_se100_L3':      (dict(type_trick='InitialBatchNorm', whetherHasSE='100', num_layers=3,
+                                   res_alpha=0.2), 44, 110, 5),
+    'residual_se010_L3':     (dict(type_trick='Residual', whetherHasSE='010', num_layers=3, res_alpha=0.3), 40, 100, 6),
+    'dense_concat_L2':       (dict(type_trick='Dense', whetherHasSE='000', num_layers=2, layer_agg='concat'), 32, 80, 7),
+    'dense_maxpool_L2':      (dict(type_trick='Dense', whetherHasSE='010', num_layers=2, layer_agg='maxpool'), 32, 80, 8),
+    'dense_attention_L2':    (dict(type_trick='Dense', whetherHasSE='000', num_layers=2, layer_agg='attention'), 32, 80, 9),
+    'jumping_concat_L3':     (dict(type_trick='Jumping', whetherHasSE='010', num_layers=3, layer_agg='concat'), 36, 90, 10),
+    'jumping_maxpool_L2':    (dict(type_trick='Jumping', whetherHasSE='000', num_layers=2, layer_agg='maxpool',
+                                   num_classes=16), 36, 90, 11),
+    'exact_batchnorm_L2':    (dict(type_trick='BatchNorm', whetherHasSE='000', num_layers=2), 40, 100, 12),
+    'exact_pairnorm_L3':     (dict(type_trick='PairNorm', whetherHasSE='111', num_layers=3), 40, 100, 13),
+    'learnable_input_L2':    (dict(type_trick='Initial', whetherHasSE='010', num_layers=2, dim_learnable_input=6), 30, 70, 14),
+    'odd_dims_L2':           (dict(type_trick='NoRes', whetherHasSE='101', num_layers=2, dim_hidden=10, num_feats=9,
+                                   num_classes=3), 33, 75, 15),
+}
+
+
+def run_case(name, over, n, m, seed):
+    from GNN_model.GNN_normalizations import TeacherGNN       # the reference's class
+    torch.manual_seed(1000 + seed)
+    ei = _graph(n, m, seed)
+    a = _args(N_nodes=n, **over)
+    x = torch.randn(n, a.num_feats)
+    y = torch.randint(0, a.num_classes, (n,))
+    mask = torch.zeros(n, dtype=torch.bool)
+    mask[: max(4, n // 3)] = True
+    model = TeacherGNN(a, None)
+    model.eval() if name.startswith('exact_batchnorm') else model.train()     # dropout p=0 either way
+    out = {'edge_index': ei.numpy(), 'x': x.numpy(), 'y': y.numpy(), 'train_mask': mask.numpy(),
+           'args_json': np.array(_json_args(a))}
+    for k, v in model.state_dict().items():
+        out['param/' + k] = v.detach().numpy().copy()
+    res = model.get_3_embs(x, ei, mask)
+    logits = res.emb4classi_full
+    out['logits'] = logits.detach().numpy()
+    se_reg = model.se_reg_all
+    out['se_reg_all'] = np.array(float(se_reg) if se_reg is not None else np.nan, dtype=np.float32)
+    loss = torch.nn.functional.nll_loss(torch.log_softmax(res.emb4classi, 1), y[mask])
+    # With >=2 SE layers the reference accumulates ``se_reg_all += se_reg`` IN PLACE on the first layer's
+    # norm output (GCN.py:116-120), which current PyTorch refuses to differentiate through; for those cases
+    # the golden loss leaves the regulariser out (its value is still recorded in se_reg_all).
+    n_se = sum(1 for k in model.state_dict() if k.endswith('.le'))
+    reg_in_loss = se_reg is not None and n_se == 1
+    if reg_in_loss:
+        loss = loss + 0.5 * se_reg
+    out['reg_in_loss'] = np.array(int(reg_in_loss))
+    out['loss'] = loss.detach().numpy()
+    model.zero_grad()
+    loss.backward()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            out['grad/' + k] = p.grad.detach().numpy().copy()
+    les = model.model.model.collect_SE(x if a.dim_learnable_input == 0 else model.embs, ei)
+    out['les'] = les.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, f'ref_{name}.npz'), **out)
+    print(f'{name:24s} N={n} E={ei.shape[1]} logits{tuple(logits.shape)} se_reg={out["se_reg_all"]} loss={float(loss):.6f}')
+
+
+def _json_args(a):
+    import json
+    d = {k: v for k, v in vars(a).items() if isinstance(v, (int, float, str, bool, type(None)))}
+    d['whetherHasSE'] = ''.join(str(int(v)) for v in a.TeacherGNN.whetherHasSE)
+    # TeacherGNN.__init__ rewrites these in place (GNN_normalizations.py:13-22); store the user-facing values
+    return json.dumps(d)
+
+
+def kat_toy():
+    """Known-answer vector on the reference's own toy graph (utils.py:1096), through the reference GCNConv."""
+    from GNN_model.GCN import GCNConv
+    ei = torch.tensor([[0, 0, 1, 1, 1, 2], [0, 1, 0, 1, 2, 2]])
+    import dgl
+    g = dgl.graph((ei[0].tolist(), ei[1].tolist()))
+    a = SimpleNamespace(N_nodes=3)
+    out = {'edge_index': ei.numpy()}
+    for se in (False, True):
+        conv = GCNConv(3, 3, args=a, whetherHasSE=se)
+        with torch.no_grad():
+            conv.weight.copy_(torch.eye(3)); conv.bias.zero_()
+            if se:
+                conv.le.copy_(torch.arange(9.).view(3, 3) / 10)
+        rst, reg = conv(g, torch.eye(3))
+        out[f'rst_se{int(se)}'] = rst.detach().numpy()
+        if se:
+            out['se_reg'] = np.array(float(reg.detach()), dtype=np.float32)
+    np.savez_compressed(os.path.join(OUT, 'ref_kat_toy.npz'), **out)
+    print('kat_toy', out['rst_se0'].round(6).tolist(), out['rst_se1'].round(6).tolist(), out['se_reg'])
+
+
+if __name__ == '__main__':
+    if not os.path.isdir(REF):
+        sys.exit('needs /root/reference (build container only)')
+    _install_shims()
+    sys.path.insert(0, REF)
+    torch.set_num_threads(1)
+    kat_toy()
+    for name, (over, n, m, seed) in CASES.items():
+        run_case(name, dict(over), n, m, seed)

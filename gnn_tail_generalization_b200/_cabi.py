@@ -1,0 +1,93 @@
+"""ctypes binding of libcoldbrew_b200.so (the C ABI declared in include/coldbrew_b200.h).
+
+The product path has no CPU fallback: if the library is missing or a call fails, this module raises.
+PyTorch is used only for device memory (``tensor.data_ptr()``) and the current CUDA stream.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcoldbrew_b200.so')
+
+CB_OK = 0
+CB_ACT_NONE, CB_ACT_RELU = 0, 1
+CB_BY_DST, CB_BY_SRC = 0, 1
+
+Q_NUM_NODES, Q_NUM_EDGES, Q_ROW_BEGIN, Q_ROW_END, Q_HAS_ZERO_IN_DEG, Q_HUB_CHUNK = 0, 1, 2, 3, 4, 5
+Q_DST_ROWPTR, Q_DST_COL, Q_DST_PERM, Q_DST_NUM_HUB_CHUNKS = 10, 11, 12, 13
+Q_SRC_ROWPTR, Q_SRC_COL, Q_SRC_PERM, Q_SRC_NUM_HUB_CHUNKS, Q_SRC_NUM_EDGES = 20, 21, 22, 23, 24
+Q_DIN_INV_SQRT, Q_DOUT_INV_SQRT, Q_IN_DEGREE, Q_OUT_DEGREE = 30, 31, 32, 33
+
+# every symbol include/coldbrew_b200.h declares: name -> (restype, argtypes)
+_vp, _i64, _int, _dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
+SYMBOLS = {
+    'cb_last_error': (ctypes.c_char_p, []),
+    'cb_abi_version': (_int, []),
+    'cb_graph_create': (_int, [_vp, _i64, _i64, _int, _vp, ctypes.POINTER(_vp)]),
+    'cb_graph_create_sliced': (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp, ctypes.POINTER(_vp)]),
+    'cb_graph_destroy': (_int, [_vp]),
+    'cb_graph_query': (_int, [_vp, _int, _vp]),
+    'cb_graph_workspace_bytes': (_i64, [_vp, _int, _i64]),
+    'cb_agg_forward': (_int, [_vp, _vp, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _vp, _i64, _vp]),
+    'cb_agg_gather': (_int, [_vp, _int, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    'cb_prep_workspace_bytes': (_i64, [_i64, _i64]),
+    'cb_agg_backward_prep': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _dbl, _vp, _vp, _vp, _int, _vp,
+                                    _i64, _vp]),
+    'cb_row_scale': (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    'cb_sumsq_workspace_bytes': (_i64, []),
+    'cb_sumsq': (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
+    'cb_launch_count': (_i64, []),
+}
+
+
+class ColdBrewError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+    def __init__(self, fn, code, text):
+        super().__init__(f'{fn} failed with code {code}: {text}')
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f'{LIB_PATH} is missing: build it with `python -m gnn_tail_generalization_b200.build` '
+                f'(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)          # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if handle.cb_abi_version() != 1:
+            raise ImportError(f'{LIB_PATH}: ABI version {handle.cb_abi_version()} != 1, rebuild')
+        _lib = handle
+    return _lib
+
+
+def check(fn_name, rc):
+    if rc != CB_OK:
+        raise ColdBrewError(fn_name, rc, lib().cb_last_error().decode('utf-8', 'replace'))
+
+
+def call(fn_name, *args):
+    check(fn_name, getattr(lib(), fn_name)(*args))
+
+
+def ptr(t):
+    """Device address of a tensor, or NULL for None."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch_count():
+    return int(lib().cb_launch_count())

@@ -1,0 +1,334 @@
+// Neighbour gather-and-reduce over a CSR side of the graph, with the GCN layer's epilogue fused in.
+//
+// Replaces DGL's gSpMM('copy_lhs','sum') reached from GNN_model/GCN.py:238
+// (graph.update_all(fn.copy_src('h','m'), fn.sum('m','h'))) and, fused behind it, GCN.py:242-253
+// (in-degree scale, bias), GCN.py:127-128 (relu), res_tricks.py:14/23 (residual mix) and the next
+// layer's GCN.py:205-213 (out-degree scale).
+//
+// Work decomposition.  A "task" is one CSR row, or one hub chunk (a run of hub_chunk consecutive
+// entries of a row longer than hub_chunk).  A group of LPR lanes owns a task; a warp holds 32/LPR
+// groups.  Every lane owns NCH column slots of VEC floats (column = (ch*LPR + sub)*VEC), so a group
+// reads a feature row with full-width coalesced 16-byte loads, and every (row, column) accumulator is
+// a strictly in-order fp32 sum over the stored neighbours -- no atomics, no cross-lane reduction, the
+// result is bit-stable from run to run and equal to the sequential sum.  Hub chunks write partial rows
+// that k_combine adds in chunk order (same association as oracle/spmm_sum_csr.c with hub_chunk).
+//
+// The neighbour ids of a task are read LPR at a time with one coalesced load and handed round with
+// warp shuffles; UNROLL independent row loads are in flight per group before the first add.
+#include "cb_internal.cuh"
+
+namespace cb {
+
+struct AggArgs {
+    const int64_t* rowptr;
+    const int32_t* col;
+    int64_t n_rows;
+    const int32_t* chunk_row;
+    const int64_t* chunk_beg;
+    int64_t n_chunks;
+    int hub_chunk;
+    const float* X;      // [n_src, d]
+    int64_t d;           // row pitch of X and of every output, in floats
+    int64_t col0;        // first column handled by this launch
+    float* partial;      // [n_chunks, d]
+    // epilogue
+    const float* row_scale;   // [rows] or null
+    const float* bias;        // [d] or null
+    const float* x0;          // [rows, d] or null
+    float alpha, one_minus_alpha;
+    int act;
+    float* out;               // [rows, d] or null
+    const float* out2_scale;  // [rows]
+    float* out2;              // [rows, d] or null
+    uint8_t* mask;            // [rows, d] or null
+};
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+    using T = float4;
+    static __device__ __forceinline__ void load(float (&v)[4], const float* p) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void load_plain(float (&v)[4], const float* p) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    static __device__ __forceinline__ void store_mask(uint8_t* p, const float (&z)[4]) {
+        uchar4 m;
+        m.x = z[0] > 0.f; m.y = z[1] > 0.f; m.z = z[2] > 0.f; m.w = z[3] > 0.f;
+        *reinterpret_cast<uchar4*>(p) = m;
+    }
+};
+template <>
+struct Vec<1> {
+    using T = float;
+    static __device__ __forceinline__ void load(float (&v)[1], const float* p) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void load_plain(float (&v)[1], const float* p) { v[0] = *p; }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
+    static __device__ __forceinline__ void store_mask(uint8_t* p, const float (&z)[1]) { *p = z[0] > 0.f; }
+};
+
+// z = rs*acc + b ; r = act(z) ; out = (1-a) r + a x0 ; out2 = s2 * out ; mask = z > 0
+// Every product and sum is rounded separately (no FMA contraction), like the reference's chain of
+// elementwise ops (GCN.py:250,253; res_tricks.py:14,23).
+template <int VEC>
+__device__ __forceinline__ void epilogue_store(const AggArgs& a, int64_t row, int64_t c, float (&acc)[VEC]) {
+    const int64_t off = row * a.d + c;
+    float z[VEC], o[VEC];
+    const float rs = a.row_scale ? __ldg(a.row_scale + row) : 1.f;
+    float b[VEC], x0[VEC];
+    if (a.bias) Vec<VEC>::load(b, a.bias + c);
+    if (a.x0) Vec<VEC>::load(x0, a.x0 + off);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        float t = a.row_scale ? __fmul_rn(acc[i], rs) : acc[i];
+        if (a.bias) t = __fadd_rn(t, b[i]);
+        z[i] = t;
+        float r = (a.act == CB_ACT_RELU) ? fmaxf(t, 0.f) : t;
+        if (a.x0) r = __fadd_rn(__fmul_rn(a.one_minus_alpha, r), __fmul_rn(a.alpha, x0[i]));
+        o[i] = r;
+    }
+    if (a.out) Vec<VEC>::store(a.out + off, o);
+    if (a.out2) {
+        const float s2 = __ldg(a.out2_scale + row);
+        float o2[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o2[i] = __fmul_rn(o[i], s2);
+        Vec<VEC>::store(a.out2 + off, o2);
+    }
+    if (a.mask) Vec<VEC>::store_mask(a.mask + off, z);
+}
+
+template <int VEC, int LPR, int NCH, int UNROLL>
+__global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
+    constexpr int GROUPS = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR;
+    const int grp = lane / LPR;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t task = warp * GROUPS + grp;
+    if (task >= a.n_rows + a.n_chunks) return;
+
+    const bool is_chunk = task >= a.n_rows;
+    int64_t row, beg, end;
+    if (!is_chunk) {
+        row = task;
+        beg = __ldg(a.rowptr + row);
+        end = __ldg(a.rowptr + row + 1);
+        if (end - beg > a.hub_chunk) return;  // hub row: its chunks and k_combine produce it
+    } else {
+        const int64_t c = task - a.n_rows;
+        row = __ldg(a.chunk_row + c);
+        beg = __ldg(a.chunk_beg + c);
+        const int64_t rend = __ldg(a.rowptr + row + 1);
+        end = beg + a.hub_chunk < rend ? beg + a.hub_chunk : rend;
+    }
+
+    float acc[NCH][VEC];
+    int64_t cofs[NCH];
+    bool cval[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        cofs[ch] = a.col0 + (int64_t)(ch * LPR + sub) * VEC;
+        cval[ch] = cofs[ch] < a.d;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
+    }
+
+    for (int64_t base = beg; base < end; base += LPR) {
+        const int n = (int)(end - base < LPR ? end - base : LPR);
+        const int my = sub < n ? __ldg(a.col + base + sub) : 0;
+        for (int k = 0; k < n; k += UNROLL) {
+            float v[UNROLL][NCH][VEC];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int s = __shfl_sync(gmask, my, (k + u) & (LPR - 1), LPR);
+                if (k + u < n) {
+                    const float* xr = a.X + (int64_t)s * a.d;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch)
+                        if (cval[ch]) Vec<VEC>::load(v[u][ch], xr + cofs[ch]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (k + u < n) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch)
+                        if (cval[ch]) {
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) acc[ch][i] += v[u][ch][i];
+                        }
+                }
+            }
+        }
+    }
+
+    if (is_chunk) {
+        float* pr = a.partial + (task - a.n_rows) * a.d;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            if (cval[ch]) Vec<VEC>::store(pr + cofs[ch], acc[ch]);
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            if (cval[ch]) epilogue_store<VEC>(a, row, cofs[ch], acc[ch]);
+    }
+}
+
+// Adds the chunk partials of every hub row in chunk order and applies the epilogue.
+template <int VEC, int LPR, int NCH>
+__global__ void __launch_bounds__(256) k_combine(const AggArgs a) {
+    constexpr int GROUPS = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR;
+    const int grp = lane / LPR;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t c = warp * GROUPS + grp;
+    if (c >= a.n_chunks) return;
+    const int64_t row = a.chunk_row[c];
+    if (c > 0 && a.chunk_row[c - 1] == row) return;  // only the first chunk of a row combines
+    const int64_t deg = a.rowptr[row + 1] - a.rowptr[row];
+    const int64_t n = (deg + a.hub_chunk - 1) / a.hub_chunk;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        const int64_t co = a.col0 + (int64_t)(ch * LPR + sub) * VEC;
+        if (co >= a.d) continue;
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        for (int64_t k = 0; k < n; ++k) {
+            float v[VEC];
+            Vec<VEC>::load_plain(v, a.partial + (c + k) * a.d + co);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] += v[i];
+        }
+        epilogue_store<VEC>(a, row, co, acc);
+    }
+}
+
+template <int VEC, int LPR, int NCH>
+static int launch_cfg(const AggArgs& a, cudaStream_t st) {
+    constexpr int GROUPS = 32 / LPR;
+    constexpr int WARPS = 8;
+    constexpr int UNROLL = (VEC * NCH >= 8) ? 4 : 8;
+    constexpr int U = UNROLL < LPR ? UNROLL : LPR;
+    const int64_t tasks = a.n_rows + a.n_chunks;
+    if (tasks > 0) {
+        const int64_t blocks = ceil_div(tasks, (int64_t)WARPS * GROUPS);
+        CB_REQUIRE(blocks < (int64_t)INT32_MAX, CB_E_UNSUPPORTED, "aggregation grid too large");
+        k_agg<VEC, LPR, NCH, U><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+        CB_LAUNCH_CHECK();
+    }
+    if (a.n_chunks > 0) {
+        const int64_t blocks = ceil_div(a.n_chunks, (int64_t)WARPS * GROUPS);
+        k_combine<VEC, LPR, NCH><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+        CB_LAUNCH_CHECK();
+    }
+    return CB_OK;
+}
+
+template <int VEC>
+static int launch_vec(AggArgs a, cudaStream_t st) {
+    const int64_t units = ceil_div(a.d, VEC);
+    if (units <= 1) return launch_cfg<VEC, 1, 1>(a, st);
+    if (units <= 2) return launch_cfg<VEC, 2, 1>(a, st);
+    if (units <= 4) return launch_cfg<VEC, 4, 1>(a, st);
+    if (units <= 8) return launch_cfg<VEC, 8, 1>(a, st);
+    if (units <= 16) return launch_cfg<VEC, 16, 1>(a, st);
+    if (units <= 32) return launch_cfg<VEC, 32, 1>(a, st);
+    if (units <= 64) return launch_cfg<VEC, 32, 2>(a, st);
+    // wider rows: column blocks of 128 vector slots, the neighbour list is walked once per block
+    for (int64_t u0 = 0; u0 < units; u0 += 128) {
+        a.col0 = u0 * VEC;
+        const int64_t left = units - u0;
+        int rc = left <= 32   ? launch_cfg<VEC, 32, 1>(a, st)
+                 : left <= 64 ? launch_cfg<VEC, 32, 2>(a, st)
+                              : launch_cfg<VEC, 32, 4>(a, st);
+        if (rc) return rc;
+    }
+    return CB_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int run_agg(const cb_graph* g, int side_id, AggArgs a, void* workspace, int64_t workspace_bytes,
+                   cudaStream_t st) {
+    const Side& s = side_id == CB_BY_DST ? g->by_dst : g->by_src;
+    a.rowptr = s.rowptr;
+    a.col = s.col;
+    a.n_rows = g->rows;
+    a.chunk_row = s.chunk_row;
+    a.chunk_beg = s.chunk_beg;
+    a.n_chunks = s.n_chunks;
+    a.hub_chunk = g->hub_chunk;
+    a.col0 = 0;
+    a.partial = (float*)workspace;
+    const int64_t need = s.n_chunks * a.d * (int64_t)sizeof(float);
+    CB_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need), CB_E_WORKSPACE,
+               "aggregation workspace missing or smaller than cb_graph_workspace_bytes()");
+    const bool vec4 = (a.d % 4 == 0) && aligned16(a.X) && aligned16(a.out) && aligned16(a.out2) &&
+                      aligned16(a.x0) && aligned16(a.bias) && aligned16(a.partial) &&
+                      (reinterpret_cast<uintptr_t>(a.mask) & 3u) == 0;
+    return vec4 ? launch_vec<4>(a, st) : launch_vec<1>(a, st);
+}
+
+}  // namespace cb
+
+extern "C" {
+
+int64_t cb_graph_workspace_bytes(const cb_graph_t* g, int side, int64_t d) {
+    if (!g || d <= 0) return 0;
+    const cb::Side& s = side == CB_BY_DST ? g->by_dst : g->by_src;
+    return s.n_chunks * d * (int64_t)sizeof(float);
+}
+
+int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t d, const float* bias, const float* x0,
+                   double alpha, int act, float* out, float* out_scaled, uint8_t* mask, void* workspace,
+                   int64_t workspace_bytes, void* stream) {
+    using namespace cb;
+    CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_forward: graph is NULL");
+    CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_forward: d must be positive");
+    CB_REQUIRE(g->rows == 0 || H != nullptr, CB_E_INVALID, "cb_agg_forward: H is NULL");
+    CB_REQUIRE(out != nullptr || out_scaled != nullptr, CB_E_INVALID, "cb_agg_forward: no output buffer");
+    CB_REQUIRE(act == CB_ACT_NONE || act == CB_ACT_RELU, CB_E_INVALID, "cb_agg_forward: unknown activation");
+    AggArgs a{};
+    a.X = H;
+    a.d = d;
+    a.row_scale = g->din_is;
+    a.bias = bias;
+    a.x0 = x0;
+    a.alpha = (float)alpha;
+    a.one_minus_alpha = (float)(1.0 - alpha);
+    a.act = act;
+    a.out = out;
+    a.out2_scale = g->dout_is;
+    a.out2 = out_scaled;
+    a.mask = mask;
+    return run_agg(g, CB_BY_DST, a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t d, const float* row_scale,
+                  float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace cb;
+    CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_gather: graph is NULL");
+    CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_agg_gather: unknown side");
+    CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_gather: d must be positive");
+    CB_REQUIRE(g->rows == 0 || (X != nullptr && out != nullptr), CB_E_INVALID, "cb_agg_gather: NULL buffer");
+    AggArgs a{};
+    a.X = X;
+    a.d = d;
+    a.row_scale = row_scale;
+    a.act = CB_ACT_NONE;
+    a.out = out;
+    return run_agg(g, side, a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

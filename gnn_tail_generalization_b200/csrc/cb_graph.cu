@@ -1,0 +1,425 @@
+// Device-side graph construction: COO edge_index -> CSR by destination + CSR by source, degrees,
+// degree^-1/2 vectors, zero-in-degree flag and the hub-chunk work lists.
+//
+// Replaces the reference's host-side graph build (GNN_model/GCN.py:92-94: edge_index -> Python lists ->
+// dgl.graph), the per-forward degree recomputation (GCN.py:205-209, 242-246) and the per-forward
+// zero-in-degree scan with its device->host sync (GCN.py:187-188).
+//
+// The stable key sort uses cub::DeviceRadixSort (header library shipped with the CUDA toolkit); every
+// other step is a kernel in this file.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <vector>
+
+#include "cb_internal.cuh"
+
+namespace cb {
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+
+// One pass over the edge list: range-check both endpoints, build the 32-bit sort key of each side
+// (local row, or `rows` as the "not owned" sentinel that sorts to the end) and count degrees.
+__global__ void k_edge_keys(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
+                            int64_t N, int64_t row_begin, int64_t row_end, uint32_t* __restrict__ key_dst,
+                            uint32_t* __restrict__ key_src, int32_t* __restrict__ eid_a,
+                            int32_t* __restrict__ eid_b, int32_t* __restrict__ in_deg,
+                            int32_t* __restrict__ out_deg, int* __restrict__ err) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint32_t rows = (uint32_t)(row_end - row_begin);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+        const int64_t s = src[e], t = dst[e];
+        if (s < 0 || s >= N || t < 0 || t >= N) {
+            *err = 1;
+            key_dst[e] = rows;
+            key_src[e] = rows;
+        } else {
+            const bool own_t = (t >= row_begin && t < row_end);
+            const bool own_s = (s >= row_begin && s < row_end);
+            key_dst[e] = own_t ? (uint32_t)(t - row_begin) : rows;
+            key_src[e] = own_s ? (uint32_t)(s - row_begin) : rows;
+            if (own_t) atomicAdd(in_deg + (t - row_begin), 1);
+            if (own_s) atomicAdd(out_deg + (s - row_begin), 1);
+        }
+        eid_a[e] = (int32_t)e;
+        eid_b[e] = (int32_t)e;
+    }
+}
+
+// col[j] = other endpoint of the j-th stored edge
+__global__ void k_gather_cols(const int64_t* __restrict__ other, const int32_t* __restrict__ perm,
+                              int64_t n, int32_t* __restrict__ col) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        col[j] = (int32_t)other[perm[j]];
+}
+
+// ---- exclusive scan int32 -> int64 (three kernels, 1024 items per block) ----------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t* total) {
+    __shared__ int64_t warp_sums[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    int64_t base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_THREADS / 32; ++i) {
+        const int64_t s = warp_sums[i];
+        if (i < w) base += s;
+        tot += s;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+template <typename Map>
+__global__ void k_scan_block_sums(int64_t n, Map map, int64_t* __restrict__ block_sums) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) s += map(base + i);
+    int64_t tot;
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void k_scan_spine(int64_t n_blocks, int64_t* __restrict__ block_sums) {
+    // single block; sequential over tiles of SCAN_THREADS entries, exclusive in place
+    int64_t carry = 0;
+    for (int64_t b = 0; b < n_blocks; b += SCAN_THREADS) {
+        const int64_t i = b + threadIdx.x;
+        const int64_t v = i < n_blocks ? block_sums[i] : 0;
+        int64_t tot;
+        const int64_t ex = block_exclusive_scan(v, &tot);
+        if (i < n_blocks) block_sums[i] = carry + ex;
+        carry += tot;
+        __syncthreads();
+    }
+}
+
+template <typename Map>
+__global__ void k_scan_write(int64_t n, Map map, const int64_t* __restrict__ block_sums,
+                             int64_t* __restrict__ out) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int64_t v[SCAN_ITEMS];
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? map(base + i) : 0;
+        s += v[i];
+    }
+    int64_t tot;
+    int64_t run = block_exclusive_scan(s, &tot) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+        if (base + i == n - 1) out[n] = run;  // grand total in the extra slot
+    }
+}
+
+struct DegMap {
+    const int32_t* deg;
+    __device__ int64_t operator()(int64_t i) const { return deg[i]; }
+};
+struct ChunkCountMap {
+    const int32_t* deg;
+    int hub_chunk;
+    __device__ int64_t operator()(int64_t i) const {
+        const int d = deg[i];
+        return d > hub_chunk ? (d + hub_chunk - 1) / hub_chunk : 0;
+    }
+};
+
+template <typename Map>
+static int exclusive_scan(int64_t n, Map map, int64_t* out /*[n+1]*/, int64_t* spine, cudaStream_t st) {
+    if (n == 0) {
+        CB_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t), st));
+        return CB_OK;
+    }
+    const int64_t nb = ceil_div(n, SCAN_TILE);
+    k_scan_block_sums<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(n, map, spine);
+    CB_LAUNCH_CHECK();
+    k_scan_spine<<<1, SCAN_THREADS, 0, st>>>(nb, spine);
+    CB_LAUNCH_CHECK();
+    k_scan_write<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(n, map, spine, out);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+// degree^-1/2 with the reference's clamp(min=1); computed in double and rounded once to fp32
+__global__ void k_inv_sqrt_deg(const int32_t* __restrict__ deg, int64_t rows, float* __restrict__ out,
+                               int* __restrict__ zero_flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
+        const int d = deg[r];
+        if (d == 0 && zero_flag) *zero_flag = 1;
+        out[r] = (float)(1.0 / sqrt((double)(d < 1 ? 1 : d)));
+    }
+}
+
+// expand hub rows into their chunk descriptors
+__global__ void k_fill_chunks(const int32_t* __restrict__ deg, const int64_t* __restrict__ rowptr,
+                              const int64_t* __restrict__ chunk_ofs, int64_t rows, int hub_chunk,
+                              int32_t* __restrict__ chunk_row, int64_t* __restrict__ chunk_beg) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
+        const int d = deg[r];
+        if (d <= hub_chunk) continue;
+        const int n = (d + hub_chunk - 1) / hub_chunk;
+        const int64_t o = chunk_ofs[r], b = rowptr[r];
+        for (int k = 0; k < n; ++k) {
+            chunk_row[o + k] = (int32_t)r;
+            chunk_beg[o + k] = b + (int64_t)k * hub_chunk;
+        }
+    }
+}
+
+static int grid_for(int64_t n, int threads) {
+    const int64_t want = ceil_div(n > 0 ? n : 1, threads);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    return (int)(want < cap ? want : cap);
+}
+
+static int bits_for(uint32_t max_value) {  // number of low bits that can be non-zero in [0, max_value]
+    int b = 1;
+    while (b < 32 && (max_value >> b) != 0) ++b;
+    return b;
+}
+
+struct Scratch {  // frees whatever build() allocated for temporary use, on every exit path
+    std::vector<void*> ptrs;
+    ~Scratch() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t alloc(T** p, int64_t n) {
+        cudaError_t e = cudaMalloc((void**)p, (size_t)(n > 0 ? n : 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+
+static void free_side(Side& s) {
+    cudaFree(s.rowptr);
+    cudaFree(s.col);
+    cudaFree(s.perm);
+    cudaFree(s.deg);
+    cudaFree(s.chunk_row);
+    cudaFree(s.chunk_beg);
+    s = Side();
+}
+
+// Finish one side given sorted edge ids (first n_edges entries are the owned edges in stable order).
+static int finish_side(Side& side, const int64_t* other_endpoint, int64_t rows, int hub_chunk,
+                       int64_t* spine, cudaStream_t st) {
+    CB_CUDA(cudaMalloc((void**)&side.rowptr, (size_t)(rows + 1) * sizeof(int64_t)));
+    int rc = exclusive_scan(rows, DegMap{side.deg}, side.rowptr, spine, st);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(&side.n_edges, side.rowptr + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    CB_CUDA(cudaMalloc((void**)&side.col, (size_t)(side.n_edges > 0 ? side.n_edges : 1) * sizeof(int32_t)));
+    if (side.n_edges > 0) {
+        k_gather_cols<<<grid_for(side.n_edges, 256), 256, 0, st>>>(other_endpoint, side.perm, side.n_edges,
+                                                                    side.col);
+        CB_LAUNCH_CHECK();
+    }
+    // hub chunk lists
+    Scratch tmp;
+    int64_t* chunk_ofs = nullptr;
+    CB_CUDA(tmp.alloc(&chunk_ofs, rows + 1));
+    rc = exclusive_scan(rows, ChunkCountMap{side.deg, hub_chunk}, chunk_ofs, spine, st);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(&side.n_chunks, chunk_ofs + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    if (side.n_chunks > 0) {
+        CB_CUDA(cudaMalloc((void**)&side.chunk_row, (size_t)side.n_chunks * sizeof(int32_t)));
+        CB_CUDA(cudaMalloc((void**)&side.chunk_beg, (size_t)side.n_chunks * sizeof(int64_t)));
+        k_fill_chunks<<<grid_for(rows, 256), 256, 0, st>>>(side.deg, side.rowptr, chunk_ofs, rows, hub_chunk,
+                                                           side.chunk_row, side.chunk_beg);
+        CB_LAUNCH_CHECK();
+        CB_CUDA(cudaStreamSynchronize(st));
+    }
+    return CB_OK;
+}
+
+static int build(cb_graph* g, const int64_t* edge_index, int64_t E, cudaStream_t st) {
+    const int64_t rows = g->rows;
+    const int64_t* src = edge_index;
+    const int64_t* dst = edge_index + E;
+    Scratch tmp;
+
+    CB_CUDA(cudaMalloc((void**)&g->by_dst.deg, (size_t)(rows > 0 ? rows : 1) * sizeof(int32_t)));
+    CB_CUDA(cudaMalloc((void**)&g->by_src.deg, (size_t)(rows > 0 ? rows : 1) * sizeof(int32_t)));
+    CB_CUDA(cudaMemsetAsync(g->by_dst.deg, 0, (size_t)(rows > 0 ? rows : 1) * sizeof(int32_t), st));
+    CB_CUDA(cudaMemsetAsync(g->by_src.deg, 0, (size_t)(rows > 0 ? rows : 1) * sizeof(int32_t), st));
+    CB_CUDA(cudaMalloc((void**)&g->din_is, (size_t)(rows > 0 ? rows : 1) * sizeof(float)));
+    CB_CUDA(cudaMalloc((void**)&g->dout_is, (size_t)(rows > 0 ? rows : 1) * sizeof(float)));
+
+    uint32_t *key_dst = nullptr, *key_src = nullptr, *key_alt = nullptr;
+    int32_t *eid_a = nullptr, *eid_b = nullptr, *eid_alt = nullptr;
+    int* flags = nullptr;  // [0] = range error, [1] = zero in-degree
+    int64_t* spine = nullptr;
+    CB_CUDA(tmp.alloc(&key_dst, E));
+    CB_CUDA(tmp.alloc(&key_src, E));
+    CB_CUDA(tmp.alloc(&key_alt, E));
+    CB_CUDA(tmp.alloc(&eid_a, E));
+    CB_CUDA(tmp.alloc(&eid_b, E));
+    CB_CUDA(tmp.alloc(&eid_alt, E));
+    CB_CUDA(tmp.alloc(&flags, 2));
+    CB_CUDA(tmp.alloc(&spine, ceil_div(rows > 0 ? rows : 1, SCAN_TILE) + 1));
+    CB_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
+
+    if (E > 0) {
+        k_edge_keys<<<grid_for(E, 256), 256, 0, st>>>(src, dst, E, g->n_nodes, g->row_begin, g->row_end,
+                                                      key_dst, key_src, eid_a, eid_b, g->by_dst.deg,
+                                                      g->by_src.deg, flags);
+        CB_LAUNCH_CHECK();
+    }
+    k_inv_sqrt_deg<<<grid_for(rows, 256), 256, 0, st>>>(g->by_dst.deg, rows, g->din_is, flags + 1);
+    CB_LAUNCH_CHECK();
+    k_inv_sqrt_deg<<<grid_for(rows, 256), 256, 0, st>>>(g->by_src.deg, rows, g->dout_is, nullptr);
+    CB_LAUNCH_CHECK();
+
+    int h_flags[2] = {0, 0};
+    CB_CUDA(cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    CB_REQUIRE(h_flags[0] == 0, CB_E_RANGE, "edge_index holds a node id outside [0, num_nodes)");
+    g->has_zero_in_deg = h_flags[1];
+
+    // stable LSD radix sort of (key, edge id); `rows` is the sentinel for edges of other slices
+    const int end_bit = bits_for((uint32_t)rows);
+    size_t cub_bytes = 0;
+    {
+        cub::DoubleBuffer<uint32_t> kb(key_dst, key_alt);
+        cub::DoubleBuffer<int32_t> vb(eid_a, eid_alt);
+        CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, kb, vb, (int)E, 0, end_bit, st));
+    }
+    void* cub_tmp = nullptr;
+    CB_CUDA(tmp.alloc((char**)&cub_tmp, (int64_t)cub_bytes));
+
+    for (int which = 0; which < 2; ++which) {
+        Side& side = which == 0 ? g->by_dst : g->by_src;
+        cub::DoubleBuffer<uint32_t> kb(which == 0 ? key_dst : key_src, key_alt);
+        cub::DoubleBuffer<int32_t> vb(which == 0 ? eid_a : eid_b, eid_alt);
+        if (E > 0) {
+            CB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, kb, vb, (int)E, 0, end_bit, st));
+            count_launch(2 * ((end_bit + 7) / 8));
+        }
+        // the owned edges are the first sum(deg) entries of the sorted list; keep exactly those
+        int rc = CB_OK;
+        // temporarily point perm at the sorted buffer; finish_side reads it to gather columns
+        int32_t* sorted = vb.Current();
+        side.perm = sorted;
+        rc = finish_side(side, which == 0 ? src : dst, rows, g->hub_chunk, spine, st);
+        if (rc) {
+            side.perm = nullptr;
+            return rc;
+        }
+        int32_t* keep = nullptr;
+        cudaError_t e = cudaMalloc((void**)&keep, (size_t)(side.n_edges > 0 ? side.n_edges : 1) * sizeof(int32_t));
+        if (e != cudaSuccess) {
+            side.perm = nullptr;
+            return cuda_fail(e, "cudaMalloc(perm)", __FILE__, __LINE__);
+        }
+        side.perm = keep;
+        CB_CUDA(cudaMemcpyAsync(keep, sorted, (size_t)side.n_edges * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        CB_CUDA(cudaStreamSynchronize(st));
+    }
+    return CB_OK;
+}
+
+}  // namespace cb
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int cb_graph_create_sliced(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes,
+                           int64_t row_begin, int64_t row_end, int hub_chunk, void* stream,
+                           cb_graph_t** out) {
+    using namespace cb;
+    CB_REQUIRE(out != nullptr, CB_E_INVALID, "cb_graph_create: out is NULL");
+    *out = nullptr;
+    CB_REQUIRE(num_edges >= 0 && num_nodes >= 0, CB_E_INVALID, "cb_graph_create: negative size");
+    CB_REQUIRE(num_edges == 0 || edge_index != nullptr, CB_E_INVALID, "cb_graph_create: edge_index is NULL");
+    CB_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= num_nodes, CB_E_INVALID,
+               "cb_graph_create: row range outside [0, num_nodes]");
+    CB_REQUIRE(num_nodes < (int64_t)INT32_MAX && num_edges < (int64_t)INT32_MAX, CB_E_UNSUPPORTED,
+               "cb_graph_create: num_nodes and num_edges must be < 2^31 per handle");
+    cb_graph* g = new cb_graph();
+    g->n_nodes = num_nodes;
+    g->row_begin = row_begin;
+    g->row_end = row_end;
+    g->rows = row_end - row_begin;
+    g->hub_chunk = hub_chunk > 0 ? hub_chunk : CB_DEFAULT_HUB_CHUNK;
+    cudaError_t e = cudaGetDevice(&g->device);
+    int rc = e == cudaSuccess ? build(g, edge_index, num_edges, (cudaStream_t)stream)
+                              : cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
+    if (rc != CB_OK) {
+        cb_graph_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return CB_OK;
+}
+
+int cb_graph_create(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int hub_chunk,
+                    void* stream, cb_graph_t** out) {
+    return cb_graph_create_sliced(edge_index, num_edges, num_nodes, 0, num_nodes, hub_chunk, stream, out);
+}
+
+int cb_graph_destroy(cb_graph_t* g) {
+    if (!g) return CB_OK;
+    cb::free_side(g->by_dst);
+    cb::free_side(g->by_src);
+    cudaFree(g->din_is);
+    cudaFree(g->dout_is);
+    delete g;
+    return CB_OK;
+}
+
+int cb_graph_query(const cb_graph_t* g, int what, void* out) {
+    using namespace cb;
+    CB_REQUIRE(g != nullptr && out != nullptr, CB_E_INVALID, "cb_graph_query: NULL argument");
+    int64_t* i = (int64_t*)out;
+    const void** p = (const void**)out;
+    switch (what) {
+        case CB_Q_NUM_NODES: *i = g->n_nodes; break;
+        case CB_Q_NUM_EDGES: *i = g->by_dst.n_edges; break;
+        case CB_Q_ROW_BEGIN: *i = g->row_begin; break;
+        case CB_Q_ROW_END: *i = g->row_end; break;
+        case CB_Q_HAS_ZERO_IN_DEG: *i = g->has_zero_in_deg; break;
+        case CB_Q_HUB_CHUNK: *i = g->hub_chunk; break;
+        case CB_Q_DST_ROWPTR: *p = g->by_dst.rowptr; break;
+        case CB_Q_DST_COL: *p = g->by_dst.col; break;
+        case CB_Q_DST_PERM: *p = g->by_dst.perm; break;
+        case CB_Q_DST_NUM_HUB_CHUNKS: *i = g->by_dst.n_chunks; break;
+        case CB_Q_SRC_ROWPTR: *p = g->by_src.rowptr; break;
+        case CB_Q_SRC_COL: *p = g->by_src.col; break;
+        case CB_Q_SRC_PERM: *p = g->by_src.perm; break;
+        case CB_Q_SRC_NUM_HUB_CHUNKS: *i = g->by_src.n_chunks; break;
+        case CB_Q_SRC_NUM_EDGES: *i = g->by_src.n_edges; break;
+        case CB_Q_DIN_INV_SQRT: *p = g->din_is; break;
+        case CB_Q_DOUT_INV_SQRT: *p = g->dout_is; break;
+        case CB_Q_IN_DEGREE: *p = g->by_dst.deg; break;
+        case CB_Q_OUT_DEGREE: *p = g->by_src.deg; break;
+        default: set_error("cb_graph_query: unknown selector"); return CB_E_INVALID;
+    }
+    return CB_OK;
+}
+
+}  // extern "C"

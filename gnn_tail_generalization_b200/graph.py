@@ -1,0 +1,133 @@
+"""Device-resident graph handle: the replacement for the ``dgl.graph`` object the reference's layer
+walks (GNN_model/GCN.py:92-94, 186-246).
+
+Only the DGL surface the TeacherGNN path touches is mirrored: ``in_degrees``, ``out_degrees``,
+``number_of_edges``, ``number_of_nodes``, ``local_scope`` (a no-op: the handle is immutable).
+Everything is built on the device by ``cb_graph_create`` from the int64 ``edge_index`` tensor.
+"""
+import contextlib
+import ctypes
+
+import torch
+
+from . import _cabi as C
+
+
+class _DevArray:
+    """Zero-copy view of library-owned device memory through __cuda_array_interface__."""
+
+    def __init__(self, addr, n, typestr):
+        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (addr, True), 'version': 2}
+
+
+class GraphHandle:
+    """CSR-by-destination + CSR-by-source of one graph (or one node slice of it) in HBM."""
+
+    def __init__(self, edge_index, num_nodes, row_begin=0, row_end=None, hub_chunk=0):
+        if not (torch.is_tensor(edge_index) and edge_index.is_cuda):
+            raise ValueError('edge_index must be a CUDA tensor (this path has no CPU implementation)')
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError(f'edge_index must be [2, E], got {tuple(edge_index.shape)}')
+        ei = edge_index.to(torch.int64).contiguous()
+        self.device = ei.device
+        self.num_nodes = int(num_nodes)
+        row_end = self.num_nodes if row_end is None else int(row_end)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            C.call('cb_graph_create_sliced', C.ptr(ei), ei.shape[1], self.num_nodes, int(row_begin), row_end,
+                   int(hub_chunk), C.stream_ptr(self.device), ctypes.byref(self._h))
+        self.row_begin, self.row_end = int(row_begin), row_end
+        self.rows = row_end - int(row_begin)
+        self.num_edges = self._qi(C.Q_NUM_EDGES)
+        self.num_edges_by_src = self._qi(C.Q_SRC_NUM_EDGES)
+        self.has_zero_in_degree = bool(self._qi(C.Q_HAS_ZERO_IN_DEG))
+        self.hub_chunk = self._qi(C.Q_HUB_CHUNK)
+        self.num_hub_chunks = (self._qi(C.Q_DST_NUM_HUB_CHUNKS), self._qi(C.Q_SRC_NUM_HUB_CHUNKS))
+        # degree^-1/2 vectors stay owned by the handle; these tensors alias them (read-only use)
+        self.din_inv_sqrt = self._view(C.Q_DIN_INV_SQRT, self.rows, '<f4')
+        self.dout_inv_sqrt = self._view(C.Q_DOUT_INV_SQRT, self.rows, '<f4')
+        self._ws = {}
+
+    # ---- C-ABI plumbing -------------------------------------------------------------------
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError('graph handle already destroyed')
+        return self._h
+
+    def _qi(self, what):
+        v = ctypes.c_int64()
+        C.call('cb_graph_query', self.handle, what, ctypes.byref(v))
+        return int(v.value)
+
+    def _view(self, what, n, typestr):
+        p = ctypes.c_void_p()
+        C.call('cb_graph_query', self.handle, what, ctypes.byref(p))
+        if n == 0:
+            dt = {'<f4': torch.float32, '<i4': torch.int32, '<i8': torch.int64}[typestr]
+            return torch.empty(0, dtype=dt, device=self.device)
+        return torch.as_tensor(_DevArray(p.value, n, typestr), device=self.device)
+
+    def workspace(self, side, d):
+        """Scratch for the hub-chunk partial rows of one aggregation (cached per (side, d))."""
+        need = int(C.lib().cb_graph_workspace_bytes(self.handle, side, d))
+        if need == 0:
+            return None, 0
+        key = (side, d)
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws[key] = buf
+        return buf, need
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.din_inv_sqrt = self.dout_inv_sqrt = None
+            C.lib().cb_graph_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- structure access (copies; for tests and diagnostics) -----------------------------------
+    def csr(self, side=C.CB_BY_DST):
+        """(rowptr int64 [rows+1], col int32 [E], perm int32 [E]) as fresh tensors."""
+        q = (C.Q_DST_ROWPTR, C.Q_DST_COL, C.Q_DST_PERM) if side == C.CB_BY_DST else \
+            (C.Q_SRC_ROWPTR, C.Q_SRC_COL, C.Q_SRC_PERM)
+        e = self.num_edges if side == C.CB_BY_DST else self.num_edges_by_src
+        return (self._view(q[0], self.rows + 1, '<i8').clone(), self._view(q[1], e, '<i4').clone(),
+                self._view(q[2], e, '<i4').clone())
+
+    # ---- the DGL surface GCNConv.forward uses (GCN.py:186-246) ------------------------------------
+    def in_degrees(self):
+        return self._view(C.Q_IN_DEGREE, self.rows, '<i4').to(torch.int64)
+
+    def out_degrees(self):
+        return self._view(C.Q_OUT_DEGREE, self.rows, '<i4').to(torch.int64)
+
+    def number_of_edges(self):
+        return self.num_edges
+
+    def number_of_nodes(self):
+        return self.num_nodes
+
+    @contextlib.contextmanager
+    def local_scope(self):
+        yield self
+
+    def to(self, device):
+        if torch.device(device) != self.device and torch.device(device).index is not None:
+            raise ValueError('a GraphHandle lives on the device it was built on')
+        return self
+
+    # ---- halo exchange hook: identity on a whole graph, overridden by the node-sliced handle -----
+    def exchange(self, local_rows):
+        """Returns the matrix holding every source row the owned rows gather from."""
+        return local_rows
+
+
+def graph_from_edge_index(edge_index, num_nodes, hub_chunk=0):
+    return GraphHandle(edge_index, num_nodes, hub_chunk=hub_chunk)

@@ -1,0 +1,214 @@
+"""Autograd bindings of the C-ABI kernels: what the replacement GCNConv calls where the reference
+called DGL (GNN_model/GCN.py:198-253) and elementwise PyTorch ops.
+
+Every function here requires CUDA tensors and raises otherwise; there is no CPU fallback.
+"""
+import torch
+
+from . import _cabi as C
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('gnn_tail_generalization_b200 kernels need CUDA tensors (no CPU fallback)')
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f'expected float32, got {t.dtype}')
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# raw (non-differentiable) kernel calls
+# ---------------------------------------------------------------------------------------------
+
+def agg_forward_raw(graph, H, bias=None, x0=None, alpha=0.0, relu=False, want_out=True, want_scaled=False,
+                    want_mask=False):
+    """One fused forward aggregation over the owned rows.  H holds every source row ([N_global, d])."""
+    _need_cuda(H, bias, x0)
+    H, bias, x0 = _f32c(H), _f32c(bias), _f32c(x0)
+    d = H.shape[1]
+    if H.shape[0] != graph.num_nodes:
+        raise ValueError(f'H has {H.shape[0]} rows, the graph has {graph.num_nodes} nodes')
+    out = torch.empty((graph.rows, d), dtype=torch.float32, device=H.device) if want_out else None
+    out_scaled = torch.empty((graph.rows, d), dtype=torch.float32, device=H.device) if want_scaled else None
+    mask = torch.empty((graph.rows, d), dtype=torch.uint8, device=H.device) if want_mask else None
+    ws, ws_bytes = graph.workspace(C.CB_BY_DST, d)
+    with torch.cuda.device(H.device):
+        C.call('cb_agg_forward', graph.handle, C.ptr(H), d, C.ptr(bias), C.ptr(x0), float(alpha),
+               C.CB_ACT_RELU if relu else C.CB_ACT_NONE, C.ptr(out), C.ptr(out_scaled), C.ptr(mask),
+               C.ptr(ws), ws_bytes, C.stream_ptr(H.device))
+    return out, out_scaled, mask
+
+
+def agg_gather_raw(graph, side, X, row_scale=None):
+    """out[r] = row_scale[r] * sum_{j in row r} X[col[j]]  over one CSR side of the graph."""
+    _need_cuda(X, row_scale)
+    X, row_scale = _f32c(X), _f32c(row_scale)
+    d = X.shape[1]
+    if X.shape[0] != graph.num_nodes:
+        raise ValueError(f'X has {X.shape[0]} rows, the graph has {graph.num_nodes} nodes')
+    out = torch.empty((graph.rows, d), dtype=torch.float32, device=X.device)
+    ws, ws_bytes = graph.workspace(side, d)
+    with torch.cuda.device(X.device):
+        C.call('cb_agg_gather', graph.handle, side, C.ptr(X), d, C.ptr(row_scale), C.ptr(out), C.ptr(ws),
+               ws_bytes, C.stream_ptr(X.device))
+    return out
+
+
+def backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, relu, mixed, alpha, want_bias, want_x0):
+    ref = d_out if d_out is not None else d_out_scaled
+    _need_cuda(ref)
+    d_out, d_out_scaled, relu_out = _f32c(d_out), _f32c(d_out_scaled), _f32c(relu_out)
+    rows, d = ref.shape
+    G = torch.empty((rows, d), dtype=torch.float32, device=ref.device)
+    d_bias = torch.empty(d, dtype=torch.float32, device=ref.device) if want_bias else None
+    d_x0 = torch.empty((rows, d), dtype=torch.float32, device=ref.device) if want_x0 else None
+    ws_bytes = int(C.lib().cb_prep_workspace_bytes(rows, d)) if want_bias else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ref.device) if ws_bytes else None
+    with torch.cuda.device(ref.device):
+        C.call('cb_agg_backward_prep', graph.handle, C.ptr(d_out), C.ptr(d_out_scaled), d, C.ptr(mask),
+               C.ptr(relu_out), C.CB_ACT_RELU if relu else C.CB_ACT_NONE, int(bool(mixed)), float(alpha),
+               C.ptr(G), C.ptr(d_bias), C.ptr(d_x0), 0, C.ptr(ws), ws_bytes, C.stream_ptr(ref.device))
+    return G, d_bias, d_x0
+
+
+def row_scale_raw(x, s):
+    _need_cuda(x, s)
+    x, s = _f32c(x), _f32c(s)
+    if x.dim() != 2 or s.shape[0] != x.shape[0]:
+        raise ValueError('row_scale: x must be [rows, d] and s [rows]')
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        C.call('cb_row_scale', C.ptr(x), C.ptr(s), x.shape[0], x.shape[1], C.ptr(y), C.stream_ptr(x.device))
+    return y
+
+
+def sumsq_raw(x):
+    _need_cuda(x)
+    x = _f32c(x)
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    nb = int(C.lib().cb_sumsq_workspace_bytes())
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        C.call('cb_sumsq', C.ptr(x), x.numel(), C.ptr(out), C.ptr(ws), nb, C.stream_ptr(x.device))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# differentiable ops
+# ---------------------------------------------------------------------------------------------
+
+class _RowScale(torch.autograd.Function):
+    """y = s[:,None] * x with s constant (GCN.py:205-213); the adjoint is the same kernel."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.save_for_backward(s)
+        return row_scale_raw(x, s)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (s,) = ctx.saved_tensors
+        return row_scale_raw(dy, s), None
+
+
+def row_scale(x, s):
+    return _RowScale.apply(x, s)
+
+
+class _FrobNorm(torch.autograd.Function):
+    """||E||_F (GCN.py:232 th.norm(self.le)); gradient g * E / ||E||, zero at E = 0 like torch.norm."""
+
+    @staticmethod
+    def forward(ctx, e):
+        n = sumsq_raw(e).sqrt_().reshape(())
+        ctx.save_for_backward(e, n)
+        return n
+
+    @staticmethod
+    def backward(ctx, g):
+        e, n = ctx.saved_tensors
+        scale = torch.where(n > 0, g / n, torch.zeros_like(n))
+        return e * scale
+
+
+def frob_norm(e):
+    return _FrobNorm.apply(e)
+
+
+class _FusedAggregate(torch.autograd.Function):
+    """out = mix(act(din^-1/2 * A^T-sum(H) + b), x0), optionally also dout^-1/2 * out.
+
+    forward : halo exchange of H (identity on one GPU) -> cb_agg_forward
+    backward: cb_agg_backward_prep -> halo exchange of G -> cb_agg_gather over the by-source CSR
+    """
+
+    @staticmethod
+    def forward(ctx, H, bias, x0, graph, alpha, relu, want_out, want_scaled):
+        mixed = x0 is not None
+        need_grad = any(t is not None and t.requires_grad for t in (H, bias, x0))
+        # relu mask source for backward: the plain relu output doubles as the mask when nothing was
+        # mixed into it, otherwise a byte mask is written by the kernel
+        use_out_as_mask = relu and not mixed and want_out
+        want_mask = relu and need_grad and not use_out_as_mask
+        Hfull = graph.exchange(H)
+        out, out_scaled, mask = agg_forward_raw(graph, Hfull, bias, x0, alpha, relu, want_out, want_scaled, want_mask)
+        ctx.graph, ctx.alpha, ctx.relu, ctx.mixed = graph, alpha, relu, mixed
+        ctx.has_bias, ctx.use_out_as_mask = bias is not None, use_out_as_mask
+        ctx.save_for_backward(mask if want_mask else None, out if (use_out_as_mask and need_grad) else None)
+        ctx.set_materialize_grads(False)
+        if out is not None and out_scaled is not None:
+            return out, out_scaled
+        # a Function must return tensors; the unused slot gets an empty placeholder
+        empty = H.new_empty(0)
+        return (out if out is not None else empty), (out_scaled if out_scaled is not None else empty)
+
+    @staticmethod
+    def backward(ctx, d_out, d_out_scaled):
+        mask, relu_out = ctx.saved_tensors
+        graph = ctx.graph
+        if d_out is not None and d_out.numel() == 0:
+            d_out = None
+        if d_out_scaled is not None and d_out_scaled.numel() == 0:
+            d_out_scaled = None
+        if d_out is None and d_out_scaled is None:
+            return (None,) * 8
+        want_bias = ctx.has_bias and ctx.needs_input_grad[1]
+        want_x0 = ctx.mixed and ctx.needs_input_grad[2]
+        G, d_bias, d_x0 = backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, ctx.relu, ctx.mixed,
+                                            ctx.alpha, want_bias, want_x0)
+        dH = None
+        if ctx.needs_input_grad[0]:
+            dH = agg_gather_raw(graph, C.CB_BY_SRC, graph.exchange(G), None)
+        return dH, d_bias, d_x0, None, None, None, None, None
+
+
+def fused_aggregate(H, graph, bias=None, x0=None, alpha=0.0, relu=False, want_out=True, want_scaled=False):
+    """Returns (out, out_scaled); the one not asked for is None."""
+    if not (want_out or want_scaled):
+        raise ValueError('fused_aggregate: nothing requested')
+    out, out_scaled = _FusedAggregate.apply(H, bias, x0, graph, float(alpha), bool(relu), bool(want_out),
+                                            bool(want_scaled))
+    return (out if want_out else None), (out_scaled if want_scaled else None)
+
+
+class _CopySum(torch.autograd.Function):
+    """rst[v] = sum_{(u->v)} h[u]: the bare update_all(copy_src, sum) of GCN.py:238."""
+
+    @staticmethod
+    def forward(ctx, H, graph):
+        ctx.graph = graph
+        return agg_gather_raw(graph, C.CB_BY_DST, graph.exchange(H), None)
+
+    @staticmethod
+    def backward(ctx, d):
+        return agg_gather_raw(ctx.graph, C.CB_BY_SRC, ctx.graph.exchange(d.contiguous()), None), None
+
+
+def copy_sum(H, graph):
+    return _CopySum.apply(H, graph)

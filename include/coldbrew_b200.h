@@ -1,0 +1,172 @@
+/*
+ * coldbrew_b200 -- C ABI of the B200-native TeacherGNN aggregation path.
+ *
+ * This is the "lower seam" of Cold Brew's GCN layer: everything the reference reaches through DGL's C
+ * API from GNN_model/GCN.py is replaced by the entry points below (reference file:line cited per
+ * function).  Plain C: raw device pointers, sizes and a cudaStream_t passed as void*.  No torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative CB_E_* code; cb_last_error() gives the text
+ *     of the last failure on the calling thread;
+ *   - the caller owns every tensor buffer; the library owns only what cb_graph_create allocates;
+ *   - no call synchronises the device except cb_graph_create / cb_graph_create_sliced (one-time build);
+ *   - all launches go to the stream passed in; no internal threads; no hidden allocations after
+ *     graph creation (per-call scratch is the caller-supplied `workspace`, sized by
+ *     cb_graph_workspace_bytes);
+ *   - feature matrices are row-major, contiguous, fp32; row r of an [n, d] matrix starts at r*d.
+ *   - node ids inside a graph handle are int32 (N < 2^31), edge offsets int64.
+ */
+#ifndef COLDBREW_B200_H
+#define COLDBREW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_ABI_VERSION 1
+
+enum {
+    CB_OK = 0,
+    CB_E_INVALID = -1,     /* bad argument (null pointer, negative size, d <= 0 ...) */
+    CB_E_RANGE = -2,       /* a node id in edge_index is outside [0, N) */
+    CB_E_CUDA = -3,        /* a CUDA runtime call failed; see cb_last_error() */
+    CB_E_UNSUPPORTED = -4, /* shape outside what the kernels cover (N or E >= 2^31) */
+    CB_E_WORKSPACE = -5    /* workspace missing or too small */
+};
+
+/* activation selector for the fused epilogue (GCN.py:127-128 applies F.relu after the layer) */
+enum { CB_ACT_NONE = 0, CB_ACT_RELU = 1 };
+
+/* which side of the graph an aggregation walks */
+enum {
+    CB_BY_DST = 0, /* rows = destination nodes, gathers over in-edges   (forward,  GCN.py:238) */
+    CB_BY_SRC = 1  /* rows = source nodes,      gathers over out-edges  (backward, autograd of :238) */
+};
+
+/* cb_graph_query selectors.  Integers are written as int64_t, pointers as const void* (device). */
+enum {
+    CB_Q_NUM_NODES = 0,      /* int64: N (global) */
+    CB_Q_NUM_EDGES = 1,      /* int64: edges stored in the BY_DST structure */
+    CB_Q_ROW_BEGIN = 2,      /* int64: first owned node */
+    CB_Q_ROW_END = 3,        /* int64: one past the last owned node */
+    CB_Q_HAS_ZERO_IN_DEG = 4,/* int64: 1 if an owned node has no in-edge (GCN.py:187-188) */
+    CB_Q_HUB_CHUNK = 5,      /* int64: rows longer than this are summed chunk-wise */
+    CB_Q_DST_ROWPTR = 10,    /* const int64_t* [rows+1] */
+    CB_Q_DST_COL = 11,       /* const int32_t* [E_dst]  source id of every stored in-edge */
+    CB_Q_DST_PERM = 12,      /* const int32_t* [E_dst]  position in the caller's edge list */
+    CB_Q_DST_NUM_HUB_CHUNKS = 13, /* int64 */
+    CB_Q_SRC_ROWPTR = 20,    /* const int64_t* [rows+1] */
+    CB_Q_SRC_COL = 21,       /* const int32_t* [E_src]  destination id of every stored out-edge */
+    CB_Q_SRC_PERM = 22,      /* const int32_t* [E_src] */
+    CB_Q_SRC_NUM_HUB_CHUNKS = 23, /* int64 */
+    CB_Q_SRC_NUM_EDGES = 24, /* int64: edges stored in the BY_SRC structure */
+    CB_Q_DIN_INV_SQRT = 30,  /* const float* [rows]  clamp(in_degree,1)^-1/2   (GCN.py:242-246) */
+    CB_Q_DOUT_INV_SQRT = 31, /* const float* [rows]  clamp(out_degree,1)^-1/2  (GCN.py:205-209) */
+    CB_Q_IN_DEGREE = 32,     /* const int32_t* [rows] */
+    CB_Q_OUT_DEGREE = 33     /* const int32_t* [rows] */
+};
+
+typedef struct cb_graph cb_graph_t;
+
+/* text of the last error raised on this thread ("" if none) */
+const char* cb_last_error(void);
+int cb_abi_version(void);
+
+/*
+ * Build the device-side graph structure from a COO edge list.
+ * Replaces GCN.py:92-94 (edge_index -> .tolist() -> dgl.graph(...).to(device)), the per-call degree
+ * computations of GCN.py:205-209,242-246 and the per-call zero-in-degree scan of GCN.py:187-188:
+ * all three are properties of the static graph and are computed once here.
+ *
+ *   edge_index  device, int64, [2, E] row-major: row 0 = source ids, row 1 = destination ids.
+ *               Multigraph semantics: duplicate edges are kept and count twice.
+ *   hub_chunk   rows with more than hub_chunk stored edges are summed as consecutive chunks of
+ *               hub_chunk entries (in order) whose partials are then added in order; <= 0 picks the
+ *               default (CB_DEFAULT_HUB_CHUNK).
+ * Result: CSR by destination and CSR by source.  Inside a row the stored order is the order of the
+ * caller's edge list (stable), so an in-order row sum equals a sequential pass over the COO list.
+ * Synchronises `stream` before returning.
+ */
+#define CB_DEFAULT_HUB_CHUNK 256
+int cb_graph_create(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int hub_chunk,
+                    void* stream, cb_graph_t** out);
+
+/*
+ * Same, for one slice of a 1-D node partition (no counterpart in the reference, which is single
+ * device): keeps the in-edges of destination nodes in [row_begin, row_end) (BY_DST structure) and the
+ * out-edges of source nodes in the same range (BY_SRC structure).  Column ids stay global; row
+ * indices, degrees and scale vectors are local (node v is row v - row_begin).
+ */
+int cb_graph_create_sliced(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes,
+                           int64_t row_begin, int64_t row_end, int hub_chunk, void* stream,
+                           cb_graph_t** out);
+
+int cb_graph_destroy(cb_graph_t* g);
+int cb_graph_query(const cb_graph_t* g, int what, void* out);
+
+/* bytes of scratch cb_agg_forward / cb_agg_backward need for feature width d (may be 0) */
+int64_t cb_graph_workspace_bytes(const cb_graph_t* g, int side, int64_t d);
+
+/*
+ * Fused forward aggregation (replaces, for one layer, GCN.py:238 update_all(copy_src,sum),
+ * GCN.py:242-250 in-degree scale, GCN.py:252-253 bias, GCN.py:127-128 relu and
+ * res_tricks.py:14/23 residual mix, plus GCN.py:205-213 out-degree scale of the NEXT layer's input):
+ *
+ *   z[v,:]    = din^-1/2[v] * sum_{(u->v)} H[u,:] + bias            (rows v owned by the handle)
+ *   r         = act == RELU ? max(z,0) : z
+ *   out[v,:]  = x0 ? (1-alpha) * r + alpha * x0[v,:] : r
+ *   out_scaled[v,:] = dout^-1/2[v] * out[v,:]                        (if out_scaled != NULL)
+ *   mask[v,c] = z[v,c] > 0                                            (if mask != NULL; 1 byte each)
+ *
+ *   H          [N_global, d]: every source row (after the halo exchange on a sliced graph)
+ *   bias       [d] or NULL;  x0, out, out_scaled, mask: [rows, d] local;  any of out/out_scaled may be
+ *              NULL but not both.
+ */
+int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t d, const float* bias,
+                   const float* x0, double alpha, int act, float* out, float* out_scaled,
+                   uint8_t* mask, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Plain gather-reduce over one side of the graph, optional per-row scale of the result:
+ *   out[r,:] = (row_scale ? row_scale[r] : 1) * sum_{j in row r} X[col[j],:]
+ * side = CB_BY_SRC is the autograd transpose of GCN.py:238 (dH[u] = sum_{(u->v)} G[v]).
+ */
+int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t d, const float* row_scale,
+                  float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Backward prologue of cb_agg_forward: from the gradient(s) arriving at the layer output build the
+ * matrix that the transposed aggregation gathers, the bias gradient and the residual gradient.
+ *   dtot = (d_out ? d_out : 0) + (d_out_scaled ? dout^-1/2[v] * d_out_scaled : 0)
+ *   dz   = (x0 was mixed ? (1-alpha) : 1) * dtot * (act == RELU ? m : 1),  m = mask ? mask!=0 : relu_out>0
+ *   G[v,:]   = din^-1/2[v] * dz                         [rows, d]
+ *   d_bias   = sum_v dz[v,:]                            [d]   (if d_bias != NULL; two-stage, fixed order)
+ *   d_x0[v,:] (+)= alpha * dtot                         (if d_x0 != NULL; accumulate_x0 selects += vs =)
+ * workspace: cb_prep_workspace_bytes(rows, d).
+ */
+int64_t cb_prep_workspace_bytes(int64_t rows, int64_t d);
+int cb_agg_backward_prep(const cb_graph_t* g, const float* d_out, const float* d_out_scaled, int64_t d,
+                         const uint8_t* mask, const float* relu_out, int act, int mixed, double alpha,
+                         float* G, float* d_bias, float* d_x0, int accumulate_x0, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+
+/* y[r,:] = s[r] * x[r,:]   (GCN.py:205-213 `feat_src * norm`; also its adjoint) */
+int cb_row_scale(const float* x, const float* s, int64_t rows, int64_t d, float* y, void* stream);
+
+/*
+ * sum of squares of n floats -> out[0] (device), fixed-order two-stage reduction (GCN.py:232
+ * th.norm(self.le) = sqrt of this).  workspace: cb_sumsq_workspace_bytes().
+ */
+int64_t cb_sumsq_workspace_bytes(void);
+int cb_sumsq(const float* x, int64_t n, float* out, void* workspace, int64_t workspace_bytes,
+             void* stream);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
+int64_t cb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLDBREW_B200_H */

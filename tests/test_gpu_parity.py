@@ -1,0 +1,412 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle (same seeded inputs),
+the reference-generated golden fixtures, and size-independent properties at larger sizes.
+
+Tolerances: integer/index work bit-exact; the bare aggregation bit-exact against the in-order C oracle
+(same association, hub chunks included); fp32 model outputs within 1e-4 (north_star) -- observed ~1e-6.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import coldbrew_oracle as O
+from tests.helpers import golden_args, golden_cases, load_golden, load_params
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+LOGIT_TOL = 1e-4          # north_star: fp32 logits within 1e-4 of the reference path
+
+
+def _pkg():
+    from gnn_tail_generalization_b200 import _cabi, graph, ops
+    return _cabi, graph, ops
+
+
+def _multigraph(n, e, seed, skew=True):
+    """Unsorted edge list with duplicates and self loops (DGL multigraph semantics)."""
+    g = torch.Generator().manual_seed(seed)
+    if skew:
+        w = torch.arange(1, n + 1, dtype=torch.float64).pow(-0.9)
+        src = torch.multinomial(w, e, replacement=True, generator=g)
+        dst = torch.multinomial(w, e, replacement=True, generator=g)
+        p = torch.randperm(n, generator=g)
+        src, dst = p[src], p[dst]
+    else:
+        src = torch.randint(0, n, (e,), generator=g)
+        dst = torch.randint(0, n, (e,), generator=g)
+    return torch.stack([src, dst])
+
+
+# ------------------------------------------------------------------------------------------------
+# graph construction: bit-exact indexing
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,e,seed', [(1, 1, 0), (7, 0, 1), (50, 400, 2), (3000, 40000, 3), (100000, 1200000, 4)])
+def test_graph_build_bit_exact(n, e, seed):
+    C, G, _ = _pkg()
+    ei = _multigraph(n, e, seed) if e else torch.zeros(2, 0, dtype=torch.int64)
+    h = G.GraphHandle(ei.to(DEV), n, hub_chunk=64)
+    for side, key, val in ((C.CB_BY_DST, ei[1], ei[0]), (C.CB_BY_SRC, ei[0], ei[1])):
+        rowptr, col, perm = h.csr(side)
+        rp, cl, pm = O.build_csr(key.numpy(), val.numpy(), n)
+        assert np.array_equal(rowptr.cpu().numpy(), rp)
+        assert np.array_equal(col.cpu().numpy().astype(np.int64), cl)
+        assert np.array_equal(perm.cpu().numpy().astype(np.int64), pm)
+    assert np.array_equal(h.in_degrees().cpu().numpy(), np.bincount(ei[1].numpy(), minlength=n))
+    assert np.array_equal(h.out_degrees().cpu().numpy(), np.bincount(ei[0].numpy(), minlength=n))
+    dout, din = O.degree_inv_sqrt(ei, n)
+    assert torch.allclose(h.din_inv_sqrt.cpu(), din, rtol=2e-7, atol=0)
+    assert torch.allclose(h.dout_inv_sqrt.cpu(), dout, rtol=2e-7, atol=0)
+    assert h.has_zero_in_degree == O.has_zero_in_degree(ei, n)
+    assert h.number_of_edges() == e and h.number_of_nodes() == n
+    h.close()
+
+
+def test_graph_build_sliced_matches_whole():
+    C, G, _ = _pkg()
+    n, e = 5000, 60000
+    ei = _multigraph(n, e, 11)
+    rp, cl, pm = O.build_csr(ei[1].numpy(), ei[0].numpy(), n)
+    for lo, hi in ((0, 1250), (1250, 3000), (3000, 5000), (777, 777)):
+        h = G.GraphHandle(ei.to(DEV), n, row_begin=lo, row_end=hi, hub_chunk=32)
+        rowptr, col, perm = h.csr(C.CB_BY_DST)
+        assert np.array_equal(rowptr.cpu().numpy(), rp[lo:hi + 1] - rp[lo])
+        assert np.array_equal(col.cpu().numpy(), cl[rp[lo]:rp[hi]])
+        assert np.array_equal(perm.cpu().numpy(), pm[rp[lo]:rp[hi]])
+        assert h.rows == hi - lo and h.num_edges == rp[hi] - rp[lo]
+
+
+def test_graph_build_rejects_bad_ids():
+    C, G, _ = _pkg()
+    ei = torch.tensor([[0, 1, 5], [1, 0, 2]])
+    with pytest.raises(C.ColdBrewError) as err:
+        G.GraphHandle(ei.to(DEV), 5)
+    assert err.value.code == -2
+    with pytest.raises(C.ColdBrewError):
+        G.GraphHandle(torch.tensor([[0, -1], [1, 0]]).to(DEV), 5)
+
+
+# ------------------------------------------------------------------------------------------------
+# the bare aggregation: bit-exact against the in-order C oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('d', [1, 2, 3, 4, 7, 8, 10, 16, 20, 40, 64, 100, 128, 130, 256, 512, 700])
+def test_aggregate_bit_exact_all_widths(d):
+    C, G, ops = _pkg()
+    n, e, hub = 2000, 30000, 48
+    ei = _multigraph(n, e, 100 + d)
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(d))
+    h = G.GraphHandle(ei.to(DEV), n, hub_chunk=hub)
+    assert h.num_hub_chunks[0] > 0 and h.num_hub_chunks[1] > 0
+    for side, key, val in ((C.CB_BY_DST, ei[1], ei[0]), (C.CB_BY_SRC, ei[0], ei[1])):
+        rp, cl, _ = O.build_csr(key.numpy(), val.numpy(), n)
+        want = O.aggregate_sum_csr_ordered(x.numpy(), rp, cl, hub_chunk=hub)
+        got = ops.agg_gather_raw(h, side, x.to(DEV)).cpu().numpy()
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize('n,e,d,hub', [(1, 1, 8, 0), (10, 0, 16, 0), (300, 300 * 40, 64, 16), (200000, 2400000, 256, 0),
+                                        (50000, 900000, 128, 128)])
+def test_aggregate_bit_exact_shapes(n, e, d, hub):
+    C, G, ops = _pkg()
+    ei = _multigraph(n, e, n + e) if e else torch.zeros(2, 0, dtype=torch.int64)
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(5))
+    h = G.GraphHandle(ei.to(DEV), n, hub_chunk=hub)
+    rp, cl, _ = O.build_csr(ei[1].numpy(), ei[0].numpy(), n)
+    want = O.aggregate_sum_csr_ordered(x.numpy(), rp, cl, hub_chunk=h.hub_chunk)
+    got = ops.agg_gather_raw(h, C.CB_BY_DST, x.to(DEV)).cpu().numpy()
+    assert np.array_equal(got, want)
+    # run-to-run determinism (no atomics anywhere on the path)
+    assert torch.equal(ops.agg_gather_raw(h, C.CB_BY_DST, x.to(DEV)).cpu(), torch.from_numpy(got))
+
+
+def test_isolated_rows_get_bias_and_zero():
+    C, G, ops = _pkg()
+    ei = torch.tensor([[0, 1], [1, 1]])                      # node 0 and 2 have no in-edge
+    h = G.GraphHandle(ei.to(DEV), 3)
+    assert h.has_zero_in_degree
+    x = torch.arange(12.).view(3, 4).to(DEV)
+    b = torch.tensor([1., 2., 3., 4.]).to(DEV)
+    out, _, _ = ops.agg_forward_raw(h, x, bias=b)
+    assert torch.equal(out[0], b) and torch.equal(out[2], b)
+    want1 = (x[0] + x[1]) * (2 ** -0.5) + b
+    assert torch.allclose(out[1], want1, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused epilogue and the backward kernels against the oracle's op-by-op arithmetic
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('d', [5, 16, 64, 256])
+@pytest.mark.parametrize('relu,mix', [(False, False), (True, False), (True, True), (False, True)])
+def test_fused_forward_matches_oracle_chain(d, relu, mix):
+    C, G, ops = _pkg()
+    n, e = 1500, 20000
+    ei = O.canonicalize_planetoid(_multigraph(n, e, d), n)
+    gen = torch.Generator().manual_seed(d)
+    hmat, bias, x0 = torch.randn(n, d, generator=gen), torch.randn(d, generator=gen), torch.randn(n, d, generator=gen)
+    alpha = 0.1
+    h = G.GraphHandle(ei.to(DEV), n)
+    out, out_s, mask = ops.agg_forward_raw(h, hmat.to(DEV), bias.to(DEV), x0.to(DEV) if mix else None, alpha, relu,
+                                           True, True, True)
+    dout_is, din_is = O.degree_inv_sqrt(ei, n)
+    z = O.aggregate_sum(hmat, ei, n) * din_is[:, None] + bias
+    r = F.relu(z) if relu else z
+    want = (1 - alpha) * r + alpha * x0 if mix else r
+    # the aggregation is bit-exact and the epilogue rounds like the op-by-op chain; the only slack is
+    # the last bit of degree^-1/2 (computed in double on the device)
+    assert torch.allclose(out.cpu(), want, rtol=3e-7, atol=1e-6)
+    assert torch.allclose(out_s.cpu(), want * dout_is[:, None], rtol=5e-7, atol=1e-6)
+    zc = z.abs() > 1e-5
+    assert torch.equal(mask.cpu().bool()[zc], (z > 0)[zc])
+
+
+@pytest.mark.parametrize('d', [6, 32, 256])
+@pytest.mark.parametrize('relu,mix', [(False, False), (True, False), (True, True)])
+def test_fused_aggregate_autograd_matches_oracle(d, relu, mix):
+    C, G, ops = _pkg()
+    n, e, alpha = 800, 9000, 0.2
+    ei = O.canonicalize_planetoid(_multigraph(n, e, 7 * d), n)
+    gen = torch.Generator().manual_seed(d)
+    base = [torch.randn(n, d, generator=gen), torch.randn(d, generator=gen), torch.randn(n, d, generator=gen)]
+    wout, wsc = torch.randn(n, d, generator=gen), torch.randn(n, d, generator=gen)
+    dout_is, din_is = O.degree_inv_sqrt(ei, n)
+
+    def oracle(hm, b, x0):
+        z = O.aggregate_sum(hm, ei, n) * din_is[:, None] + b
+        r = F.relu(z) if relu else z
+        o = (1 - alpha) * r + alpha * x0 if mix else r
+        return o, o * dout_is[:, None]
+
+    cpu = [t.clone().requires_grad_() for t in base]
+    o, os_ = oracle(*cpu)
+    ((o * wout).sum() + (os_ * wsc).sum()).backward()
+
+    h = G.GraphHandle(ei.to(DEV), n)
+    gpu = [t.clone().to(DEV).requires_grad_() for t in base]
+    o2, os2 = ops.fused_aggregate(gpu[0], h, gpu[1], gpu[2] if mix else None, alpha, relu, True, True)
+    ((o2 * wout.to(DEV)).sum() + (os2 * wsc.to(DEV)).sum()).backward()
+    assert torch.allclose(o2.detach().cpu(), o.detach(), rtol=1e-6, atol=1e-6)
+    for a, b_, name in zip(gpu, cpu, 'H bias x0'.split()):
+        if name == 'x0' and not mix:
+            assert a.grad is None
+            continue
+        scale = float(b_.grad.abs().max()) + 1e-12
+        assert float((a.grad.cpu() - b_.grad).abs().max()) <= 2e-6 * scale + 1e-6, name
+
+    # only the scaled output consumed (the fused layer-to-layer hand-off)
+    gpu = [t.clone().to(DEV).requires_grad_() for t in base]
+    _, os3 = ops.fused_aggregate(gpu[0], h, gpu[1], gpu[2] if mix else None, alpha, relu, False, True)
+    (os3 * wsc.to(DEV)).sum().backward()
+    cpu = [t.clone().requires_grad_() for t in base]
+    (oracle(*cpu)[1] * wsc).sum().backward()
+    assert torch.allclose(gpu[0].grad.cpu(), cpu[0].grad, rtol=1e-5, atol=1e-5)
+
+
+def test_transpose_identity():
+    """<A x, y> == <x, A^T y>: the backward gather is the exact transpose of the forward one."""
+    C, G, ops = _pkg()
+    n, e, d = 20000, 300000, 64
+    ei = _multigraph(n, e, 77)
+    h = G.GraphHandle(ei.to(DEV), n)
+    gen = torch.Generator().manual_seed(1)
+    x, y = torch.randn(n, d, generator=gen).to(DEV), torch.randn(n, d, generator=gen).to(DEV)
+    lhs = (ops.agg_gather_raw(h, C.CB_BY_DST, x).double() * y.double()).sum()
+    rhs = (x.double() * ops.agg_gather_raw(h, C.CB_BY_SRC, y).double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-6 * abs(float(lhs))
+
+
+def test_row_scale_and_frobenius():
+    C, G, ops = _pkg()
+    gen = torch.Generator().manual_seed(3)
+    for rows, d in ((1, 1), (33, 7), (1000, 256), (4097, 12)):
+        x, s = torch.randn(rows, d, generator=gen), torch.rand(rows, generator=gen)
+        assert torch.equal(ops.row_scale_raw(x.to(DEV), s.to(DEV)).cpu(), x * s[:, None])
+        got = float(ops.frob_norm(x.to(DEV)))
+        assert got == pytest.approx(float(torch.norm(x.double())), rel=2e-6)
+    e = torch.randn(500, 64, generator=gen)
+    a, b = e.clone().to(DEV).requires_grad_(), e.clone().requires_grad_()
+    (3 * ops.frob_norm(a)).backward()
+    (3 * torch.norm(b)).backward()
+    assert torch.allclose(a.grad.cpu(), b.grad, rtol=1e-5, atol=1e-7)
+    z = torch.zeros(4, 4, device=DEV, requires_grad=True)
+    ops.frob_norm(z).backward()
+    assert torch.equal(z.grad, torch.zeros_like(z))
+
+
+# ------------------------------------------------------------------------------------------------
+# whole model against the reference-generated fixtures and the oracle
+# ------------------------------------------------------------------------------------------------
+def _teacher(a):
+    from gnn_tail_generalization_b200.GNN_model.GNN_normalizations import TeacherGNN
+    return TeacherGNN(a, None)
+
+
+def test_kat_toy_through_gcnconv():
+    from gnn_tail_generalization_b200.GNN_model.GCN import GCNConv
+    _, G, _ = _pkg()
+    z = load_golden('kat_toy')
+    ei = torch.from_numpy(z['edge_index'])
+    g = G.GraphHandle(ei.to(DEV), 3)
+    from types import SimpleNamespace
+    for se in (False, True):
+        conv = GCNConv(3, 3, args=SimpleNamespace(N_nodes=3), whetherHasSE=se).to(DEV)
+        with torch.no_grad():
+            conv.weight.copy_(torch.eye(3)); conv.bias.zero_()
+            if se:
+                conv.le.copy_(torch.arange(9.).view(3, 3) / 10)
+        rst, reg = conv(g, torch.eye(3, device=DEV))
+        assert np.allclose(rst.detach().cpu().numpy(), z[f'rst_se{int(se)}'], rtol=1e-6, atol=1e-7)
+        if se:
+            assert float(reg) == pytest.approx(float(z['se_reg']), rel=1e-6)
+        else:
+            assert reg is None
+
+
+@pytest.mark.parametrize('name', golden_cases())
+def test_model_matches_reference_fixture(name):
+    z = load_golden(name)
+    a = golden_args(z, O.make_args)
+    a.device = DEV
+    model = _teacher(a)
+    load_params(model, z)
+    model.to(DEV)
+    model.eval() if name.startswith('exact_batchnorm') else model.train()
+    x, ei = torch.from_numpy(z['x']).to(DEV), torch.from_numpy(z['edge_index']).to(DEV)
+    y, mask = torch.from_numpy(z['y']).to(DEV), torch.from_numpy(z['train_mask']).to(DEV)
+    res = model.get_3_embs(x, ei, mask)
+    got = res.emb4classi_full.detach().cpu().numpy()
+    assert np.abs(got - z['logits']).max() <= LOGIT_TOL
+    assert np.allclose(got, z['logits'], rtol=2e-5, atol=2e-6)            # what is actually observed
+    if np.isnan(z['se_reg_all']):
+        assert model.se_reg_all is None
+    else:
+        assert float(model.se_reg_all) == pytest.approx(float(z['se_reg_all']), rel=1e-6)
+    loss = F.nll_loss(F.log_softmax(res.emb4classi, 1), y[mask])
+    if int(z['reg_in_loss']):
+        loss = loss + 0.5 * model.se_reg_all
+    assert float(loss) == pytest.approx(float(z['loss']), rel=1e-5)
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    want = {k[5:]: v for k, v in z.items() if k.startswith('grad/')}
+    assert set(grads) == set(want)
+    for k, v in want.items():
+        g = grads[k].cpu().numpy()
+        assert np.abs(g - v).max() <= 1e-5 * max(1.0, np.abs(v).max()), k
+    xin = x if a.dim_learnable_input == 0 else model.embs
+    les = model.model.model.collect_SE(xin, ei)
+    assert np.allclose(les.cpu().numpy(), z['les'], rtol=2e-5, atol=2e-6)
+    assert model.model.model.get_se_dim(xin, ei) == z['les'].shape[1]
+
+
+CONFIG_SHAPES = {
+    # BASELINE.json configs at their real shapes, shape-matched synthetic data (datasets are not on disk)
+    'cfg1_cora_nores_se000': dict(n=2708, und=5278, F=1433, H=64, C=7, trick='NoResNodeNorm', se='000', ds='Cora'),
+    'cfg2_pubmed_initial_se111': dict(n=19717, und=44324, F=500, H=256, C=3, trick='InitialBatchNorm', se='111',
+                                      ds='Pubmed'),
+    'cfg3_arxiv_initial_se100': dict(n=169343, und=1157799, F=128, H=256, C=40, trick='InitialBatchNorm', se='100',
+                                     ds='ogbn-arxiv'),
+}
+
+
+@pytest.mark.parametrize('cfg', sorted(CONFIG_SHAPES))
+def test_config_shapes_match_oracle(cfg):
+    c = CONFIG_SHAPES[cfg]
+    torch.manual_seed(3)
+    ei = O.powerlaw_graph(c['n'], c['und'], seed=0)
+    kw = dict(type_trick=c['trick'], whetherHasSE=c['se'], num_layers=2, dim_hidden=c['H'], num_feats=c['F'],
+              num_classes=c['C'], N_nodes=c['n'], dataset=c['ds'], res_alpha=0.1)
+    ref = O.OracleTeacherGNN(O.make_args(**kw), None)
+    a = O.make_args(**kw)
+    a.device = DEV
+    model = _teacher(a)
+    model.load_state_dict(ref.state_dict(), strict=True)
+    model.to(DEV)
+    x = torch.randn(c['n'], c['F'], generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, c['C'], (c['n'],), generator=torch.Generator().manual_seed(2))
+    mask = torch.zeros(c['n'], dtype=torch.bool)
+    mask[: c['n'] // 10] = True
+    for m in (ref, model):
+        m.train()
+    lr = O.teacher_loss(ref, x, ei, y, mask, 0.5)
+    lr.backward()
+    res = model.get_3_embs(x.to(DEV), ei.to(DEV), mask.to(DEV))
+    lg = F.nll_loss(F.log_softmax(res.emb4classi, 1), y.to(DEV)[mask.to(DEV)])
+    if model.se_reg_all is not None:
+        lg = lg + 0.5 * model.se_reg_all
+    lg.backward()
+    want = ref.get_3_embs(x, ei, mask).emb4classi_full.detach()
+    got = res.emb4classi_full.detach().cpu()
+    assert float((got - want).abs().max()) <= LOGIT_TOL
+    assert float(lg) == pytest.approx(float(lr), rel=1e-5)
+    rg = dict(ref.named_parameters())
+    for k, p in model.named_parameters():
+        if rg[k].grad is None:
+            assert p.grad is None, k
+            continue
+        scale = max(1e-6, float(rg[k].grad.abs().max()))
+        assert float((p.grad.cpu() - rg[k].grad).abs().max()) <= 2e-4 * scale, k
+
+
+def test_zero_in_degree_raises_dglerror():
+    from gnn_tail_generalization_b200 import DGLError
+    a = O.make_args(N_nodes=3, num_feats=4, dim_hidden=4, num_classes=2)
+    a.device = DEV
+    model = _teacher(a).to(DEV)
+    ei = torch.tensor([[0, 1], [1, 1]]).to(DEV)
+    with pytest.raises(DGLError):
+        model(torch.randn(3, 4, device=DEV), ei)
+    for conv in model.model.model.layers_GCN:
+        conv.set_allow_zero_in_degree(True)
+    model.model.model.dglgraph = None
+    assert model(torch.randn(3, 4, device=DEV), ei).shape == (3, 2)
+
+
+def test_training_dropout_path_runs_and_eval_is_deterministic():
+    n = 400
+    ei = O.powerlaw_graph(n, 1500, seed=4)
+    a = O.make_args(N_nodes=n, num_feats=32, dim_hidden=64, num_classes=5, type_trick='InitialBatchNorm',
+                    whetherHasSE='111', dropout=0.5)
+    a.device = DEV
+    model = _teacher(a).to(DEV)
+    x = torch.randn(n, 32, device=DEV)
+    model.train()
+    out = model(x, ei.to(DEV))
+    (out.sum() + model.se_reg_all).backward()
+    assert all(p.grad is not None for k, p in model.named_parameters() if 'layers_norm' not in k)
+    model.eval()
+    with torch.no_grad():
+        assert torch.equal(model(x, ei.to(DEV)), model(x, ei.to(DEV)))
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at a size the oracle would not finish quickly
+# ------------------------------------------------------------------------------------------------
+def test_large_graph_properties():
+    C, G, ops = _pkg()
+    n, und, d = 1_000_000, 5_000_000, 256
+    ei = O.powerlaw_graph(n, und, seed=0).to(DEV)
+    h = G.GraphHandle(ei, n)
+    assert h.num_edges == 2 * und + n and not h.has_zero_in_degree
+    rowptr, col, perm = h.csr(C.CB_BY_DST)
+    # sortedness + stability: keys nondecreasing, edge ids increasing inside a row
+    dst_sorted = ei[1][perm.long()]
+    assert bool((dst_sorted[1:] >= dst_sorted[:-1]).all())
+    same = dst_sorted[1:] == dst_sorted[:-1]
+    assert bool((perm[1:][same] > perm[:-1][same]).all())
+    assert torch.equal(col.long(), ei[0][perm.long()])
+    assert torch.equal(rowptr[1:] - rowptr[:-1], torch.bincount(ei[1], minlength=n))
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(n, d, device=DEV, generator=gen)
+    y = torch.randn(n, d, device=DEV, generator=gen)
+    ax, ay = ops.agg_gather_raw(h, C.CB_BY_DST, x), ops.agg_gather_raw(h, C.CB_BY_DST, y)
+    # checksum: column sums of A x equal out-degree-weighted column sums of x
+    lhs = ax.double().sum(0)
+    rhs = (x.double() * h.out_degrees().double()[:, None]).sum(0)
+    assert torch.allclose(lhs, rhs, rtol=1e-6, atol=1e-3)
+    # linearity
+    axy = ops.agg_gather_raw(h, C.CB_BY_DST, x + 2 * y)
+    assert torch.allclose(axy, ax + 2 * ay, rtol=1e-4, atol=1e-3)
+    # symmetric graph: by-source gather == by-destination gather up to summation order
+    assert torch.allclose(ops.agg_gather_raw(h, C.CB_BY_SRC, x), ax, rtol=1e-4, atol=1e-3)
+    # against torch's own scatter on the GPU
+    want = torch.zeros_like(x).index_add_(0, ei[1], x[ei[0]])
+    assert torch.allclose(ax, want, rtol=1e-4, atol=1e-3)

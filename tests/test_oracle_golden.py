@@ -78,7 +78,7 @@ def test_csr_stable_and_c_oracle_bit_exact():
     for r in np.random.default_rng(0).integers(0, n, 50):
         seg = perm[rowptr[r]:rowptr[r + 1]]
         assert np.all(np.diff(seg) > 0)
-    h = torch.randn(n, 40)
+    h = torch.randn(n, 40, generator=torch.Generator().manual_seed(0))
     a = O.aggregate_sum_csr_ordered(h.numpy(), rowptr, cols, threads=1)
     b = O.aggregate_sum_csr_ordered(h.numpy(), rowptr, cols, threads=4)
     c = O.aggregate_sum(h, ei, n).numpy()
@@ -87,7 +87,7 @@ def test_csr_stable_and_c_oracle_bit_exact():
     d = O.aggregate_sum_csr_ordered(h.numpy(), rowptr, cols, hub_chunk=64)
     deg = np.diff(rowptr)
     assert np.array_equal(a[deg <= 64], d[deg <= 64])
-    np.testing.assert_allclose(a, d, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(a, d, rtol=1e-5, atol=2e-4)   # hub rows: a few thousand terms, re-associated
 
 
 def test_powerlaw_graph_is_canonical():

@@ -17,7 +17,7 @@ class _DevArray:
     """Zero-copy view of library-owned device memory through __cuda_array_interface__."""
 
     def __init__(self, addr, n, typestr):
-        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (addr, True), 'version': 2}
+        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (addr, False), 'version': 2}
 
 
 class GraphHandle:

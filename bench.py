@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the TeacherGNN aggregation hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] --steps K --warmup W # CPU restatement of the reference path
+
+A "step" is one full-graph training step of the 2-layer GCN teacher (Initial topology:
+Linear F->H, 2 x GCNConv H->H with the Initial residual, Linear H->C): forward, NLL loss on the train
+rows, backward, Adam step.  It aggregates 2*L*E edges (L forward + L transposed aggregations).
+N=1 workload = BASELINE.json configs[3]: synthetic power-law graph, 10M nodes / 100M directed edges,
+256-dim fp32.  N>1 = the same graph node-sliced over N GPUs ("strong" scaling), NCCL all-gather of the
+row blocks per aggregation.
+
+Prints ONE JSON line (rank 0).  Extra keys beside the driver contract: roofline (forward aggregation
+kernel), roofline_kernels (every C-ABI kernel), cpu_baseline, e2e, clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'edges-aggregated/sec (2-layer GCN fwd+bwd)'
+UNIT = 'edges/s'
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument('--gpus', type=int, default=1)
+    p.add_argument('--steps', type=int, default=10)
+    p.add_argument('--warmup', type=int, default=3)
+    p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    p.add_argument('--nodes', type=int, default=10_000_000)
+    p.add_argument('--edges', type=int, default=100_000_000, help='directed edges incl. one self loop per node')
+    p.add_argument('--dim', type=int, default=256)
+    p.add_argument('--classes', type=int, default=64)
+    p.add_argument('--layers', type=int, default=2)
+    p.add_argument('--se', default='000', help='whetherHasSE flags (BASELINE configs[3] has no SE)')
+    p.add_argument('--no-e2e', action='store_true')
+    p.add_argument('--no-cpu-baseline', action='store_true')
+    p.add_argument('--cpu-nodes', type=int, default=1_000_000, help='sample size of the CPU baseline / reference arm')
+    p.add_argument('--cpu-steps', type=int, default=2)
+    return p.parse_args()
+
+
+def workload_name(a):
+    return (f'synthetic power-law (gamma=2.5) N={a.nodes} E={a.edges} d={a.dim} fp32, {a.layers}-layer GCN '
+            f'(Initial topology, C={a.classes}, SE={a.se}), fwd+bwd+Adam')
+
+
+def model_args(a, n_nodes, device):
+    from types import SimpleNamespace
+    m = SimpleNamespace(type_trick='Initial', type_model='GCN', num_layers=a.layers, dim_hidden=a.dim,
+                        num_feats=a.dim, num_classes=a.classes, dropout=0.0, res_alpha=0.1, layer_agg='concat',
+                        transductive=True, N_nodes=n_nodes, device=device, dataset='synthetic',
+                        dim_learnable_input=0, lamda=0.5, num_groups=None, skip_weight=None, graph_dropout=0.0,
+                        layerwise_dropout=False, dim_commonEmb=a.classes)
+    m.TeacherGNN = SimpleNamespace(whetherHasSE=[int(c) for c in a.se], change_to_featureless=False)
+    return m
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML), runs during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    BAD = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20}
+    NOTE = {'sw_power_cap': 0x4}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        return False
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm / cpu_baseline leg: the oracle on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(a, steps, warmup):
+    """Times the CPU restatement of the reference path (oracle/, DGL-style OpenMP CSR aggregation,
+    torch CPU GEMMs) on a bounded sample of the workload: same generator, degree law, d, L and topology,
+    fewer nodes (average degree kept).  Returns (edges_per_s, ms_per_step, sample description, threads)."""
+    import torch
+    from oracle import coldbrew_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n = min(a.cpu_nodes, a.nodes)
+    e_dir = int(round(a.edges * (n / a.nodes)))
+    und = max(1, (e_dir - n) // 2)
+    ei = O.powerlaw_graph(n, und, seed=0)
+    E = ei.shape[1]
+    margs = O.make_args(type_trick='Initial', num_layers=a.layers, dim_hidden=a.dim, num_feats=a.dim,
+                        num_classes=a.classes, N_nodes=n, whetherHasSE=a.se, dataset='Cora')
+    torch.manual_seed(3)
+    model = O.OracleTeacherGNN(margs, None)
+    model.model.model.plan = O.CsrPlan(ei, n)
+    x = torch.randn(n, a.dim, generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, a.classes, (n,), generator=torch.Generator().manual_seed(2))
+    idx = torch.arange(n // 10)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    model.train()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = O.teacher_loss(model, x, ei, y, idx, 0.5)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    sample = (f'N={n} E={E} d={a.dim} L={a.layers} (1/{max(1, a.nodes // n)} of the workload, same degree law), '
+              f'{steps} steps after {warmup} warm-up, OpenMP CSR aggregation + torch CPU GEMM')
+    return 2 * a.layers * E / dt, dt * 1e3, sample, min(threads, O.c_oracle_threads())
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, a.steps)
+    warm = max(1, min(a.warmup, 3))
+    # bounded sample: ~11 us of host time per node per step on 8 cores; keep the whole run near 2 minutes
+    a.cpu_nodes = int(max(50_000, min(a.cpu_nodes, 120.0 / ((steps + warm) * 11e-6))))
+    val, ms, sample, threads = cpu_reference_run(a, steps, warm)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': steps,
+            'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(a), 'timed_on': 'bounded sample, see cpu_baseline.sample'},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from gnn_tail_generalization_b200 import _cabi, dist as cbdist, ops, synth
+    from gnn_tail_generalization_b200.GNN_model.GNN_normalizations import TeacherGNN
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device; there is no CPU fallback for this path '
+                         '(use --impl reference for the CPU restatement)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_kind = 'measured' if 'hbm_gbs' in peaks else 'fallback'
+
+    # ---- workload (generated on the device, identical on every rank) ---------------------------
+    N, d, L = a.nodes, a.dim, a.layers
+    und = max(1, (a.edges - N) // 2)
+    ei = synth.powerlaw_graph(N, und, seed=0, device=dev)
+    E = ei.shape[1]
+    graph = cbdist.SlicedGraph(ei, N, rank, world)
+    del ei
+    torch.cuda.empty_cache()
+    lo, hi = graph.row_begin, graph.row_end
+    rows = hi - lo
+    x = synth.features(N, d, seed=1, device=dev)[lo:hi].clone() if world > 1 else synth.features(N, d, 1, dev)
+    y = synth.labels(N, a.classes, seed=2, device=dev)[lo:hi]
+    n_train = N // 10
+    idx = torch.arange(max(0, min(n_train, hi) - lo), device=dev)       # train rows = first 10% of the nodes
+    torch.manual_seed(3)
+    model = TeacherGNN(model_args(a, rows, str(dev)), None).to(dev)     # same seed => same dense weights on all ranks
+    cbdist.attach_graph(model, graph)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    se_coef = 0.5
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        res = model.get_3_embs(x, None, idx)
+        loss = F.nll_loss(F.log_softmax(res.emb4classi, 1), y[idx], reduction='sum') / n_train
+        if model.se_reg_all is not None:
+            loss = loss + se_coef * model.se_reg_all
+        loss.backward()
+        cbdist.allreduce_dense_grads(model, world)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            fn()
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(max(3, a.warmup)):
+        step()
+    launches0, exch0 = _cabi.launch_count(), graph.exchanged_bytes
+    with ClockSampler(local) as clk:
+        ms_step = timed(step, a.steps)
+    launches = _cabi.launch_count() - launches0
+    exch_per_step = (graph.exchanged_bytes - exch0) // a.steps
+    value = 2 * L * E / (ms_step * 1e-3)
+
+    # ---- per-kernel probe: CUDA events around every C-ABI launch, over a second timed region ----
+    sink = []
+    ops.set_timing_sink(sink)
+    probe_steps = min(a.steps, 5)
+    ms_probe = timed(step, probe_steps)
+    ops.set_timing_sink(None)
+    torch.cuda.synchronize()
+    per = {}
+    for name, e0, e1, nbytes in sink:
+        r = per.setdefault(name, {'launches': 0, 'ms': 0.0, 'bytes': 0})
+        r['launches'] += 1
+        r['ms'] += e0.elapsed_time(e1)
+        r['bytes'] += nbytes
+    kernels = {}
+    for name, r in per.items():
+        avg_ms = r['ms'] / r['launches']
+        gbs = r['bytes'] / r['launches'] / (avg_ms * 1e-3) / 1e9
+        kernels[name] = {'launches_per_step': r['launches'] / probe_steps, 'avg_ms': round(avg_ms, 4),
+                         'alg_bytes': r['bytes'] // r['launches'], 'achieved_gbs': round(gbs, 1),
+                         'frac': round(gbs / hbm_peak, 4), 'share_of_step': round(r['ms'] / probe_steps / ms_probe, 4)}
+    dom = kernels.get('agg_forward', {})
+    roofline = {'bound': 'hbm', 'kernel': 'k_agg (cb_agg_forward)', 'achieved': dom.get('achieved_gbs'),
+                'peak': hbm_peak, 'peak_source': f'{peak_kind} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)',
+                'unit': 'GB/s', 'frac': dom.get('frac'), 'traffic': None,
+                'avg_launch_ms': dom.get('avg_ms'), 'alg_bytes_per_launch': dom.get('alg_bytes')}
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+        roofline['traffic'] = tr.get('k_agg_forward_dram_bytes_per_launch')
+        roofline['traffic_source'] = tr.get('source')
+    except Exception:
+        pass
+
+    # ---- end to end: host features in pinned memory -> device every step, loss read back ---------
+    e2e = None
+    if not a.no_e2e:
+        x_host = torch.empty((rows, d), dtype=torch.float32, pin_memory=True)
+        x_host.copy_(x)
+        result = torch.zeros(1, dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            x.copy_(x_host, non_blocking=True)
+            loss = step()
+            result.copy_(loss.detach().reshape(1), non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, max(2, min(a.steps, 5)))
+        e2e = {'value': 2 * L * E / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': rows * d * 4 * world,
+               'd2h_bytes_per_step': 4 * world, 'ms_per_step': ms_e2e,
+               'what': 'features copied from pinned host memory each step, loss read back to the host'}
+        del x_host
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        del model, opt
+        torch.cuda.empty_cache()
+        v, ms_cpu, sample, threads = cpu_reference_run(a, a.cpu_steps, 1)
+        cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample, 'ms_per_step': ms_cpu}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps,
+                'warmup': max(3, a.warmup), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': workload_name(a), 'edges': E, 'edges_aggregated_per_step': 2 * L * E,
+                           'l2': 'inputs exceed L2 (feature matrix %.1f GB vs 126 MB)' % (N * d * 4 / 1e9),
+                           'parallelism': f'node-slice x{world}' if world > 1 else 'single GPU',
+                           'gemm': 'cuBLAS fp32 (no TF32)'},
+                'roofline': roofline, 'roofline_kernels': kernels, 'cpu_baseline': cpu, 'e2e': e2e,
+                'clocks': clk.summary(), 'gpu_launches': launches,
+                'exchange_bytes_per_step_per_rank': exch_per_step}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == '__main__':
+    main()

@@ -83,11 +83,11 @@ class GCNConv(nn.Module):
                            'weight parameter. Please create the module with flag weight=False.')
         return weight if weight is not None else self.weight
 
-    def _transform(self, feat_scaled, weight):
+    def _transform(self, graph, feat_scaled, weight):
         """(already out-degree-scaled X) W + E, and the SE regulariser (GCN.py:223-236)."""
         if self.whetherHasSE:
             h = th.addmm(self.le, feat_scaled, weight) if weight is not None else feat_scaled + self.le
-            return h, _ops.frob_norm(self.le)
+            return h, _ops.frob_norm(self.le, graph)
         return (th.matmul(feat_scaled, weight) if weight is not None else feat_scaled), None
 
     def fused(self, graph, feat, prescaled=False, relu=False, x0=None, alpha=0.0, want_out=True,
@@ -102,7 +102,7 @@ class GCNConv(nn.Module):
         assert self._norm == 'both'
         weight = self._check(graph, weight)
         xs = feat if prescaled else _ops.row_scale(feat, graph.dout_inv_sqrt)
-        h, se_reg = self._transform(xs, weight)
+        h, se_reg = self._transform(graph, xs, weight)
         out, out_scaled = _ops.fused_aggregate(h, graph, self.bias, x0, alpha, relu, want_out, want_scaled)
         return out, out_scaled, se_reg
 
@@ -118,7 +118,7 @@ class GCNConv(nn.Module):
             x = feat
             if self._norm == 'left':
                 x = x * (1.0 / graph.out_degrees().float().clamp(min=1)).unsqueeze(-1)
-            h, se_reg = self._transform(x, weight)
+            h, se_reg = self._transform(graph, x, weight)
             rst = _ops.copy_sum(h, graph)
             if self._norm == 'right':
                 rst = rst * (1.0 / graph.in_degrees().float().clamp(min=1)).unsqueeze(-1)

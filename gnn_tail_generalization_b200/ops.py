@@ -8,6 +8,48 @@ import torch
 from . import _cabi as C
 
 
+# ---------------------------------------------------------------------------------------------
+# optional per-launch timing (bench.py's roofline probe): CUDA events on the launching stream
+# ---------------------------------------------------------------------------------------------
+_timing_sink = None
+
+
+def set_timing_sink(sink):
+    """``sink`` is a list that receives (name, start_event, end_event, algorithmic_bytes) per kernel
+    call, or None to switch the probe off.  Events are recorded on the stream the kernel runs on."""
+    global _timing_sink
+    _timing_sink = sink
+
+
+class _Timed:
+    def __init__(self, name, alg_bytes, device):
+        self.name, self.bytes, self.device = name, alg_bytes, device
+
+    def __enter__(self):
+        if _timing_sink is not None:
+            self.t0 = torch.cuda.Event(enable_timing=True)
+            self.t1 = torch.cuda.Event(enable_timing=True)
+            self.t0.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if _timing_sink is not None and exc[0] is None:
+            self.t1.record(torch.cuda.current_stream(self.device))
+            _timing_sink.append((self.name, self.t0, self.t1, self.bytes))
+        return False
+
+
+def gather_alg_bytes(graph, side, d, n_out_mats=1, n_in_mats=1, mask=False, scales=1):
+    """Algorithmic bytes of one aggregation launch: every feature matrix once, the CSR once."""
+    e = graph.num_edges if side == C.CB_BY_DST else graph.num_edges_by_src
+    b = graph.num_nodes * d * 4                       # gathered matrix, read once
+    b += (n_in_mats - 1) * graph.rows * d * 4         # x0
+    b += n_out_mats * graph.rows * d * 4              # outputs
+    b += graph.rows * d if mask else 0
+    b += e * 4 + (graph.rows + 1) * 8 + scales * graph.rows * 4 + d * 4
+    return b
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -38,7 +80,9 @@ def agg_forward_raw(graph, H, bias=None, x0=None, alpha=0.0, relu=False, want_ou
     out_scaled = torch.empty((graph.rows, d), dtype=torch.float32, device=H.device) if want_scaled else None
     mask = torch.empty((graph.rows, d), dtype=torch.uint8, device=H.device) if want_mask else None
     ws, ws_bytes = graph.workspace(C.CB_BY_DST, d)
-    with torch.cuda.device(H.device):
+    alg = gather_alg_bytes(graph, C.CB_BY_DST, d, int(want_out) + int(want_scaled), 1 + int(x0 is not None),
+                           want_mask, 1 + int(want_scaled))
+    with torch.cuda.device(H.device), _Timed('agg_forward', alg, H.device):
         C.call('cb_agg_forward', graph.handle, C.ptr(H), d, C.ptr(bias), C.ptr(x0), float(alpha),
                C.CB_ACT_RELU if relu else C.CB_ACT_NONE, C.ptr(out), C.ptr(out_scaled), C.ptr(mask),
                C.ptr(ws), ws_bytes, C.stream_ptr(H.device))
@@ -54,7 +98,9 @@ def agg_gather_raw(graph, side, X, row_scale=None):
         raise ValueError(f'X has {X.shape[0]} rows, the graph has {graph.num_nodes} nodes')
     out = torch.empty((graph.rows, d), dtype=torch.float32, device=X.device)
     ws, ws_bytes = graph.workspace(side, d)
-    with torch.cuda.device(X.device):
+    alg = gather_alg_bytes(graph, side, d, 1, 1, False, int(row_scale is not None))
+    with torch.cuda.device(X.device), _Timed('agg_gather_dst' if side == C.CB_BY_DST else 'agg_gather_src', alg,
+                                             X.device):
         C.call('cb_agg_gather', graph.handle, side, C.ptr(X), d, C.ptr(row_scale), C.ptr(out), C.ptr(ws),
                ws_bytes, C.stream_ptr(X.device))
     return out
@@ -70,7 +116,9 @@ def backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, relu, mixed, a
     d_x0 = torch.empty((rows, d), dtype=torch.float32, device=ref.device) if want_x0 else None
     ws_bytes = int(C.lib().cb_prep_workspace_bytes(rows, d)) if want_bias else 0
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ref.device) if ws_bytes else None
-    with torch.cuda.device(ref.device):
+    mats = int(d_out is not None) + int(d_out_scaled is not None) + 1 + int(want_x0) + int(relu_out is not None)
+    alg = mats * rows * d * 4 + (rows * d if mask is not None else 0) + 2 * rows * 4
+    with torch.cuda.device(ref.device), _Timed('backward_prep', alg, ref.device):
         C.call('cb_agg_backward_prep', graph.handle, C.ptr(d_out), C.ptr(d_out_scaled), d, C.ptr(mask),
                C.ptr(relu_out), C.CB_ACT_RELU if relu else C.CB_ACT_NONE, int(bool(mixed)), float(alpha),
                C.ptr(G), C.ptr(d_bias), C.ptr(d_x0), 0, C.ptr(ws), ws_bytes, C.stream_ptr(ref.device))
@@ -83,7 +131,7 @@ def row_scale_raw(x, s):
     if x.dim() != 2 or s.shape[0] != x.shape[0]:
         raise ValueError('row_scale: x must be [rows, d] and s [rows]')
     y = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Timed('row_scale', 2 * x.numel() * 4 + x.shape[0] * 4, x.device):
         C.call('cb_row_scale', C.ptr(x), C.ptr(s), x.shape[0], x.shape[1], C.ptr(y), C.stream_ptr(x.device))
     return y
 
@@ -125,8 +173,11 @@ class _FrobNorm(torch.autograd.Function):
     """||E||_F (GCN.py:232 th.norm(self.le)); gradient g * E / ||E||, zero at E = 0 like torch.norm."""
 
     @staticmethod
-    def forward(ctx, e):
-        n = sumsq_raw(e).sqrt_().reshape(())
+    def forward(ctx, e, graph):
+        ss = sumsq_raw(e)
+        if graph is not None:
+            ss = graph.allreduce_sum(ss)        # row-sharded table: the norm is over every rank's rows
+        n = ss.sqrt_().reshape(())
         ctx.save_for_backward(e, n)
         return n
 
@@ -134,11 +185,11 @@ class _FrobNorm(torch.autograd.Function):
     def backward(ctx, g):
         e, n = ctx.saved_tensors
         scale = torch.where(n > 0, g / n, torch.zeros_like(n))
-        return e * scale
+        return e * scale, None
 
 
-def frob_norm(e):
-    return _FrobNorm.apply(e)
+def frob_norm(e, graph=None):
+    return _FrobNorm.apply(e, graph)
 
 
 class _FusedAggregate(torch.autograd.Function):
@@ -151,7 +202,7 @@ class _FusedAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, H, bias, x0, graph, alpha, relu, want_out, want_scaled):
         mixed = x0 is not None
-        need_grad = any(t is not None and t.requires_grad for t in (H, bias, x0))
+        need_grad = any(ctx.needs_input_grad[:3])
         # relu mask source for backward: the plain relu output doubles as the mask when nothing was
         # mixed into it, otherwise a byte mask is written by the kernel
         use_out_as_mask = relu and not mixed and want_out

@@ -162,11 +162,42 @@ def c_oracle_threads() -> int:
     return int(_c_oracle().cb_oracle_num_threads())
 
 
+class CsrPlan:
+    """Both CSR views of a graph for the multi-threaded C aggregation (the timed CPU baseline).
+
+    DGL builds the same two structures lazily (CSC for the forward gSpMM, CSR for its autograd
+    transpose, dgl/python/dgl/backend/pytorch/sparse.py GSpMM.backward -> gspmm on the reversed graph).
+    """
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        src, dst = edge_index[0].numpy(), edge_index[1].numpy()
+        self.n = num_nodes
+        self.by_dst = build_csr(dst, src, num_nodes)[:2]
+        self.by_src = build_csr(src, dst, num_nodes)[:2]
+
+
+class _CsrAggregate(torch.autograd.Function):
+    """update_all(copy_src, sum) through the OpenMP C restatement; backward = the transposed walk."""
+
+    @staticmethod
+    def forward(ctx, h, plan):
+        ctx.plan = plan
+        return torch.from_numpy(aggregate_sum_csr_ordered(h.detach().numpy(), *plan.by_dst))
+
+    @staticmethod
+    def backward(ctx, g):
+        return torch.from_numpy(aggregate_sum_csr_ordered(g.contiguous().numpy(), *ctx.plan.by_src)), None
+
+
+def aggregate_sum_planned(h: torch.Tensor, plan: CsrPlan) -> torch.Tensor:
+    return _CsrAggregate.apply(h, plan)
+
+
 # --------------------------------------------------------------------------------------
 # one GCNConv layer (GCN.py:184-258)
 # --------------------------------------------------------------------------------------
 
-def gcn_conv(feat, edge_index, num_nodes, weight, bias=None, le=None, allow_zero_in_degree=False):
+def gcn_conv(feat, edge_index, num_nodes, weight, bias=None, le=None, allow_zero_in_degree=False, plan=None):
     """Returns (rst, se_reg).  Order of operations is the reference's:
 
     scale source rows by dout^-1/2  ->  @ W  ->  + E (unscaled)  ->  sum over in-edges  ->
@@ -183,7 +214,7 @@ def gcn_conv(feat, edge_index, num_nodes, weight, bias=None, le=None, allow_zero
     if le is not None:
         h = h + le                                                             # GCN.py:231
         se_reg = torch.norm(le)                                                # GCN.py:232
-    rst = aggregate_sum(h, edge_index, num_nodes)                              # GCN.py:238
+    rst = aggregate_sum(h, edge_index, num_nodes) if plan is None else aggregate_sum_planned(h, plan)  # GCN.py:238
     rst = rst * din_is.reshape(-1, 1)                                          # GCN.py:242-250
     if bias is not None:
         rst = rst + bias                                                       # GCN.py:252-253
@@ -362,6 +393,7 @@ class OracleTricksComb(nn.Module):
     def __init__(self, args):
         super().__init__()
         self.args = args
+        self.plan = None          # set to a CsrPlan to aggregate through the OpenMP C path (CPU baseline timing)
         t = args.type_trick
         L, H, Fin, C = args.num_layers, args.dim_hidden, args.num_feats, args.num_classes
         se = args.TeacherGNN.whetherHasSE
@@ -407,7 +439,7 @@ class OracleTricksComb(nn.Module):
         for i in range(a.num_layers):                                                     # GCN.py:109-131
             x = F.dropout(x, p=a.dropout, training=self.training)
             lyr = self.layers_GCN[i]
-            x, reg = gcn_conv(x, edge_index, n, lyr.weight, lyr.bias, lyr.le if lyr.has_se else None)
+            x, reg = gcn_conv(x, edge_index, n, lyr.weight, lyr.bias, lyr.le if lyr.has_se else None, plan=self.plan)
             if reg is not None:
                 se_reg_all = reg if se_reg_all is None else se_reg_all + reg
             if t in _EXACT_NORM_NAMES:                                                    # norm_tricks.py:146-150

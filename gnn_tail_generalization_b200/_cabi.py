@@ -38,6 +38,10 @@ SYMBOLS = {
     'cb_row_scale': (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     'cb_sumsq_workspace_bytes': (_i64, []),
     'cb_sumsq': (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
+    'cb_gemm_split_weight': (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp]),
+    'cb_gemm_rows_supported': (_int, [_i64, _i64, _i64]),
+    'cb_gemm_rows': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _int, _vp, _i64, _vp, _vp,
+                            _i64, _vp]),
     'cb_launch_count': (_i64, []),
 }
 

@@ -1,0 +1,503 @@
+// Dense transform of the GCN layer on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32 in /
+// fp32 out with "3xTF32" split operands so that the result keeps fp32-level accuracy:
+//
+//   cb_gemm_rows     C[M,N] = epilogue( A[M,K] . Bt[N,K]^T )
+//       GNN_model/GCN.py:225   th.matmul(feat_src, weight)      (and its adjoint  dX = dH . W^T)
+//       GCN.py:205-213         out-degree row scale             (epilogue: rs[row] * acc, since (D X) W = D (X W))
+//       GCN.py:230-231         + self.le                        (epilogue: + add[row, col])
+//       GCN.py:104-106,138     Linear + bias (+ relu)           (epilogue: + bias[col], relu)
+//   cb_gemm_split_weight       hi/lo TF32 split of the small weight operand (done once per call, 256 KB)
+//
+// Precision.  Every fp32 value x is split as x = hi + lo with hi = tf32_rna(x), lo = tf32_rna(x - hi)
+// (x - hi is exact in fp32).  The kernel accumulates  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  in fp32 in
+// tensor memory; the dropped term A_lo.B_lo and the rounding of lo are O(2^-21) relative per product,
+// i.e. fp32-class accuracy (the reference GEMM is cuBLAS/MKL SGEMM with TF32 off, GCN.py:225).
+//
+// Structure (one CTA per SM, persistent over 128-row tiles, 320 threads):
+//   warp 0      TMA producer: per 32-wide k-chunk one box of A (128 x 32 fp32, raw) and the matching
+//               boxes of Bt_hi / Bt_lo (BN x 32) into a SWIZZLE_128B stage; mbarrier expect_tx
+//   warps 2-5   split: read the raw A chunk from shared memory, write hi in place and lo beside it
+//               (element-wise at identical offsets, so the TMA swizzle is preserved), fence.proxy.async
+//   warp 1      MMA issuer: 3 x (BK/8) tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per chunk into one of two
+//               TMEM accumulators; tcgen05.commit frees the stage / publishes the accumulator
+//   warps 6-9   epilogue: tcgen05.ld 32x32b.x32 -> registers -> per-warp padded smem transpose ->
+//               coalesced 16-byte global loads/stores with the fused row-scale / bias / add / relu
+// The weight operand is re-streamed from L2 per tile (it is 2 x N x K x 4 bytes = 512 KB at 256x256).
+#include <cuda.h>
+
+#include "cb_internal.cuh"
+
+namespace cb {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;     // fp32 per k-chunk = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;  // K of one tcgen05.mma.kind::tf32
+constexpr int THREADS = 320;
+constexpr int STG_LD = 36;  // floats per staging row (32 + 4 pad: 16-byte aligned, conflict-free)
+
+template <int BN>
+struct Cfg {
+    static constexpr int STAGES = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
+    static constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
+    static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;  // barriers + alignment slack
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+struct GemmArgs {
+    int64_t M;
+    int N, K;
+    const float* row_scale;  // [M] or null
+    const float* bias;       // [N] or null
+    const float* add;        // [M, ld_add] or null
+    int64_t ld_add;
+    int act;
+    float* out;              // [M, ld_out] or null
+    int64_t ld_out;
+    const float* out2_scale; // [M]
+    float* out2;             // [M, ld_out2] or null
+    int64_t ld_out2;
+    int64_t n_tiles_m;
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug traps instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// x = hi + lo, both representable in TF32 (low 13 mantissa bits zero)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float rest = __fsub_rn(x, __uint_as_float(hi));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms of 1024 bytes)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+    uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t instr_desc_tf32() {
+    return (1u << 4)                 // D format  = F32
+           | (2u << 7)               // A format  = TF32
+           | (2u << 10)              // B format  = TF32
+           | ((uint32_t)(BN >> 3) << 17)   // N >> 3
+           | ((uint32_t)(BM >> 4) << 24);  // M >> 4   (A and B both K-major: bits 15/16 = 0)
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+            const __grid_constant__ CUtensorMap map_blo, const GemmArgs g) {
+    using C = Cfg<BN>;
+    constexpr int STAGES = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const uint32_t bar_base = smem_base + C::BAR_OFF;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto ready_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::BAR_OFF + 8 * (3 * STAGES + 4));
+
+    auto a_hi = [&](int s) { return smem_base + (uint32_t)s * C::STAGE_BYTES; };
+    auto a_lo = [&](int s) { return smem_base + (uint32_t)s * C::STAGE_BYTES + C::A_BYTES; };
+    auto b_hi = [&](int s) { return smem_base + (uint32_t)s * C::STAGE_BYTES + 2 * C::A_BYTES; };
+    auto b_lo = [&](int s) { return smem_base + (uint32_t)s * C::STAGE_BYTES + 2 * C::A_BYTES + C::B_BYTES; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a);
+            tma_prefetch_desc(&map_bhi);
+            tma_prefetch_desc(&map_blo);
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(full_bar(s), 1);
+                mbar_init(ready_bar(s), 4);
+                mbar_init(empty_bar(s), 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(tfull_bar(a), 1);
+                mbar_init(tempty_bar(a), 4);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n0 = blockIdx.y * BN;
+    const int nk = (g.K + BK - 1) / BK;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x) {
+            for (int kc = 0; kc < nk; ++kc, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
+                    tma_load_2d(a_hi(s), &map_a, full_bar(s), kc * BK, (int)(tile * BM));
+                    tma_load_2d(b_hi(s), &map_bhi, full_bar(s), kc * BK, n0);
+                    tma_load_2d(b_lo(s), &map_blo, full_bar(s), kc * BK, n0);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = instr_desc_tf32<BN>();
+        uint32_t it = 0, tl = 0;
+        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x, ++tl) {
+            const int acc = tl & 1u;
+            const uint32_t aph = (tl >> 1) & 1u;
+            mbar_wait(tempty_bar(acc), aph ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kc = 0; kc < nk; ++kc, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(full_bar(s), ph);
+                mbar_wait(ready_bar(s), ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t dah = smem_desc_sw128(a_hi(s));
+                    const uint64_t dal = smem_desc_sw128(a_lo(s));
+                    const uint64_t dbh = smem_desc_sw128(b_hi(s));
+                    const uint64_t dbl = smem_desc_sw128(b_lo(s));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // 32 bytes per k-step
+                        umma_tf32(d_tmem, dal + adv, dbh + adv, idesc, (kc | k) != 0);
+                        umma_tf32(d_tmem, dah + adv, dbl + adv, idesc, 1u);
+                        umma_tf32(d_tmem, dah + adv, dbh + adv, idesc, 1u);
+                    }
+                    umma_commit(empty_bar(s));
+                    if (kc == nk - 1) umma_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 6) {
+        // ===== split warps: raw fp32 A chunk -> TF32 hi (in place) + lo =====
+        const int t = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x) {
+            for (int kc = 0; kc < nk; ++kc, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(full_bar(s), ph);
+                uint8_t* hi_p = smem_gen + (size_t)s * C::STAGE_BYTES;
+                uint8_t* lo_p = hi_p + C::A_BYTES;
+#pragma unroll
+                for (int i = 0; i < C::A_BYTES / 16 / 128; ++i) {
+                    const int idx = t + 128 * i;
+                    const float4 v = *reinterpret_cast<const float4*>(hi_p + 16 * idx);
+                    uint4 h, l;
+                    split_tf32(v.x, h.x, l.x);
+                    split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z);
+                    split_tf32(v.w, h.w, l.w);
+                    *reinterpret_cast<uint4*>(hi_p + 16 * idx) = h;
+                    *reinterpret_cast<uint4*>(lo_p + 16 * idx) = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ready_bar(s));
+            }
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        float* stg = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES) + q * 32 * STG_LD;
+        const int rsub = lane >> 3;  // 0..3
+        const int c4 = lane & 7;     // 0..7
+        uint32_t tl = 0;
+        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x, ++tl) {
+            const int acc = tl & 1u;
+            const uint32_t aph = (tl >> 1) & 1u;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const int64_t row0 = tile * BM + q * 32;
+            const int n_slabs = min(BN, g.N - n0 + 31) / 32;
+            for (int j = 0; j < n_slabs; ++j) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + j * 32), r);
+                tmem_ld_wait();
+                if (j == n_slabs - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<uint4*>(stg + lane * STG_LD + 4 * i) =
+                        make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+                __syncwarp();
+                const int col = n0 + j * 32 + c4 * 4;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.bias && col < g.N) bv = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr) {
+                    const int rr = itr * 4 + rsub;
+                    const int64_t row = row0 + rr;
+                    float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + 4 * c4);
+                    if (row < g.M && col < g.N) {
+                        if (g.row_scale) {
+                            const float rs = __ldg(g.row_scale + row);
+                            v.x = __fmul_rn(v.x, rs); v.y = __fmul_rn(v.y, rs);
+                            v.z = __fmul_rn(v.z, rs); v.w = __fmul_rn(v.w, rs);
+                        }
+                        if (g.bias) {
+                            v.x = __fadd_rn(v.x, bv.x); v.y = __fadd_rn(v.y, bv.y);
+                            v.z = __fadd_rn(v.z, bv.z); v.w = __fadd_rn(v.w, bv.w);
+                        }
+                        if (g.add) {
+                            const float4 e = __ldg(reinterpret_cast<const float4*>(g.add + row * g.ld_add + col));
+                            v.x = __fadd_rn(v.x, e.x); v.y = __fadd_rn(v.y, e.y);
+                            v.z = __fadd_rn(v.z, e.z); v.w = __fadd_rn(v.w, e.w);
+                        }
+                        if (g.act == CB_ACT_RELU) {
+                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                            v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                        }
+                        if (g.out) *reinterpret_cast<float4*>(g.out + row * g.ld_out + col) = v;
+                        if (g.out2) {
+                            const float s2 = __ldg(g.out2_scale + row);
+                            v.x = __fmul_rn(v.x, s2); v.y = __fmul_rn(v.y, s2);
+                            v.z = __fmul_rn(v.z, s2); v.w = __fmul_rn(v.w, s2);
+                            *reinterpret_cast<float4*>(g.out2 + row * g.ld_out2 + col) = v;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// hi/lo TF32 split of the weight operand, optionally transposed:  dst[n, k] = src[n, k] or src[k, n]
+__global__ void __launch_bounds__(256) k_split_weight(const float* __restrict__ W, int n_rows, int k_cols,
+                                                      int transpose, float* __restrict__ hi,
+                                                      float* __restrict__ lo) {
+    const int64_t total = (int64_t)n_rows * k_cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / k_cols), k = (int)(i % k_cols);
+        const float x = transpose ? W[(int64_t)k * n_rows + n] : W[i];
+        uint32_t h, l;
+        split_tf32(x, h, l);
+        hi[i] = __uint_as_float(h);
+        lo[i] = __uint_as_float(l);
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, cols] fp32 row-major with a row pitch of ld floats; box = box_rows x 32 floats, SWIZZLE_128B
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    CB_REQUIRE(fn != nullptr, CB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return CB_E_CUDA;
+    }
+    return CB_OK;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const GemmArgs& g,
+                       cudaStream_t st) {
+    using C = Cfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        CB_CUDA(cudaFuncSetAttribute(k_gemm_rows<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    const int64_t gx = g.n_tiles_m < sm_count() ? g.n_tiles_m : sm_count();
+    dim3 grid((unsigned)gx, (unsigned)ceil_div(g.N, BN));
+    k_gemm_rows<BN><<<grid, THREADS, C::SMEM_BYTES, st>>>(ma, mh, ml, g);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+}  // namespace tc
+}  // namespace cb
+
+extern "C" {
+
+int cb_gemm_split_weight(const float* W, int64_t n_rows, int64_t k_cols, int transpose, float* hi, float* lo,
+                         void* stream) {
+    using namespace cb;
+    CB_REQUIRE(W && hi && lo, CB_E_INVALID, "cb_gemm_split_weight: NULL buffer");
+    CB_REQUIRE(n_rows > 0 && k_cols > 0 && n_rows * k_cols < (int64_t)1 << 31, CB_E_INVALID,
+               "cb_gemm_split_weight: bad shape");
+    const int64_t total = n_rows * k_cols;
+    const int blocks = (int)(ceil_div(total, 256) < 1184 ? ceil_div(total, 256) : 1184);
+    tc::k_split_weight<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, (int)n_rows, (int)k_cols, transpose, hi, lo);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_gemm_rows_supported(int64_t M, int64_t N, int64_t K) {
+    return M > 0 && N > 0 && K > 0 && N % 4 == 0 && K % 4 == 0 && M < ((int64_t)1 << 31) - 128 && N < (1 << 20) &&
+           K < (1 << 20);
+}
+
+int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float* Bt_hi, const float* Bt_lo,
+                 int64_t N, const float* row_scale, const float* bias, const float* add, int64_t ld_add, int act,
+                 float* out, int64_t ld_out, const float* out2_scale, float* out2, int64_t ld_out2, void* stream) {
+    using namespace cb;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    CB_REQUIRE(A && Bt_hi && Bt_lo, CB_E_INVALID, "cb_gemm_rows: NULL operand");
+    CB_REQUIRE(out || out2, CB_E_INVALID, "cb_gemm_rows: no output buffer");
+    CB_REQUIRE(!out2 || out2_scale, CB_E_INVALID, "cb_gemm_rows: out2 needs out2_scale");
+    CB_REQUIRE(act == CB_ACT_NONE || act == CB_ACT_RELU, CB_E_INVALID, "cb_gemm_rows: unknown activation");
+    CB_REQUIRE(cb_gemm_rows_supported(M, N, K), CB_E_UNSUPPORTED,
+               "cb_gemm_rows: needs N % 4 == 0, K % 4 == 0 and M < 2^31");
+    CB_REQUIRE(lda >= K && lda % 4 == 0 && al16(A) && al16(Bt_hi) && al16(Bt_lo), CB_E_UNSUPPORTED,
+               "cb_gemm_rows: operands must be 16-byte aligned with a row pitch that is a multiple of 4 floats");
+    CB_REQUIRE((!out || (al16(out) && ld_out % 4 == 0 && ld_out >= N)) &&
+                   (!out2 || (al16(out2) && ld_out2 % 4 == 0 && ld_out2 >= N)) &&
+                   (!add || (al16(add) && ld_add % 4 == 0 && ld_add >= N)) && (!bias || al16(bias)),
+               CB_E_UNSUPPORTED, "cb_gemm_rows: epilogue buffers must be 16-byte aligned, pitches multiples of 4");
+    const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    CUtensorMap ma, mh, ml;
+    int rc = tc::make_map(&ma, A, M, K, lda, tc::BM);
+    if (rc) return rc;
+    rc = tc::make_map(&mh, Bt_hi, N, K, K, bn);
+    if (rc) return rc;
+    rc = tc::make_map(&ml, Bt_lo, N, K, K, bn);
+    if (rc) return rc;
+    tc::GemmArgs g{};
+    g.M = M; g.N = (int)N; g.K = (int)K;
+    g.row_scale = row_scale; g.bias = bias; g.add = add; g.ld_add = ld_add; g.act = act;
+    g.out = out; g.ld_out = ld_out; g.out2_scale = out2_scale; g.out2 = out2; g.ld_out2 = ld_out2;
+    g.n_tiles_m = ceil_div(M, tc::BM);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 64) return tc::launch_gemm<64>(ma, mh, ml, g, st);
+    if (bn == 128) return tc::launch_gemm<128>(ma, mh, ml, g, st);
+    return tc::launch_gemm<256>(ma, mh, ml, g, st);
+}
+
+}  // extern "C"

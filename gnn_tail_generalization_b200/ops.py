@@ -22,8 +22,8 @@ def set_timing_sink(sink):
 
 
 class _Timed:
-    def __init__(self, name, alg_bytes, device):
-        self.name, self.bytes, self.device = name, alg_bytes, device
+    def __init__(self, name, alg_bytes, device, flops=0):
+        self.name, self.bytes, self.device, self.flops = name, alg_bytes, device, flops
 
     def __enter__(self):
         if _timing_sink is not None:
@@ -145,6 +145,55 @@ def sumsq_raw(x):
     with torch.cuda.device(x.device):
         C.call('cb_sumsq', C.ptr(x), x.numel(), C.ptr(out), C.ptr(ws), nb, C.stream_ptr(x.device))
     return out
+
+
+class SplitWeight:
+    """The weight operand of cb_gemm_rows: K-major [N, K] TF32 hi/lo halves (hi + lo ~= W to 2^-22)."""
+
+    __slots__ = ('hi', 'lo', 'n', 'k')
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+        self.n, self.k = hi.shape
+
+
+def split_weight(W, transpose):
+    """transpose=False: W is already [N, K] (nn.Linear.weight; or the GCNConv weight for the adjoint).
+    transpose=True: W is [K, N] (GCNConv.weight used forward) and is transposed while splitting."""
+    _need_cuda(W)
+    W = _f32c(W.detach())
+    n, k = (W.shape[1], W.shape[0]) if transpose else W.shape
+    buf = torch.empty((2, n, k), dtype=torch.float32, device=W.device)
+    with torch.cuda.device(W.device):
+        C.call('cb_gemm_split_weight', C.ptr(W), n, k, int(bool(transpose)), C.ptr(buf[0]), C.ptr(buf[1]),
+               C.stream_ptr(W.device))
+    return SplitWeight(buf[0], buf[1])
+
+
+def gemm_supported(M, N, K):
+    return bool(C.lib().cb_gemm_rows_supported(int(M), int(N), int(K)))
+
+
+def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_scale=None, want_out=True,
+                  want_out2=False):
+    """act(row_scale * (A @ W^T) + bias + add) on the tcgen05 tensor cores (3xTF32, fp32-class accuracy).
+    Returns out, or (out, out2) when want_out2 (out2 = out2_scale[:,None] * out)."""
+    _need_cuda(A, row_scale, bias, add, out2_scale)
+    A, row_scale, bias, add, out2_scale = _f32c(A), _f32c(row_scale), _f32c(bias), _f32c(add), _f32c(out2_scale)
+    M, K = A.shape
+    if K != wt.k:
+        raise ValueError(f'A is [{M},{K}] but the weight operand is [{wt.n},{wt.k}]')
+    N = wt.n
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device) if want_out else None
+    out2 = torch.empty((M, N), dtype=torch.float32, device=A.device) if want_out2 else None
+    if M == 0:
+        return (out, out2) if want_out2 else out
+    alg = 4 * (M * K + 2 * N * K + M * N * (int(want_out) + int(want_out2) + int(add is not None)))
+    with torch.cuda.device(A.device), _Timed('gemm_rows', alg, A.device, flops=6 * M * N * K):
+        C.call('cb_gemm_rows', C.ptr(A), M, K, K, C.ptr(wt.hi), C.ptr(wt.lo), N, C.ptr(row_scale), C.ptr(bias),
+               C.ptr(add), N, C.CB_ACT_RELU if relu else C.CB_ACT_NONE, C.ptr(out), N, C.ptr(out2_scale),
+               C.ptr(out2), N, C.stream_ptr(A.device))
+    return (out, out2) if want_out2 else out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -163,6 +163,31 @@ int64_t cb_sumsq_workspace_bytes(void);
 int cb_sumsq(const float* x, int64_t n, float* out, void* workspace, int64_t workspace_bytes,
              void* stream);
 
+/*
+ * Dense transform on the tcgen05 tensor cores, fp32 in / fp32 out, "3xTF32" split operands (fp32-class
+ * accuracy; the reference GEMM is th.matmul in fp32 with TF32 off, GCN.py:225).
+ *
+ * cb_gemm_split_weight: hi/lo TF32 split of the small weight operand into the K-major layout the kernel
+ *   streams:  hi[n,k] + lo[n,k] ~= (transpose ? W[k,n] : W[n,k]);  hi, lo: [n_rows, k_cols] each.
+ *   GCNConv forward (X @ W, W is [in,out], GCN.py:225): transpose=1, n_rows=out, k_cols=in.
+ *   Its adjoint dX = dH @ W^T: transpose=0 on the same W (n_rows=in, k_cols=out).
+ *   nn.Linear forward (x @ weight^T, weight is [out,in], GCN.py:43,106): transpose=0.
+ *
+ * cb_gemm_rows:  acc = A[M,K] . Bt[N,K]^T
+ *                v   = act( (row_scale ? row_scale[m] : 1) * acc + bias[n] + add[m,n] )
+ *                out[m,n] = v ;  out2[m,n] = out2_scale[m] * v
+ *   fuses GCN.py:205-213 (out-degree scale, (D X) W = D (X W)), GCN.py:230-231 (+ le), the Linear bias
+ *   and relu of GCN.py:104-106, and the next layer's out-degree scale (out2).
+ *   A: row pitch lda floats; out/out2/add: row pitches ld_*; every pointer 16-byte aligned, pitches,
+ *   N and K multiples of 4 (else CB_E_UNSUPPORTED: the caller then uses a library GEMM).
+ */
+int cb_gemm_split_weight(const float* W, int64_t n_rows, int64_t k_cols, int transpose, float* hi, float* lo,
+                         void* stream);
+int cb_gemm_rows_supported(int64_t M, int64_t N, int64_t K);
+int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float* Bt_hi, const float* Bt_lo,
+                 int64_t N, const float* row_scale, const float* bias, const float* add, int64_t ld_add, int act,
+                 float* out, int64_t ld_out, const float* out2_scale, float* out2, int64_t ld_out2, void* stream);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
 int64_t cb_launch_count(void);
 

@@ -1,0 +1,21 @@
+import torch, time, sys
+sys.path.insert(0, '/root/repo')
+from gnn_tail_generalization_b200 import ops
+torch.backends.cuda.matmul.allow_tf32 = False
+def t(fn, n=5):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+for (M, K, N) in [(10_000_000, 256, 256), (10_000_000, 256, 64), (10_000_000, 64, 256), (2_000_000, 128, 128)]:
+    A = torch.randn(M, K, device='cuda'); W = torch.randn(N, K, device='cuda') / K ** 0.5
+    wt = ops.split_weight(W, False)
+    out = ops.gemm_rows_raw(A, wt)
+    ref = A[:4096].double() @ W.double().t()
+    err = float((out[:4096].double() - ref).abs().max()); errc = float(((A[:4096] @ W.t()).double() - ref).abs().max())
+    ms = t(lambda: ops.gemm_rows_raw(A, wt)); msc = t(lambda: A @ W.t())
+    fl = 2 * M * K * N
+    print(f'M={M} K={K} N={N}: ours {ms:.2f} ms ({fl/ms/1e9:.1f} TF/s fp32-equiv, {4*(M*K+M*N)/ms/1e6:.0f} GB/s) cublas fp32 {msc:.2f} ms  err ours {err:.2e} cublas {errc:.2e}', flush=True)
+    del A, out

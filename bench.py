@@ -45,6 +45,7 @@ def parse():
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--cpu-nodes', type=int, default=1_000_000, help='sample size of the CPU baseline / reference arm')
     p.add_argument('--cpu-steps', type=int, default=2)
+    p.add_argument('--profile', default='', help='write a torch.profiler kernel table of 2 steps to this file')
     return p.parse_args()
 
 
@@ -266,6 +267,15 @@ def run_ours(a):
     exch_per_step = (graph.exchanged_bytes - exch0) // a.steps
     value = 2 * L * E / (ms_step * 1e-3)
 
+    if a.profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+        with open(a.profile, 'w') as f:
+            f.write(prof.key_averages().table(sort_by='cuda_time_total', row_limit=40, max_name_column_width=90))
+
     # ---- per-kernel probe: CUDA events around every C-ABI launch, over a second timed region ----
     sink = []
     ops.set_timing_sink(sink)
@@ -332,7 +342,7 @@ def run_ours(a):
                 'config': {'workload': workload_name(a), 'edges': E, 'edges_aggregated_per_step': 2 * L * E,
                            'l2': 'inputs exceed L2 (feature matrix %.1f GB vs 126 MB)' % (N * d * 4 / 1e9),
                            'parallelism': f'node-slice x{world}' if world > 1 else 'single GPU',
-                           'gemm': 'cuBLAS fp32 (no TF32)'},
+                           'gemm': 'tcgen05 3xTF32 split (fp32-class accuracy), fp32 accumulate in TMEM'},
                 'roofline': roofline, 'roofline_kernels': kernels, 'cpu_baseline': cpu, 'e2e': e2e,
                 'clocks': clk.summary(), 'gpu_launches': launches,
                 'exchange_bytes_per_step_per_rank': exch_per_step}

@@ -12,7 +12,9 @@ What changed underneath:
     the transposed gather ``cb_agg_gather``;
   * the zero-in-degree check (GCN.py:187-197) reads a flag computed once at graph build instead of
     synchronising the device in every layer of every forward.
-The dense ``X W`` stays a GEMM (torch.addmm / cuBLAS fp32, the SE table added through beta=1).
+The dense ``X W`` is a true GEMM and runs on the tensor cores: ``cb_gemm_rows`` (tcgen05, 3xTF32 split for
+fp32-class accuracy) with the out-degree scale, the SE add, the Linear bias and relu in its epilogue;
+weight gradients use ``cb_gemm_tn``.  Shapes those kernels do not cover fall back to cuBLAS fp32.
 """
 import math
 
@@ -83,12 +85,17 @@ class GCNConv(nn.Module):
                            'weight parameter. Please create the module with flag weight=False.')
         return weight if weight is not None else self.weight
 
-    def _transform(self, graph, feat_scaled, weight):
-        """(already out-degree-scaled X) W + E, and the SE regulariser (GCN.py:223-236)."""
-        if self.whetherHasSE:
-            h = th.addmm(self.le, feat_scaled, weight) if weight is not None else feat_scaled + self.le
-            return h, _ops.frob_norm(self.le, graph)
-        return (th.matmul(feat_scaled, weight) if weight is not None else feat_scaled), None
+    def _transform(self, graph, feat, weight, row_scale=None):
+        """row_scale * (X W) + E  ( = (D_out^-1/2 X) W + E, GCN.py:205-231) and the SE regulariser
+        (GCN.py:232-236).  One tcgen05 GEMM with the scale and the SE add in its epilogue."""
+        le = self.le if self.whetherHasSE else None
+        if weight is not None:
+            h, _ = _ops.dense(feat, weight, 'kn', add=le, row_scale=row_scale)
+        else:
+            h = feat if row_scale is None else _ops.row_scale(feat, row_scale)
+            if le is not None:
+                h = h + le
+        return h, (_ops.frob_norm(self.le, graph) if self.whetherHasSE else None)
 
     def fused(self, graph, feat, prescaled=False, relu=False, x0=None, alpha=0.0, want_out=True,
               want_scaled=False, weight=None):
@@ -101,8 +108,7 @@ class GCNConv(nn.Module):
         """
         assert self._norm == 'both'
         weight = self._check(graph, weight)
-        xs = feat if prescaled else _ops.row_scale(feat, graph.dout_inv_sqrt)
-        h, se_reg = self._transform(graph, xs, weight)
+        h, se_reg = self._transform(graph, feat, weight, None if prescaled else graph.dout_inv_sqrt)
         out, out_scaled = _ops.fused_aggregate(h, graph, self.bias, x0, alpha, relu, want_out, want_scaled)
         return out, out_scaled, se_reg
 
@@ -205,7 +211,8 @@ class TricksComb(nn.Module):
 
         if self.has_residual_MLP:
             x = F.dropout(x, p=self.embedding_dropout, training=self.training)
-            x = F.relu(self.layers_MLP[0](x))
+            lin = self.layers_MLP[0]
+            x, _ = _ops.dense(x, lin.weight, 'nk', bias=lin.bias, relu=True)
             x_list.append(x)
 
         norm_runs = norm_is_executed(trick)
@@ -252,7 +259,8 @@ class TricksComb(nn.Module):
             if AcontainsB(trick, ['Jumping']):
                 x = self.layers_res[0](x_list)
             else:
-                x = self.layers_MLP[-1](x)
+                lin = self.layers_MLP[-1]
+                x, _ = _ops.dense(x, lin.weight, 'nk', bias=lin.bias)
         if want_les:
             return x, se_reg_all, th.cat(le_collection, dim=-1)
         return x, se_reg_all

@@ -24,6 +24,7 @@
 //               coalesced 16-byte global loads/stores with the fused row-scale / bias / add / relu
 // The weight operand is re-streamed from L2 per tile (it is 2 x N x K x 4 bytes = 512 KB at 256x256).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "cb_internal.cuh"
 
@@ -441,6 +442,288 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mh, const CUten
     return CB_OK;
 }
 
+
+// =====================================================================================================
+// Weight gradient:  C[Ka, Nb] = A[M, Ka]^T . B[M, Nb]   (reduction over the M node rows)
+//   autograd of GCN.py:225 (dW = (D X)^T dH) and of the Linear layers (dW = dY^T X).
+// Both operands are read as stored (row-major, feature-contiguous = "MN-major" for the tensor core):
+// a k-chunk is 16 node rows; TMA lands it as [feature group of 32][16 nodes][128 bytes]
+// (SWIZZLE_128B_ATOM_32B = UMMA SWIZZLE_128B_BASE32B, the one layout MN-major TF32 operands may use),
+// the canonical MN-major UMMA layout with leading byte offset = 16*128 between feature groups and
+// stride byte offset = 512 between 4-node swizzle atoms.  Both operands are split hi/lo in shared
+// memory by warps 2-9.
+// Accumulation order.  The tensor core adds into its fp32 accumulator with truncation, so the error of
+// one TMEM accumulation chain grows linearly with its length.  The node rows are therefore cut into
+// segments of seg_chunks k-chunks (<= 1024 rows; measured bias 3e-8 per accumulation, 6 per chunk): a CTA accumulates one segment in TMEM (two 128-lane
+// halves), warps 10-13 drain it to its own slot of the workspace, and k_reduce_partials adds the slots
+// in segment order in double precision (fixed association, bit-stable run to run).
+// =====================================================================================================
+constexpr int TN_BK = 16;                    // node rows per k-chunk
+constexpr int TN_GROUP_BYTES = TN_BK * 128;  // one 32-feature group of a chunk: 2 KB
+constexpr int TN_OP_BYTES = 8 * TN_GROUP_BYTES;  // up to 256 features: 16 KB per operand per chunk
+constexpr int TN_STAGE_BYTES = 4 * TN_OP_BYTES;  // A raw | B raw | A lo | B lo
+constexpr int TN_STAGES = 3;
+constexpr int TN_BAR_OFF = TN_STAGES * TN_STAGE_BYTES;
+constexpr int TN_SMEM_BYTES = TN_BAR_OFF + 256 + 1024;
+constexpr int TN_THREADS = 448;              // warp 0 TMA, warp 1 MMA, warps 2-9 split, warps 10-13 drain
+constexpr int TN_MAX_SEG_CHUNKS = 64;   // 1024 rows: 384 accumulations per chain, ~1e-5 worst-case relative bias
+
+struct TnArgs {
+    int64_t n_chunks;   // ceil(M / TN_BK)
+    int64_t n_segs;     // ceil(n_chunks / seg_chunks)
+    int seg_chunks;
+    int ka, nb;         // features of A / B handled by this launch (ka <= 256, nb <= 256, multiples of 32)
+    int ga, gb;         // ka/32, nb/32
+    float* partial;     // [n_segs, ka, nb]
+    uint32_t lbo, sbo;  // descriptor byte offsets (host-computed)
+    const float* row_scale;  // [M] or null: per-node scale applied to one operand while it is split
+    int scale_op;            // 0 = A, 1 = B
+    int64_t M;
+};
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B: the only shared-memory layout for MN-major TF32 operands
+    return d;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(TN_THREADS, 1)
+k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TnArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const uint32_t bar_base = smem_base + TN_BAR_OFF;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto ready_bar = [&](int s) { return bar_base + 8u * (TN_STAGES + s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * TN_STAGES + s); };
+    const uint32_t done_bar = bar_base + 8u * (3 * TN_STAGES);         // segment accumulated (tcgen05.commit)
+    const uint32_t drained_bar = bar_base + 8u * (3 * TN_STAGES + 1);  // segment read out of TMEM (4 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + TN_BAR_OFF + 8 * (3 * TN_STAGES + 2));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a);
+            tma_prefetch_desc(&map_b);
+            for (int s = 0; s < TN_STAGES; ++s) {
+                mbar_init(full_bar(s), 1);
+                mbar_init(ready_bar(s), 8);
+                mbar_init(empty_bar(s), 1);
+            }
+            mbar_init(done_bar, 1);
+            mbar_init(drained_bar, 4);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // this CTA's contiguous range of segments (host guarantees gridDim.x <= n_segs)
+    const int64_t s_beg = g.n_segs * blockIdx.x / gridDim.x;
+    const int64_t s_end = g.n_segs * (blockIdx.x + 1) / gridDim.x;
+    const int64_t c_beg = s_beg * g.seg_chunks;
+    const int64_t c_end = s_end * g.seg_chunks < g.n_chunks ? s_end * g.seg_chunks : g.n_chunks;
+    const int a_bytes = g.ga * TN_GROUP_BYTES, b_bytes = g.gb * TN_GROUP_BYTES;
+    const int halves = g.ka > 128 ? 2 : 1;
+
+    if (warp == 0) {
+        uint32_t it = 0;
+        for (int64_t c = c_beg; c < c_end; ++c, ++it) {
+            const int s = it % TN_STAGES;
+            const uint32_t ph = (it / TN_STAGES) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            if (lane == 0) {
+                const uint32_t st = smem_base + (uint32_t)s * TN_STAGE_BYTES;
+                mbar_arrive_expect_tx(full_bar(s), (uint32_t)(a_bytes + b_bytes));
+                tma_load_3d(st, &map_a, full_bar(s), 0, (int)(c * TN_BK), 0);
+                tma_load_3d(st + TN_OP_BYTES, &map_b, full_bar(s), 0, (int)(c * TN_BK), 0);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // A and B both MN-major (bits 15 / 16), N = nb
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(g.nb >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        uint32_t it = 0, seg = 0;
+        for (int64_t c = c_beg; c < c_end; ++c, ++it) {
+            const int s = it % TN_STAGES;
+            const uint32_t ph = (it / TN_STAGES) & 1u;
+            const int pos = (int)((c - c_beg) % g.seg_chunks);
+            const bool seg_last = pos == g.seg_chunks - 1 || c == c_end - 1;
+            if (pos == 0 && seg > 0) {  // the previous segment must have left TMEM
+                mbar_wait(drained_bar, (seg - 1) & 1u);
+                tc_fence_after();
+            }
+            mbar_wait(full_bar(s), ph);
+            mbar_wait(ready_bar(s), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = smem_base + (uint32_t)s * TN_STAGE_BYTES;
+                for (int h = 0; h < halves; ++h) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(h * 256);
+                    const uint32_t a_off = (uint32_t)h * 4u * TN_GROUP_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TN_BK / UMMA_K; ++k) {
+                        const uint32_t koff = (uint32_t)k * 1024u;  // next group of 8 node rows
+                        const uint64_t dah = smem_desc_mn_sw128(st + a_off + koff, g.lbo, g.sbo);
+                        const uint64_t dal = smem_desc_mn_sw128(st + 2 * TN_OP_BYTES + a_off + koff, g.lbo, g.sbo);
+                        const uint64_t dbh = smem_desc_mn_sw128(st + TN_OP_BYTES + koff, g.lbo, g.sbo);
+                        const uint64_t dbl = smem_desc_mn_sw128(st + 3 * TN_OP_BYTES + koff, g.lbo, g.sbo);
+                        umma_tf32(d_tmem, dal, dbh, idesc, (pos | k) != 0);
+                        umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                        umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                    }
+                }
+                umma_commit(empty_bar(s));
+                if (seg_last) umma_commit(done_bar);
+            }
+            __syncwarp();
+            if (seg_last) ++seg;
+        }
+    } else if (warp < 10) {
+        // ===== split warps (2..9): hi in place, lo at +2*TN_OP_BYTES =====
+        const int t = threadIdx.x - 64;  // 0..255
+        uint32_t it = 0;
+        for (int64_t c = c_beg; c < c_end; ++c, ++it) {
+            const int s = it % TN_STAGES;
+            const uint32_t ph = (it / TN_STAGES) & 1u;
+            mbar_wait(full_bar(s), ph);
+            uint8_t* st = smem_gen + (size_t)s * TN_STAGE_BYTES;
+            for (int op = 0; op < 2; ++op) {
+                uint8_t* hi_p = st + op * TN_OP_BYTES;
+                uint8_t* lo_p = hi_p + 2 * TN_OP_BYTES;
+                const int n16 = (op == 0 ? a_bytes : b_bytes) >> 4;
+                const bool scaled = g.row_scale != nullptr && g.scale_op == op;
+                for (int idx = t; idx < n16; idx += 256) {
+                    float4 v = *reinterpret_cast<const float4*>(hi_p + 16 * idx);
+                    if (scaled) {  // 16-byte chunk idx sits in node row (idx / 8) % 16 of the chunk (swizzle keeps rows)
+                        const int64_t node = c * TN_BK + ((idx >> 3) & (TN_BK - 1));
+                        const float sc = node < g.M ? __ldg(g.row_scale + node) : 0.f;
+                        v.x = __fmul_rn(v.x, sc); v.y = __fmul_rn(v.y, sc);
+                        v.z = __fmul_rn(v.z, sc); v.w = __fmul_rn(v.w, sc);
+                    }
+                    uint4 h, l;
+                    split_tf32(v.x, h.x, l.x);
+                    split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z);
+                    split_tf32(v.w, h.w, l.w);
+                    *reinterpret_cast<uint4*>(hi_p + 16 * idx) = h;
+                    *reinterpret_cast<uint4*>(lo_p + 16 * idx) = l;
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready_bar(s));
+        }
+    } else {
+        // ===== drain warps (10..13): one finished segment [ka, nb] -> its workspace slot =====
+        const int q = warp & 3;
+        uint32_t seg = 0;
+        for (int64_t sg = s_beg; sg < s_end; ++sg, ++seg) {
+            mbar_wait(done_bar, seg & 1u);
+            tc_fence_after();
+            float* part = g.partial + (size_t)sg * g.ka * g.nb;
+            for (int h = 0; h < halves; ++h) {
+                const int row = h * 128 + q * 32 + lane;
+                for (int j = 0; j < g.gb; ++j) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + j * 32), r);
+                    tmem_ld_wait();
+                    if (h == halves - 1 && j == g.gb - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(drained_bar);
+                    }
+                    if (row < g.ka) {
+                        float* dst = part + (size_t)row * g.nb + j * 32;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            __stcs(reinterpret_cast<uint4*>(dst + 4 * i),
+                                   make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// Two-stage, fixed-order reduction of the segment partials (double accumulators):
+//   stage 1: slice y of the partials -> mid[y, i]      stage 2: out[i] = sum_y mid[y, i]
+constexpr int TN_REDUCE_SLICES = 32;
+
+__global__ void __launch_bounds__(256) k_reduce_partials_1(const float* __restrict__ partial, int64_t n_part,
+                                                           int total, double* __restrict__ mid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t p_beg = n_part * blockIdx.y / gridDim.y, p_end = n_part * (blockIdx.y + 1) / gridDim.y;
+    double acc = 0.0;
+    int64_t p = p_beg;
+    for (; p + 8 <= p_end; p += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(partial + (size_t)(p + u) * total + i);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += (double)v[u];
+    }
+    for (; p < p_end; ++p) acc += (double)__ldcs(partial + (size_t)p * total + i);
+    mid[(size_t)blockIdx.y * total + i] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_reduce_partials_2(const double* __restrict__ mid, int n_slices, int ka,
+                                                           int nb, float* __restrict__ out, int64_t ld_out) {
+    const int total = ka * nb;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    double acc = 0.0;
+    for (int y = 0; y < n_slices; ++y) acc += mid[(size_t)y * total + i];
+    out[(int64_t)(i / nb) * ld_out + (i % nb)] = (float)acc;
+}
+
+// [rows, feat0 .. feat0 + 32*groups) of a row-major fp32 matrix viewed as {32 features, rows, groups}
+static int make_map_tn(CUtensorMap* map, const float* base, int64_t rows, int64_t ld, int groups) {
+    EncodeTiledFn fn = encode_fn();
+    CB_REQUIRE(fn != nullptr, CB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)groups};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+    const cuuint32_t box[3] = {32, (cuuint32_t)TN_BK, (cuuint32_t)groups};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult " + std::to_string((int)r));
+        return CB_E_CUDA;
+    }
+    return CB_OK;
+}
+
 }  // namespace tc
 }  // namespace cb
 
@@ -498,6 +781,90 @@ int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float*
     if (bn == 64) return tc::launch_gemm<64>(ma, mh, ml, g, st);
     if (bn == 128) return tc::launch_gemm<128>(ma, mh, ml, g, st);
     return tc::launch_gemm<256>(ma, mh, ml, g, st);
+}
+
+int cb_gemm_tn_supported(int64_t M, int64_t Ka, int64_t Nb) {
+    return M > 0 && Ka > 0 && Nb > 0 && Ka % 32 == 0 && Nb % 32 == 0 && M < ((int64_t)1 << 31) - 64 &&
+           Ka <= 4096 && Nb <= 4096;
+}
+
+static void tn_plan(int64_t M, int64_t* chunks, int* seg_chunks, int64_t* n_segs, int* ctas) {
+    const int64_t ch = cb::ceil_div(M, cb::tc::TN_BK);
+    const int sms = cb::sm_count();
+    int64_t sc = cb::ceil_div(ch, sms);
+    static const int64_t max_sc = getenv("CB_TN_SEG_CHUNKS") ? atoll(getenv("CB_TN_SEG_CHUNKS")) : cb::tc::TN_MAX_SEG_CHUNKS;
+    if (sc > max_sc) sc = max_sc;
+    if (sc < 1) sc = 1;
+    *chunks = ch;
+    *seg_chunks = (int)sc;
+    *n_segs = cb::ceil_div(ch, sc);
+    *ctas = (int)(*n_segs < sms ? *n_segs : sms);
+}
+
+int64_t cb_gemm_tn_workspace_bytes(int64_t M, int64_t Ka, int64_t Nb) {
+    if (!cb_gemm_tn_supported(M, Ka, Nb)) return 0;
+    int64_t chunks, n_segs;
+    int sc, ctas;
+    tn_plan(M, &chunks, &sc, &n_segs, &ctas);
+    const int64_t ka = Ka < 256 ? Ka : 256, nb = Nb < 256 ? Nb : 256;
+    return n_segs * ka * nb * (int64_t)sizeof(float) + cb::tc::TN_REDUCE_SLICES * ka * nb * (int64_t)sizeof(double);
+}
+
+int cb_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Nb,
+               const float* row_scale, int scale_b, float* out, int64_t ld_out, void* workspace,
+               int64_t workspace_bytes, void* stream) {
+    using namespace cb;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    CB_REQUIRE(A && B && out, CB_E_INVALID, "cb_gemm_tn: NULL buffer");
+    CB_REQUIRE(cb_gemm_tn_supported(M, Ka, Nb), CB_E_UNSUPPORTED,
+               "cb_gemm_tn: needs Ka % 32 == 0, Nb % 32 == 0 and M < 2^31");
+    CB_REQUIRE(al16(A) && al16(B) && lda % 4 == 0 && ldb % 4 == 0 && lda >= Ka && ldb >= Nb && ld_out >= Nb,
+               CB_E_UNSUPPORTED, "cb_gemm_tn: operands must be 16-byte aligned, pitches multiples of 4 floats");
+    CB_REQUIRE(workspace && workspace_bytes >= cb_gemm_tn_workspace_bytes(M, Ka, Nb), CB_E_WORKSPACE,
+               "cb_gemm_tn: workspace missing or smaller than cb_gemm_tn_workspace_bytes()");
+    static bool configured = false;
+    if (!configured) {
+        CB_CUDA(cudaFuncSetAttribute(tc::k_gemm_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TN_SMEM_BYTES));
+        configured = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t chunks, n_segs;
+    int seg_chunks, ctas;
+    tn_plan(M, &chunks, &seg_chunks, &n_segs, &ctas);
+    for (int64_t a0 = 0; a0 < Ka; a0 += 256) {
+        for (int64_t b0 = 0; b0 < Nb; b0 += 256) {
+            tc::TnArgs g{};
+            g.n_chunks = chunks;
+            g.n_segs = n_segs;
+            g.seg_chunks = seg_chunks;
+            g.ka = (int)(Ka - a0 < 256 ? Ka - a0 : 256);
+            g.nb = (int)(Nb - b0 < 256 ? Nb - b0 : 256);
+            g.ga = g.ka / 32;
+            g.gb = g.nb / 32;
+            g.partial = (float*)workspace;
+            g.row_scale = row_scale;
+            g.scale_op = scale_b ? 1 : 0;
+            g.M = M;
+            g.lbo = (uint32_t)tc::TN_GROUP_BYTES;   // between 32-feature groups
+            g.sbo = 512u;                           // between 4-node-row swizzle atoms
+            CUtensorMap ma, mb;
+            int rc = tc::make_map_tn(&ma, A + a0, M, lda, g.ga);
+            if (rc) return rc;
+            rc = tc::make_map_tn(&mb, B + b0, M, ldb, g.gb);
+            if (rc) return rc;
+            tc::k_gemm_tn<<<ctas, tc::TN_THREADS, tc::TN_SMEM_BYTES, st>>>(ma, mb, g);
+            CB_LAUNCH_CHECK();
+            const int total = g.ka * g.nb;
+            const int slices = (int)(n_segs < tc::TN_REDUCE_SLICES ? n_segs : tc::TN_REDUCE_SLICES);
+            double* mid = reinterpret_cast<double*>(g.partial + (size_t)n_segs * total);   // 8-byte aligned: total % 1024 == 0
+            tc::k_reduce_partials_1<<<dim3((total + 255) / 256, slices), 256, 0, st>>>(g.partial, n_segs, total, mid);
+            CB_LAUNCH_CHECK();
+            tc::k_reduce_partials_2<<<(total + 255) / 256, 256, 0, st>>>(mid, slices, g.ka, g.nb,
+                                                                        out + a0 * ld_out + b0, ld_out);
+            CB_LAUNCH_CHECK();
+        }
+    }
+    return CB_OK;
 }
 
 }  // extern "C"

@@ -196,6 +196,33 @@ def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_s
     return (out, out2) if want_out2 else out
 
 
+def gemm_tn_supported(M, Ka, Nb):
+    return bool(C.lib().cb_gemm_tn_supported(int(M), int(Ka), int(Nb)))
+
+
+def gemm_tn_raw(A, B, a_row_scale=None, b_row_scale=None):
+    """A^T @ B for row-major A [M, Ka], B [M, Nb] (the weight gradient), 3xTF32 on the tensor cores.
+    A per-row scale s[m] of either operand (sum_m s[m] A[m,:]^T B[m,:]) is applied while the operand is
+    split in shared memory."""
+    _need_cuda(A, B, a_row_scale, b_row_scale)
+    A, B = _f32c(A), _f32c(B)
+    if a_row_scale is not None and b_row_scale is not None:
+        raise ValueError('one row scale at most')
+    scale, scale_b = (_f32c(b_row_scale), 1) if b_row_scale is not None else (_f32c(a_row_scale), 0)
+    M, Ka = A.shape
+    if B.shape[0] != M:
+        raise ValueError(f'A has {M} rows, B has {B.shape[0]}')
+    Nb = B.shape[1]
+    out = torch.empty((Ka, Nb), dtype=torch.float32, device=A.device)
+    nb = int(C.lib().cb_gemm_tn_workspace_bytes(M, Ka, Nb))
+    ws = torch.empty(nb, dtype=torch.uint8, device=A.device)
+    alg = 4 * (M * Ka + M * Nb + Ka * Nb)
+    with torch.cuda.device(A.device), _Timed('gemm_tn', alg, A.device, flops=6 * M * Ka * Nb):
+        C.call('cb_gemm_tn', C.ptr(A), Ka, C.ptr(B), Nb, M, Ka, Nb, C.ptr(scale), scale_b, C.ptr(out), Nb,
+               C.ptr(ws), nb, C.stream_ptr(A.device))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # differentiable ops
 # ---------------------------------------------------------------------------------------------
@@ -239,6 +266,107 @@ class _FrobNorm(torch.autograd.Function):
 
 def frob_norm(e, graph=None):
     return _FrobNorm.apply(e, graph)
+
+
+# ---------------------------------------------------------------------------------------------
+# dense transform: act(row_scale * (x @ W) + bias + add) with the tcgen05 kernels, cuBLAS for the
+# shapes they do not cover (N or K not a multiple of 4; weight gradient: not a multiple of 32)
+# ---------------------------------------------------------------------------------------------
+_dense_backend = 'tcgen05'
+
+
+def set_dense_backend(name):
+    """'tcgen05' (default): 3xTF32 tensor-core kernels of this library wherever the shape allows;
+    'cublas': torch.matmul in fp32 everywhere (the reference's own GEMM path, for A/B comparisons)."""
+    global _dense_backend
+    if name not in ('tcgen05', 'cublas'):
+        raise ValueError(name)
+    _dense_backend = name
+
+
+def _w_as_kn(weight, layout):
+    return weight if layout == 'kn' else weight.t()
+
+
+def _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, want_out, want_out2):
+    acc = x @ _w_as_kn(weight, layout)
+    if row_scale is not None:
+        acc = acc * row_scale[:, None]
+    if bias is not None:
+        acc = acc + bias
+    if add is not None:
+        acc = acc + add
+    if relu:
+        acc = torch.relu(acc)
+    return (acc if want_out else None), (acc * out2_scale[:, None] if want_out2 else None)
+
+
+class _Dense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, add, row_scale, out2_scale, layout, relu, want_out, want_out2):
+        wt = split_weight(weight, transpose=(layout == 'kn'))
+        res = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2)
+        out, out2 = res if want_out2 else (res, None)
+        ctx.layout, ctx.relu = layout, relu
+        ctx.has_bias, ctx.has_add = bias is not None, add is not None
+        need = any(ctx.needs_input_grad[:4])
+        keep_y = (out if out is not None else out2) if (relu and need) else None
+        ctx.save_for_backward(x if need else None, weight if need else None, row_scale, out2_scale, keep_y)
+        ctx.set_materialize_grads(False)
+        empty = x.new_empty(0)
+        return (out if out is not None else empty), (out2 if out2 is not None else empty)
+
+    @staticmethod
+    def backward(ctx, dy, dy2):
+        x, weight, row_scale, out2_scale, y = ctx.saved_tensors
+        if dy is not None and dy.numel() == 0:
+            dy = None
+        if dy2 is not None and dy2.numel() == 0:
+            dy2 = None
+        if dy is None and dy2 is None:
+            return (None,) * 10
+        if dy2 is not None:
+            dy2 = dy2 * out2_scale[:, None]
+        dtot = dy2 if dy is None else (dy if dy2 is None else dy + dy2)
+        if ctx.relu:
+            dtot = torch.where(y > 0, dtot, torch.zeros((), dtype=dtot.dtype, device=dtot.device))
+        dtot = dtot.contiguous()
+        d_add = dtot if (ctx.has_add and ctx.needs_input_grad[3]) else None
+        d_bias = dtot.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        M, K = x.shape
+        N = dtot.shape[1]
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            if gemm_supported(M, K, N):
+                wb = split_weight(weight, transpose=(ctx.layout == 'nk'))
+                dx = gemm_rows_raw(dtot, wb, row_scale=row_scale)
+            else:
+                dx = dtot @ _w_as_kn(weight, ctx.layout).t()
+                if row_scale is not None:
+                    dx = dx * row_scale[:, None]
+        if ctx.needs_input_grad[1]:
+            if gemm_tn_supported(M, K, N):
+                dw = gemm_tn_raw(x, dtot, a_row_scale=row_scale) if ctx.layout == 'kn' else \
+                    gemm_tn_raw(dtot, x, b_row_scale=row_scale)
+            else:
+                xs = x if row_scale is None else x * row_scale[:, None]
+                dw = xs.t() @ dtot if ctx.layout == 'kn' else dtot.t() @ xs
+        return dx, dw, d_bias, d_add, None, None, None, None, None, None
+
+
+def dense(x, weight, layout, bias=None, add=None, relu=False, row_scale=None, out2_scale=None, want_out=True,
+          want_out2=False):
+    """act(row_scale[:,None] * (x @ W) + bias + add); also out2_scale[:,None] * that when want_out2.
+    layout 'kn': weight is [in, out] (GCNConv.weight, GCN.py:170); 'nk': [out, in] (nn.Linear.weight).
+    Returns (out, out2); the one not asked for is None."""
+    M, K = x.shape
+    N = weight.shape[1] if layout == 'kn' else weight.shape[0]
+    if _dense_backend == 'tcgen05' and x.is_cuda and M > 0 and gemm_supported(M, N, K):
+        out, out2 = _Dense.apply(x, weight, bias, add, row_scale, out2_scale, layout, bool(relu), bool(want_out),
+                                 bool(want_out2))
+        return (out if want_out else None), (out2 if want_out2 else None)
+    _need_cuda(x)
+    return _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, want_out, want_out2)
 
 
 class _FusedAggregate(torch.autograd.Function):

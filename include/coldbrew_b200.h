@@ -188,6 +188,22 @@ int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float*
                  int64_t N, const float* row_scale, const float* bias, const float* add, int64_t ld_add, int act,
                  float* out, int64_t ld_out, const float* out2_scale, float* out2, int64_t ld_out2, void* stream);
 
+/*
+ * Weight gradient on the tcgen05 tensor cores (3xTF32): out[Ka, Nb] = A[M, Ka]^T . B[M, Nb], the reduction
+ * running over the M node rows (autograd of GCN.py:225: dW = (D X)^T dH; and of the Linear layers).
+ * Split-K over the SMs with a fixed-order second pass, so the result is bit-stable from run to run.
+ * row_scale [M] or NULL: out = sum_m row_scale[m] * A[m,:]^T B[m,:] (the out-degree scale of GCN.py:205-213
+ * folded into the gradient); it is applied to A's rows, or to B's when scale_b != 0, while the operand is
+ * split in shared memory.
+ * Needs Ka % 32 == 0, Nb % 32 == 0, 16-byte aligned operands (else CB_E_UNSUPPORTED).
+ * workspace: cb_gemm_tn_workspace_bytes(M, Ka, Nb).
+ */
+int cb_gemm_tn_supported(int64_t M, int64_t Ka, int64_t Nb);
+int64_t cb_gemm_tn_workspace_bytes(int64_t M, int64_t Ka, int64_t Nb);
+int cb_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Nb,
+               const float* row_scale, int scale_b, float* out, int64_t ld_out, void* workspace,
+               int64_t workspace_bytes, void* stream);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
 int64_t cb_launch_count(void);
 

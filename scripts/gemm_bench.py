@@ -19,3 +19,14 @@ for (M, K, N) in [(10_000_000, 256, 256), (10_000_000, 256, 64), (10_000_000, 64
     fl = 2 * M * K * N
     print(f'M={M} K={K} N={N}: ours {ms:.2f} ms ({fl/ms/1e9:.1f} TF/s fp32-equiv, {4*(M*K+M*N)/ms/1e6:.0f} GB/s) cublas fp32 {msc:.2f} ms  err ours {err:.2e} cublas {errc:.2e}', flush=True)
     del A, out
+
+for (M, Ka, Nb) in [(10_000_000, 256, 256), (10_000_000, 256, 64)]:
+    A = torch.randn(M, Ka, device='cuda'); B = torch.randn(M, Nb, device='cuda')
+    out = ops.gemm_tn_raw(A, B)
+    ref = A[:200000].double().t() @ B[:200000].double()
+    o2 = ops.gemm_tn_raw(A[:200000], B[:200000])
+    err = float((o2.double() - ref).abs().max()); errc = float(((A[:200000].t() @ B[:200000]).double() - ref).abs().max())
+    ms = t(lambda: ops.gemm_tn_raw(A, B)); msc = t(lambda: A.t() @ B)
+    fl = 2 * M * Ka * Nb
+    print(f'TN M={M} Ka={Ka} Nb={Nb}: ours {ms:.2f} ms ({fl/ms/1e9:.1f} TF/s fp32-equiv, {4*(M*Ka+M*Nb)/ms/1e6:.0f} GB/s) cublas fp32 {msc:.2f} ms  err(200k rows) ours {err:.2e} cublas {errc:.2e}', flush=True)
+    del A, B

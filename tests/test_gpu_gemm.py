@@ -89,3 +89,33 @@ def test_gemm_rows_close_to_fp32_cublas_at_scale():
     # every tile was written (no stale rows): compare a strided sample against fp32 matmul loosely
     sl = slice(0, M, 997)
     assert torch.allclose(out[sl], A[sl] @ W.t(), atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize('M,Ka,Nb', [(16, 32, 32), (100, 32, 64), (4096, 256, 256), (5000, 128, 256), (7777, 256, 64),
+                                     (30001, 64, 32), (200000, 256, 256), (3000, 512, 288)])
+def test_gemm_tn_matches_fp64(M, Ka, Nb):
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(M + Ka + Nb)
+    A = torch.randn(M, Ka, device='cuda', generator=g)
+    B = torch.randn(M, Nb, device='cuda', generator=g)
+    out = ops.gemm_tn_raw(A, B)
+    ref = A.double().t() @ B.double()
+    bound = 2e-6 * (A.abs().double().t() @ B.abs().double()) + 1e-7
+    err = (out.double() - ref).abs()
+    assert bool((err <= bound).all()), f'max err {float(err.max()):.3e}, worst ratio {float((err / bound).max()):.2f}'
+    assert torch.equal(out, ops.gemm_tn_raw(A, B)), 'split-K reduction must be bit-stable'
+
+
+def test_gemm_tn_same_sign_data_keeps_fp32_class_relative_error():
+    """All-positive operands: every truncation of the tensor core's accumulator has the same sign, which is
+    the worst case for a long accumulation chain.  The segmented accumulation bounds it."""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(3)
+    M = 600_000
+    A = torch.rand(M, 64, device='cuda', generator=g) + 0.5
+    B = torch.rand(M, 96, device='cuda', generator=g) + 0.5
+    out = ops.gemm_tn_raw(A, B)
+    ref = A.double().t() @ B.double()
+    rel = float(((out.double() - ref).abs() / ref.abs()).max())
+    rel_cublas = float((((A.t() @ B).double() - ref).abs() / ref.abs()).max())
+    assert rel <= 4e-5, (rel, rel_cublas)

@@ -229,7 +229,7 @@ def run_ours(a):
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     se_coef = 0.5
 
-    def step():
+    def step(x=x):
         opt.zero_grad(set_to_none=True)
         res = model.get_3_embs(x, None, idx)
         loss = F.nll_loss(F.log_softmax(res.emb4classi, 1), y[idx], reduction='sum') / n_train
@@ -284,11 +284,12 @@ def run_ours(a):
     ops.set_timing_sink(None)
     torch.cuda.synchronize()
     per = {}
-    for name, e0, e1, nbytes in sink:
-        r = per.setdefault(name, {'launches': 0, 'ms': 0.0, 'bytes': 0})
+    for name, e0, e1, nbytes, flops in sink:
+        r = per.setdefault(name, {'launches': 0, 'ms': 0.0, 'bytes': 0, 'flops': 0})
         r['launches'] += 1
         r['ms'] += e0.elapsed_time(e1)
         r['bytes'] += nbytes
+        r['flops'] += flops
     kernels = {}
     for name, r in per.items():
         avg_ms = r['ms'] / r['launches']
@@ -296,6 +297,9 @@ def run_ours(a):
         kernels[name] = {'launches_per_step': r['launches'] / probe_steps, 'avg_ms': round(avg_ms, 4),
                          'alg_bytes': r['bytes'] // r['launches'], 'achieved_gbs': round(gbs, 1),
                          'frac': round(gbs / hbm_peak, 4), 'share_of_step': round(r['ms'] / probe_steps / ms_probe, 4)}
+        if r['flops']:
+            # 3 TF32 tensor-core products per fp32 product: flops counts the MMA work actually issued
+            kernels[name]['tensor_tflops_tf32'] = round(r['flops'] / r['launches'] / (avg_ms * 1e-3) / 1e12, 1)
     dom = kernels.get('agg_forward', {})
     roofline = {'bound': 'hbm', 'kernel': 'k_agg (cb_agg_forward)', 'achieved': dom.get('achieved_gbs'),
                 'peak': hbm_peak, 'peak_source': f'{peak_kind} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)',
@@ -309,24 +313,57 @@ def run_ours(a):
         pass
 
     # ---- end to end: host features in pinned memory -> device every step, loss read back ---------
+    # The step's features travel host -> device inside the timed region, every step.  Like any input
+    # pipeline, the copy of step i+1 runs on a side stream into the second of two device buffers while
+    # step i computes; the first copy of the timed region is fully exposed.
     e2e = None
     if not a.no_e2e:
         x_host = torch.empty((rows, d), dtype=torch.float32, pin_memory=True)
         x_host.copy_(x)
         result = torch.zeros(1, dtype=torch.float32, pin_memory=True)
+        bufs = [x, torch.empty_like(x)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        state = {'i': 0, 'primed': False, 'left': 0}
+
+        def upload(slot):
+            copy_stream.wait_event(consumed[slot])          # the step that read this buffer has finished
+            with torch.cuda.stream(copy_stream):
+                bufs[slot].copy_(x_host, non_blocking=True)
+                copied[slot].record(copy_stream)
 
         def e2e_step():
-            x.copy_(x_host, non_blocking=True)
-            loss = step()
+            cur = state['i'] & 1
+            if not state['primed']:                          # first step of a region: nothing was prefetched
+                upload(cur)
+                state['primed'] = True
+            state['left'] -= 1
+            if state['left'] > 0:
+                upload(cur ^ 1)                              # next step's features, overlapped with this step
+            torch.cuda.current_stream().wait_event(copied[cur])
+            loss = step(bufs[cur])
+            consumed[cur].record()
             result.copy_(loss.detach().reshape(1), non_blocking=True)
+            state['i'] += 1
 
-        for _ in range(2):
-            e2e_step()
-        ms_e2e = timed(e2e_step, max(2, min(a.steps, 5)))
+        def e2e_region(steps):
+            # exactly one upload per step; the first one of a region is fully exposed
+            state['primed'], state['left'] = False, steps
+            torch.cuda.synchronize()
+            for ev in consumed:
+                ev.record()
+            return timed(e2e_step, steps)
+
+        e2e_region(2)
+        e2e_steps = max(2, a.steps)
+        ms_e2e = e2e_region(e2e_steps)
         e2e = {'value': 2 * L * E / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': rows * d * 4 * world,
-               'd2h_bytes_per_step': 4 * world, 'ms_per_step': ms_e2e,
-               'what': 'features copied from pinned host memory each step, loss read back to the host'}
-        del x_host
+               'd2h_bytes_per_step': 4 * world, 'ms_per_step': ms_e2e, 'steps': e2e_steps,
+               'h2d_copies_in_region': e2e_steps,
+               'what': 'features copied from pinned host memory every step (double-buffered, the copy of step '
+                       'i+1 overlaps step i on a side stream), loss read back to the host'}
+        del x_host, bufs
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -85,12 +85,12 @@ class GCNConv(nn.Module):
                            'weight parameter. Please create the module with flag weight=False.')
         return weight if weight is not None else self.weight
 
-    def _transform(self, graph, feat, weight, row_scale=None):
+    def _transform(self, graph, feat, weight, row_scale=None, dx_sink=None):
         """row_scale * (X W) + E  ( = (D_out^-1/2 X) W + E, GCN.py:205-231) and the SE regulariser
         (GCN.py:232-236).  One tcgen05 GEMM with the scale and the SE add in its epilogue."""
         le = self.le if self.whetherHasSE else None
         if weight is not None:
-            h, _ = _ops.dense(feat, weight, 'kn', add=le, row_scale=row_scale)
+            h, _ = _ops.dense(feat, weight, 'kn', add=le, row_scale=row_scale, dx_sink=dx_sink)
         else:
             h = feat if row_scale is None else _ops.row_scale(feat, row_scale)
             if le is not None:
@@ -98,7 +98,7 @@ class GCNConv(nn.Module):
         return h, (_ops.frob_norm(self.le, graph) if self.whetherHasSE else None)
 
     def fused(self, graph, feat, prescaled=False, relu=False, x0=None, alpha=0.0, want_out=True,
-              want_scaled=False, weight=None):
+              want_scaled=False, weight=None, x0_sink=None, dx_sink=None):
         """The whole layer plus what follows it in TricksComb, norm='both' only.
 
         feat        layer input; if ``prescaled`` it already carries the D_out^-1/2 factor
@@ -108,8 +108,9 @@ class GCNConv(nn.Module):
         """
         assert self._norm == 'both'
         weight = self._check(graph, weight)
-        h, se_reg = self._transform(graph, feat, weight, None if prescaled else graph.dout_inv_sqrt)
-        out, out_scaled = _ops.fused_aggregate(h, graph, self.bias, x0, alpha, relu, want_out, want_scaled)
+        h, se_reg = self._transform(graph, feat, weight, None if prescaled else graph.dout_inv_sqrt, dx_sink)
+        out, out_scaled = _ops.fused_aggregate(h, graph, self.bias, x0, alpha, relu, want_out, want_scaled,
+                                               x0_sink)
         return out, out_scaled, se_reg
 
     def forward(self, graph, feat, weight=None, edge_weight=None):
@@ -206,13 +207,17 @@ class TricksComb(nn.Module):
             self.dglgraph = self.build_graph(x, edge_index)
         graph = self.dglgraph
         trick, L = self.type_trick, self.num_layers
-        x_list, le_collection, se_reg_all = [], [], None
+        x_list, le_collection, se_reg_all, x0_sink = [], [], None, None
         self.graph_dropout(edge_index)  # result unused by the layers, exactly like GCN.py:101-115
 
         if self.has_residual_MLP:
             x = F.dropout(x, p=self.embedding_dropout, training=self.training)
             lin = self.layers_MLP[0]
             x, _ = _ops.dense(x, lin.weight, 'nk', bias=lin.bias, relu=True)
+            if AcontainsB(self.type_trick, ['Initial']) and x.requires_grad:
+                # x0 feeds every layer's residual mix: collect those gradients inside the backward kernels
+                x0_sink = _ops.GradSink()
+                x = _ops.sink_hub(x, x0_sink)
             x_list.append(x)
 
         norm_runs = norm_is_executed(trick)
@@ -225,7 +230,7 @@ class TricksComb(nn.Module):
         for i in range(L):
             x_in = None
             if xs_next is None:
-                x_in = F.dropout(x, p=self.dropout, training=self.training)
+                x_in = x if no_drop else F.dropout(x, p=self.dropout, training=self.training)
             layer = self.layers_GCN[i]
             want_relu = self.has_residual_MLP or i < L - 1
             # the epilogue (relu, Initial mix) can ride on the aggregation kernel unless a norm layer
@@ -239,7 +244,9 @@ class TricksComb(nn.Module):
             out, out_scaled, se_reg = layer.fused(
                 graph, xs_next if xs_next is not None else x_in, prescaled=xs_next is not None,
                 relu=relu_fused, x0=x_list[0] if mix_fused else None, alpha=self.alpha,
-                want_out=need_plain, want_scaled=feeds_conv)
+                want_out=need_plain, want_scaled=feeds_conv, x0_sink=x0_sink if mix_fused else None,
+                # layer 0 reads x0 itself: its dX GEMM adds the parked residual gradients in its epilogue
+                dx_sink=x0_sink if (x0_sink is not None and x_in is not None and x_in is x_list[0]) else None)
             if se_reg is not None:
                 se_reg_all = se_reg if se_reg_all is None else se_reg_all + se_reg
             x = out

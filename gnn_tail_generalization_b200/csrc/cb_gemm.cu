@@ -323,16 +323,30 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
                 __syncwarp();
                 const int col = n0 + j * 32 + c4 * 4;
+                const bool col_ok = col < g.N;
                 float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g.bias && col < g.N) bv = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+                if (g.bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+                // all global reads of the slab are issued before the first store (stores may alias in the
+                // compiler's eyes, which would otherwise serialise one load latency per row group)
+                float4 ev[8];
+                float rsv[8], s2v[8];
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr) {
+                    const int64_t row = row0 + itr * 4 + rsub;
+                    const bool ok = col_ok && row < g.M;
+                    ev[itr] = (g.add && ok) ? __ldg(reinterpret_cast<const float4*>(g.add + row * g.ld_add + col))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                    rsv[itr] = (g.row_scale && ok) ? __ldg(g.row_scale + row) : 1.f;
+                    s2v[itr] = (g.out2 && ok) ? __ldg(g.out2_scale + row) : 1.f;
+                }
 #pragma unroll
                 for (int itr = 0; itr < 8; ++itr) {
                     const int rr = itr * 4 + rsub;
                     const int64_t row = row0 + rr;
                     float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + 4 * c4);
-                    if (row < g.M && col < g.N) {
+                    if (row < g.M && col_ok) {
                         if (g.row_scale) {
-                            const float rs = __ldg(g.row_scale + row);
+                            const float rs = rsv[itr];
                             v.x = __fmul_rn(v.x, rs); v.y = __fmul_rn(v.y, rs);
                             v.z = __fmul_rn(v.z, rs); v.w = __fmul_rn(v.w, rs);
                         }
@@ -341,7 +355,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                             v.z = __fadd_rn(v.z, bv.z); v.w = __fadd_rn(v.w, bv.w);
                         }
                         if (g.add) {
-                            const float4 e = __ldg(reinterpret_cast<const float4*>(g.add + row * g.ld_add + col));
+                            const float4 e = ev[itr];
                             v.x = __fadd_rn(v.x, e.x); v.y = __fadd_rn(v.y, e.y);
                             v.z = __fadd_rn(v.z, e.z); v.w = __fadd_rn(v.w, e.w);
                         }
@@ -349,12 +363,12 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
                             v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                         }
-                        if (g.out) *reinterpret_cast<float4*>(g.out + row * g.ld_out + col) = v;
+                        if (g.out) __stcs(reinterpret_cast<float4*>(g.out + row * g.ld_out + col), v);
                         if (g.out2) {
-                            const float s2 = __ldg(g.out2_scale + row);
+                            const float s2 = s2v[itr];
                             v.x = __fmul_rn(v.x, s2); v.y = __fmul_rn(v.y, s2);
                             v.z = __fmul_rn(v.z, s2); v.w = __fmul_rn(v.w, s2);
-                            *reinterpret_cast<float4*>(g.out2 + row * g.ld_out2 + col) = v;
+                            __stcs(reinterpret_cast<float4*>(g.out2 + row * g.ld_out2 + col), v);
                         }
                     }
                 }

@@ -15,7 +15,7 @@ _timing_sink = None
 
 
 def set_timing_sink(sink):
-    """``sink`` is a list that receives (name, start_event, end_event, algorithmic_bytes) per kernel
+    """``sink`` is a list that receives (name, start_event, end_event, algorithmic_bytes, flops) per kernel
     call, or None to switch the probe off.  Events are recorded on the stream the kernel runs on."""
     global _timing_sink
     _timing_sink = sink
@@ -35,7 +35,7 @@ class _Timed:
     def __exit__(self, *exc):
         if _timing_sink is not None and exc[0] is None:
             self.t1.record(torch.cuda.current_stream(self.device))
-            _timing_sink.append((self.name, self.t0, self.t1, self.bytes))
+            _timing_sink.append((self.name, self.t0, self.t1, self.bytes, self.flops))
         return False
 
 
@@ -106,22 +106,27 @@ def agg_gather_raw(graph, side, X, row_scale=None):
     return out
 
 
-def backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, relu, mixed, alpha, want_bias, want_x0):
+def backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, relu, mixed, alpha, want_bias, want_x0,
+                      d_x0_accum=None):
+    """d_x0_accum: an existing [rows, d] buffer that receives ``+= alpha * dtot`` instead of a fresh d_x0."""
     ref = d_out if d_out is not None else d_out_scaled
     _need_cuda(ref)
     d_out, d_out_scaled, relu_out = _f32c(d_out), _f32c(d_out_scaled), _f32c(relu_out)
     rows, d = ref.shape
     G = torch.empty((rows, d), dtype=torch.float32, device=ref.device)
     d_bias = torch.empty(d, dtype=torch.float32, device=ref.device) if want_bias else None
-    d_x0 = torch.empty((rows, d), dtype=torch.float32, device=ref.device) if want_x0 else None
+    accumulate = int(want_x0 and d_x0_accum is not None)
+    d_x0 = (d_x0_accum if accumulate else torch.empty((rows, d), dtype=torch.float32, device=ref.device)) \
+        if want_x0 else None
     ws_bytes = int(C.lib().cb_prep_workspace_bytes(rows, d)) if want_bias else 0
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ref.device) if ws_bytes else None
-    mats = int(d_out is not None) + int(d_out_scaled is not None) + 1 + int(want_x0) + int(relu_out is not None)
+    mats = int(d_out is not None) + int(d_out_scaled is not None) + 1 + int(want_x0) + accumulate + \
+        int(relu_out is not None)
     alg = mats * rows * d * 4 + (rows * d if mask is not None else 0) + 2 * rows * 4
     with torch.cuda.device(ref.device), _Timed('backward_prep', alg, ref.device):
         C.call('cb_agg_backward_prep', graph.handle, C.ptr(d_out), C.ptr(d_out_scaled), d, C.ptr(mask),
                C.ptr(relu_out), C.CB_ACT_RELU if relu else C.CB_ACT_NONE, int(bool(mixed)), float(alpha),
-               C.ptr(G), C.ptr(d_bias), C.ptr(d_x0), 0, C.ptr(ws), ws_bytes, C.stream_ptr(ref.device))
+               C.ptr(G), C.ptr(d_bias), C.ptr(d_x0), accumulate, C.ptr(ws), ws_bytes, C.stream_ptr(ref.device))
     return G, d_bias, d_x0
 
 
@@ -269,6 +274,44 @@ def frob_norm(e, graph=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# gradient sink: the Initial residual x0 feeds every layer (res_tricks.py:23), so autograd would add
+# one [N, d] gradient per consumer with separate full passes.  The fused backward kernels instead
+# accumulate their contributions in place into one buffer, which the last consumer folds into its own
+# GEMM epilogue (or, failing that, the hub adds once).
+# ---------------------------------------------------------------------------------------------
+class GradSink:
+    __slots__ = ('buf',)
+
+    def __init__(self):
+        self.buf = None
+
+    def take(self):
+        b, self.buf = self.buf, None
+        return b
+
+
+class _SinkHub(torch.autograd.Function):
+    """Identity on the shared tensor; its backward adds whatever is still parked in the sink."""
+
+    @staticmethod
+    def forward(ctx, x, sink):
+        ctx.sink = sink
+        ctx.set_materialize_grads(False)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        parked = ctx.sink.take()
+        if parked is not None:
+            g = parked if g is None else g + parked
+        return g, None
+
+
+def sink_hub(x, sink):
+    return _SinkHub.apply(x, sink)
+
+
+# ---------------------------------------------------------------------------------------------
 # dense transform: act(row_scale * (x @ W) + bias + add) with the tcgen05 kernels, cuBLAS for the
 # shapes they do not cover (N or K not a multiple of 4; weight gradient: not a multiple of 32)
 # ---------------------------------------------------------------------------------------------
@@ -303,7 +346,8 @@ def _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, 
 
 class _Dense(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, add, row_scale, out2_scale, layout, relu, want_out, want_out2):
+    def forward(ctx, x, weight, bias, add, row_scale, out2_scale, layout, relu, want_out, want_out2, dx_sink):
+        ctx.dx_sink = dx_sink
         wt = split_weight(weight, transpose=(layout == 'kn'))
         res = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2)
         out, out2 = res if want_out2 else (res, None)
@@ -324,7 +368,7 @@ class _Dense(torch.autograd.Function):
         if dy2 is not None and dy2.numel() == 0:
             dy2 = None
         if dy is None and dy2 is None:
-            return (None,) * 10
+            return (None,) * 11
         if dy2 is not None:
             dy2 = dy2 * out2_scale[:, None]
         dtot = dy2 if dy is None else (dy if dy2 is None else dy + dy2)
@@ -337,13 +381,16 @@ class _Dense(torch.autograd.Function):
         N = dtot.shape[1]
         dx = dw = None
         if ctx.needs_input_grad[0]:
+            parked = ctx.dx_sink.take() if ctx.dx_sink is not None else None   # other consumers' share of dx
             if gemm_supported(M, K, N):
                 wb = split_weight(weight, transpose=(ctx.layout == 'nk'))
-                dx = gemm_rows_raw(dtot, wb, row_scale=row_scale)
+                dx = gemm_rows_raw(dtot, wb, row_scale=row_scale, add=parked)
             else:
                 dx = dtot @ _w_as_kn(weight, ctx.layout).t()
                 if row_scale is not None:
                     dx = dx * row_scale[:, None]
+                if parked is not None:
+                    dx = dx + parked
         if ctx.needs_input_grad[1]:
             if gemm_tn_supported(M, K, N):
                 dw = gemm_tn_raw(x, dtot, a_row_scale=row_scale) if ctx.layout == 'kn' else \
@@ -351,11 +398,11 @@ class _Dense(torch.autograd.Function):
             else:
                 xs = x if row_scale is None else x * row_scale[:, None]
                 dw = xs.t() @ dtot if ctx.layout == 'kn' else dtot.t() @ xs
-        return dx, dw, d_bias, d_add, None, None, None, None, None, None
+        return dx, dw, d_bias, d_add, None, None, None, None, None, None, None
 
 
 def dense(x, weight, layout, bias=None, add=None, relu=False, row_scale=None, out2_scale=None, want_out=True,
-          want_out2=False):
+          want_out2=False, dx_sink=None):
     """act(row_scale[:,None] * (x @ W) + bias + add); also out2_scale[:,None] * that when want_out2.
     layout 'kn': weight is [in, out] (GCNConv.weight, GCN.py:170); 'nk': [out, in] (nn.Linear.weight).
     Returns (out, out2); the one not asked for is None."""
@@ -363,7 +410,7 @@ def dense(x, weight, layout, bias=None, add=None, relu=False, row_scale=None, ou
     N = weight.shape[1] if layout == 'kn' else weight.shape[0]
     if _dense_backend == 'tcgen05' and x.is_cuda and M > 0 and gemm_supported(M, N, K):
         out, out2 = _Dense.apply(x, weight, bias, add, row_scale, out2_scale, layout, bool(relu), bool(want_out),
-                                 bool(want_out2))
+                                 bool(want_out2), dx_sink)
         return (out if want_out else None), (out2 if want_out2 else None)
     _need_cuda(x)
     return _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, want_out, want_out2)
@@ -377,7 +424,8 @@ class _FusedAggregate(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, H, bias, x0, graph, alpha, relu, want_out, want_scaled):
+    def forward(ctx, H, bias, x0, graph, alpha, relu, want_out, want_scaled, x0_sink):
+        ctx.x0_sink = x0_sink
         mixed = x0 is not None
         need_grad = any(ctx.needs_input_grad[:3])
         # relu mask source for backward: the plain relu output doubles as the mask when nothing was
@@ -405,23 +453,28 @@ class _FusedAggregate(torch.autograd.Function):
         if d_out_scaled is not None and d_out_scaled.numel() == 0:
             d_out_scaled = None
         if d_out is None and d_out_scaled is None:
-            return (None,) * 8
+            return (None,) * 9
         want_bias = ctx.has_bias and ctx.needs_input_grad[1]
         want_x0 = ctx.mixed and ctx.needs_input_grad[2]
+        sink = ctx.x0_sink if want_x0 else None
         G, d_bias, d_x0 = backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, ctx.relu, ctx.mixed,
-                                            ctx.alpha, want_bias, want_x0)
+                                            ctx.alpha, want_bias, want_x0,
+                                            d_x0_accum=sink.buf if sink is not None else None)
+        if sink is not None:   # parked for the hub / the last consumer's GEMM epilogue
+            sink.buf, d_x0 = d_x0, None
         dH = None
         if ctx.needs_input_grad[0]:
             dH = agg_gather_raw(graph, C.CB_BY_SRC, graph.exchange(G), None)
-        return dH, d_bias, d_x0, None, None, None, None, None
+        return dH, d_bias, d_x0, None, None, None, None, None, None
 
 
-def fused_aggregate(H, graph, bias=None, x0=None, alpha=0.0, relu=False, want_out=True, want_scaled=False):
+def fused_aggregate(H, graph, bias=None, x0=None, alpha=0.0, relu=False, want_out=True, want_scaled=False,
+                    x0_sink=None):
     """Returns (out, out_scaled); the one not asked for is None."""
     if not (want_out or want_scaled):
         raise ValueError('fused_aggregate: nothing requested')
     out, out_scaled = _FusedAggregate.apply(H, bias, x0, graph, float(alpha), bool(relu), bool(want_out),
-                                            bool(want_scaled))
+                                            bool(want_scaled), x0_sink)
     return (out if want_out else None), (out_scaled if want_scaled else None)
 
 

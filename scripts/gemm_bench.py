@@ -16,6 +16,10 @@ for (M, K, N) in [(10_000_000, 256, 256), (10_000_000, 256, 64), (10_000_000, 64
     ref = A[:4096].double() @ W.double().t()
     err = float((out[:4096].double() - ref).abs().max()); errc = float(((A[:4096] @ W.t()).double() - ref).abs().max())
     ms = t(lambda: ops.gemm_rows_raw(A, wt)); msc = t(lambda: A @ W.t())
+    if N == 256 and K == 256:
+        add = torch.randn(M, N, device='cuda'); rs = torch.rand(M, device='cuda')
+        print('   with row_scale+add: %.2f ms; with bias+relu: %.2f ms' % (t(lambda: ops.gemm_rows_raw(A, wt, row_scale=rs, add=add)), t(lambda: ops.gemm_rows_raw(A, wt, bias=rs[:N].contiguous(), relu=True))), flush=True)
+        del add
     fl = 2 * M * K * N
     print(f'M={M} K={K} N={N}: ours {ms:.2f} ms ({fl/ms/1e9:.1f} TF/s fp32-equiv, {4*(M*K+M*N)/ms/1e6:.0f} GB/s) cublas fp32 {msc:.2f} ms  err ours {err:.2e} cublas {errc:.2e}', flush=True)
     del A, out

@@ -1,0 +1,74 @@
+"""world_size=2 coverage of the node-sliced path's host logic on CPU (gloo): slice bounds, the per-aggregation
+row exchange, the dense-gradient all-reduce and the sharded Frobenius norm, against the single-process oracle."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import coldbrew_oracle as O
+from gnn_tail_generalization_b200 import dist as cbdist
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, d, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        ei = O.powerlaw_graph(n, 4 * n, seed=0)
+        H = torch.randn(n, d, generator=torch.Generator().manual_seed(1))
+        lo, hi = cbdist.slice_bounds(n, world, rank)
+        # forward: exchange the row blocks, aggregate the owned destination rows only
+        full = cbdist.exchange_rows(H[lo:hi].clone(), n, world)
+        assert torch.equal(full, H)
+        src, dst = ei
+        keep = (dst >= lo) & (dst < hi)
+        mine = torch.zeros(hi - lo, d).index_add_(0, dst[keep] - lo, full[src[keep]])
+        want = O.aggregate_sum(H, ei, n)[lo:hi]
+        assert torch.allclose(mine, want, rtol=1e-6, atol=1e-6)
+        # backward: owned source rows gather from the exchanged gradient rows
+        keep_s = (src >= lo) & (src < hi)
+        back = torch.zeros(hi - lo, d).index_add_(0, src[keep_s] - lo, full[dst[keep_s]])
+        want_b = torch.zeros(n, d).index_add_(0, src, H[dst])[lo:hi]
+        assert torch.allclose(back, want_b, rtol=1e-6, atol=1e-6)
+        # dense gradients are summed over ranks, row-sharded parameters are left alone
+        lin = torch.nn.Linear(4, 3)
+        lin.le = torch.nn.Parameter(torch.zeros(2, 2))
+        holder = torch.nn.Module()
+        holder.layer = lin                                  # parameter names: layer.weight, layer.bias, layer.le
+        for p in lin.parameters():
+            p.grad = torch.full_like(p, float(rank + 1))
+        n_red = cbdist.allreduce_dense_grads(holder, world)
+        assert n_red == 4 * 3 + 3
+        assert torch.equal(lin.weight.grad, torch.full_like(lin.weight, 3.0))
+        assert torch.equal(lin.le.grad, torch.full_like(lin.le, float(rank + 1)))
+        # sharded ||E||_F: sqrt of the all-reduced sum of squares
+        ss = cbdist.allreduce_scalar_sum((H[lo:hi] ** 2).sum().reshape(1), world)
+        assert float(ss.sqrt()) == pytest.approx(float(torch.linalg.vector_norm(H)), rel=1e-5)
+        open(os.path.join(out_dir, f'ok{rank}'), 'w').close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n', [1001, 64])
+def test_world2_exchange_and_reductions(tmp_path, n):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), n, 8, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f'ok{r}') for r in range(world))
+
+
+def test_slice_bounds_cover_everything():
+    for n in (0, 1, 7, 8, 9, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [cbdist.slice_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert cbdist.is_row_sharded('model.model.layers_GCN.0.le') and not cbdist.is_row_sharded('x.weight')

@@ -85,12 +85,12 @@ class GCNConv(nn.Module):
                            'weight parameter. Please create the module with flag weight=False.')
         return weight if weight is not None else self.weight
 
-    def _transform(self, graph, feat, weight, row_scale=None, dx_sink=None):
+    def _transform(self, graph, feat, weight, row_scale=None, dx_sink=None, dx_plan=None):
         """row_scale * (X W) + E  ( = (D_out^-1/2 X) W + E, GCN.py:205-231) and the SE regulariser
         (GCN.py:232-236).  One tcgen05 GEMM with the scale and the SE add in its epilogue."""
         le = self.le if self.whetherHasSE else None
         if weight is not None:
-            h, _ = _ops.dense(feat, weight, 'kn', add=le, row_scale=row_scale, dx_sink=dx_sink)
+            h, _ = _ops.dense(feat, weight, 'kn', add=le, row_scale=row_scale, dx_sink=dx_sink, dx_plan=dx_plan)
         else:
             h = feat if row_scale is None else _ops.row_scale(feat, row_scale)
             if le is not None:
@@ -98,19 +98,22 @@ class GCNConv(nn.Module):
         return h, (_ops.frob_norm(self.le, graph) if self.whetherHasSE else None)
 
     def fused(self, graph, feat, prescaled=False, relu=False, x0=None, alpha=0.0, want_out=True,
-              want_scaled=False, weight=None, x0_sink=None, dx_sink=None):
+              want_scaled=False, weight=None, x0_sink=None, dx_sink=None, my_plan=None, dx_plan=None):
         """The whole layer plus what follows it in TricksComb, norm='both' only.
 
         feat        layer input; if ``prescaled`` it already carries the D_out^-1/2 factor
         relu/x0     epilogue: out = (1-alpha) * relu(z) + alpha * x0
         want_scaled also return D_out^-1/2 * out (the next layer's pre-scaled input)
+        my_plan     BwdPlan for this layer's backward prologue (run by the consumer of its output)
+        dx_plan     BwdPlan of the op that produced ``feat`` (run by this layer's dX GEMM)
         Returns (out, out_scaled, se_reg).
         """
         assert self._norm == 'both'
         weight = self._check(graph, weight)
-        h, se_reg = self._transform(graph, feat, weight, None if prescaled else graph.dout_inv_sqrt, dx_sink)
+        h, se_reg = self._transform(graph, feat, weight, None if prescaled else graph.dout_inv_sqrt, dx_sink,
+                                    dx_plan)
         out, out_scaled = _ops.fused_aggregate(h, graph, self.bias, x0, alpha, relu, want_out, want_scaled,
-                                               x0_sink)
+                                               x0_sink, my_plan)
         return out, out_scaled, se_reg
 
     def forward(self, graph, feat, weight=None, edge_weight=None):
@@ -210,14 +213,20 @@ class TricksComb(nn.Module):
         x_list, le_collection, se_reg_all, x0_sink = [], [], None, None
         self.graph_dropout(edge_index)  # result unused by the layers, exactly like GCN.py:101-115
 
+        # plan of the op whose output is the current x, handed to x's single consumer (see ops.BwdPlan)
+        prev_plan = None
         if self.has_residual_MLP:
             x = F.dropout(x, p=self.embedding_dropout, training=self.training)
             lin = self.layers_MLP[0]
-            x, _ = _ops.dense(x, lin.weight, 'nk', bias=lin.bias, relu=True)
+            lin_plan = _ops.new_plan()
+            x, _ = _ops.dense(x, lin.weight, 'nk', bias=lin.bias, relu=True, my_plan=lin_plan)
             if AcontainsB(self.type_trick, ['Initial']) and x.requires_grad:
                 # x0 feeds every layer's residual mix: collect those gradients inside the backward kernels
                 x0_sink = _ops.GradSink()
                 x = _ops.sink_hub(x, x0_sink)
+                # every gradient of x0 ends in layer 0's dX GEMM (the residual shares are parked in the
+                # sink and added in its epilogue), so that GEMM can also run the Linear's relu/bias backward
+                prev_plan = lin_plan
             x_list.append(x)
 
         norm_runs = norm_is_executed(trick)
@@ -241,12 +250,22 @@ class TricksComb(nn.Module):
             last = i == L - 1
             feeds_conv = (not last) and no_drop and (mix_fused or not mixes) and fuse_tail
             need_plain = last or keeps_history or not feeds_conv
+            # this layer's output has one consumer whose backward is a GEMM: the next conv (pre-scaled
+            # copy only), or the final Linear (plain output, nothing in between)
+            single_consumer = fuse_tail and not keeps_history and (
+                (feeds_conv and not need_plain) or
+                (last and self.has_residual_MLP and not AcontainsB(trick, ['Jumping']) and
+                 (mix_fused or not mixes) and ((not self.training) or self.args.dropout == 0)))
+            my_plan = _ops.new_plan() if single_consumer else None
+            dx_plan = prev_plan if (xs_next is not None or (x_in is not None and x_in is x)) else None
             out, out_scaled, se_reg = layer.fused(
                 graph, xs_next if xs_next is not None else x_in, prescaled=xs_next is not None,
                 relu=relu_fused, x0=x_list[0] if mix_fused else None, alpha=self.alpha,
                 want_out=need_plain, want_scaled=feeds_conv, x0_sink=x0_sink if mix_fused else None,
                 # layer 0 reads x0 itself: its dX GEMM adds the parked residual gradients in its epilogue
-                dx_sink=x0_sink if (x0_sink is not None and x_in is not None and x_in is x_list[0]) else None)
+                dx_sink=x0_sink if (x0_sink is not None and x_in is not None and x_in is x_list[0]) else None,
+                my_plan=my_plan, dx_plan=dx_plan)
+            prev_plan = my_plan
             if se_reg is not None:
                 se_reg_all = se_reg if se_reg_all is None else se_reg_all + se_reg
             x = out
@@ -267,7 +286,7 @@ class TricksComb(nn.Module):
                 x = self.layers_res[0](x_list)
             else:
                 lin = self.layers_MLP[-1]
-                x, _ = _ops.dense(x, lin.weight, 'nk', bias=lin.bias)
+                x, _ = _ops.dense(x, lin.weight, 'nk', bias=lin.bias, dx_plan=prev_plan)
         if want_les:
             return x, se_reg_all, th.cat(le_collection, dim=-1)
         return x, se_reg_all

@@ -42,6 +42,9 @@ SYMBOLS = {
     'cb_gemm_rows_supported': (_int, [_i64, _i64, _i64]),
     'cb_gemm_rows': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _int, _vp, _i64, _vp, _vp,
                             _i64, _vp]),
+    'cb_gemm_rows_grad_workspace_bytes': (_i64, [_i64, _i64]),
+    'cb_gemm_rows_grad': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _int, _dbl,
+                                 _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     'cb_gemm_tn_supported': (_int, [_i64, _i64, _i64]),
     'cb_gemm_tn_workspace_bytes': (_i64, [_i64, _i64, _i64]),
     'cb_gemm_tn': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp, _i64, _vp, _i64, _vp]),

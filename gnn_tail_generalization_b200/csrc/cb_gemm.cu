@@ -45,7 +45,8 @@ struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
     static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES;
+    static constexpr int CS_BYTES = 4 * BN * 4;   // per-epilogue-warp column sums (gradient epilogue)
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES + CS_BYTES;
     static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;  // barriers + alignment slack
     static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -64,6 +65,17 @@ struct GemmArgs {
     float* out2;             // [M, ld_out2] or null
     int64_t ld_out2;
     int64_t n_tiles_m;
+    // ---- gradient epilogue (k_gemm_rows<BN, true>): the backward prologue of the layer below ----
+    const uint8_t* gate_u8;   // [M, ld_gate] relu mask bytes, or null
+    const float* gate_f32;    // [M, ld_gate] relu output (gate = value > 0), or null
+    int64_t ld_gate;
+    int mixed;                // dz = (1-alpha) * dtot when the layer output was mixed with x0
+    float alpha, one_minus_alpha;
+    float* d_x0;              // [M, ld_dx0] (+)= alpha * dtot, or null
+    int64_t ld_dx0;
+    int accumulate_x0;
+    const float* post_scale;  // [M] scale of the stored value (din^-1/2), or null
+    float* col_partial;       // [gridDim.x, N] per-CTA column sums of dz, or null
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
@@ -98,6 +110,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+// Pull [ptr, ptr + bytes) into L2 (bytes a multiple of 16): the epilogue's streamed operands are requested one
+// tile ahead so that its loads hit L2 instead of waiting a DRAM round trip with few bytes in flight.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+// rows [r0, r0 + nrows) x cols [c0, c0 + ncols) of a row-major matrix with `ld` elements per row
+__device__ __forceinline__ void l2_prefetch_rows(const void* base, int elem_bytes, int64_t ld, int64_t r0, int nrows,
+                                                 int c0, int ncols, int lane) {
+    const char* p = reinterpret_cast<const char*>(base) + (r0 * ld + c0) * elem_bytes;
+    if (c0 == 0 && ncols == ld) {                       // the rows are one contiguous block: 16 KB pieces
+        const int64_t total = (int64_t)nrows * ld * elem_bytes;
+        for (int64_t o = (int64_t)lane * 16384; o < total; o += 32 * 16384)
+            l2_prefetch_bulk(p + o, (uint32_t)(total - o < 16384 ? total - o : 16384));
+    } else {
+        for (int r = lane; r < nrows; r += 32) l2_prefetch_bulk(p + (int64_t)r * ld * elem_bytes, (uint32_t)(ncols * elem_bytes));
+    }
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -159,7 +188,7 @@ __device__ __forceinline__ constexpr uint32_t instr_desc_tf32() {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool GRAD>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
             const __grid_constant__ CUtensorMap map_blo, const GemmArgs g) {
@@ -219,6 +248,17 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // ===== TMA producer =====
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x) {
+            {   // epilogue operands of this tile -> L2 (the epilogue reads them about one tile later)
+                const int64_t r0 = tile * BM;
+                const int nr = (int)(g.M - r0 < BM ? g.M - r0 : BM);
+                const int nc = g.N - n0 < BN ? g.N - n0 : BN;
+                if (g.add) l2_prefetch_rows(g.add, 4, g.ld_add, r0, nr, n0, nc, lane);
+                if (GRAD) {
+                    if (g.d_x0 && g.accumulate_x0) l2_prefetch_rows(g.d_x0, 4, g.ld_dx0, r0, nr, n0, nc, lane);
+                    if (g.gate_u8) l2_prefetch_rows(g.gate_u8, 1, g.ld_gate, r0, nr, n0, nc, lane);
+                    if (g.gate_f32) l2_prefetch_rows(g.gate_f32, 4, g.ld_gate, r0, nr, n0, nc, lane);
+                }
+            }
             for (int kc = 0; kc < nk; ++kc, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
@@ -300,6 +340,12 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         float* stg = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES) + q * 32 * STG_LD;
         const int rsub = lane >> 3;  // 0..3
         const int c4 = lane & 7;     // 0..7
+        // GRAD: running column sums of dz over all tiles of the CTA, one row of BN floats per epilogue warp
+        float* csw = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES + C::STG_BYTES) + q * BN;
+        if (GRAD) {
+            for (int c = lane; c < BN; c += 32) csw[c] = 0.f;
+            __syncwarp();
+        }
         uint32_t tl = 0;
         for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x, ++tl) {
             const int acc = tl & 1u;
@@ -324,55 +370,228 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 __syncwarp();
                 const int col = n0 + j * 32 + c4 * 4;
                 const bool col_ok = col < g.N;
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g.bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(g.bias + col));
-                // all global reads of the slab are issued before the first store (stores may alias in the
-                // compiler's eyes, which would otherwise serialise one load latency per row group)
-                float4 ev[8];
-                float rsv[8], s2v[8];
+                if (GRAD) {
+                    // dtot = rs*acc + add ; d_x0 (+)= alpha*dtot ; dz = [(1-alpha)*] dtot * gate ; out = ps*dz
+                    // (same operations, in the same order, as cb_gemm_rows followed by cb_agg_backward_prep).
+                    // Every option is a uniform branch around a straight pass over the lane's 8 x float4
+                    // register tile, so no per-element predicates are executed; rows are valid for itr < nval.
+                    const int64_t rbase = row0 + rsub;
+                    const int64_t left = (g.M - rbase + 3) >> 2;
+                    const int nval = !col_ok || left <= 0 ? 0 : (left < 8 ? (int)left : 8);
+                    float4 av[8], gy[8];      // add or old d_x0 (mutually exclusive); fp32 gate source
+                    float rsv[8], psv[8];
+                    uint32_t gm[8];
+                    const bool acc_x0 = g.d_x0 && g.accumulate_x0;
+                    if (g.add || acc_x0) {
+                        const int64_t ld = g.add ? g.ld_add : g.ld_dx0;
+                        const float* p = (g.add ? g.add : g.d_x0) + rbase * ld + col;
 #pragma unroll
-                for (int itr = 0; itr < 8; ++itr) {
-                    const int64_t row = row0 + itr * 4 + rsub;
-                    const bool ok = col_ok && row < g.M;
-                    ev[itr] = (g.add && ok) ? __ldg(reinterpret_cast<const float4*>(g.add + row * g.ld_add + col))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-                    rsv[itr] = (g.row_scale && ok) ? __ldg(g.row_scale + row) : 1.f;
-                    s2v[itr] = (g.out2 && ok) ? __ldg(g.out2_scale + row) : 1.f;
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nval) av[itr] = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)itr * 4 * ld));
+                    }
+                    if (g.gate_u8) {
+                        const uint8_t* p = g.gate_u8 + rbase * g.ld_gate + col;
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nval) gm[itr] = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)itr * 4 * g.ld_gate));
+                    } else if (g.gate_f32) {
+                        const float* p = g.gate_f32 + rbase * g.ld_gate + col;
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nval) gy[itr] = __ldg(reinterpret_cast<const float4*>(p + (int64_t)itr * 4 * g.ld_gate));
+                    }
+                    if (g.row_scale) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nval) rsv[itr] = __ldg(g.row_scale + rbase + itr * 4);
+                    }
+                    if (g.post_scale) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nval) psv[itr] = __ldg(g.post_scale + rbase + itr * 4);
+                    }
+                    float4 v[8];
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        v[itr] = *reinterpret_cast<const float4*>(stg + (itr * 4 + rsub) * STG_LD + 4 * c4);
+                    if (g.row_scale) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const float r_ = rsv[itr];
+                            v[itr].x = __fmul_rn(r_, v[itr].x); v[itr].y = __fmul_rn(r_, v[itr].y);
+                            v[itr].z = __fmul_rn(r_, v[itr].z); v[itr].w = __fmul_rn(r_, v[itr].w);
+                        }
+                    }
+                    if (g.add) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            v[itr].x = __fadd_rn(v[itr].x, av[itr].x); v[itr].y = __fadd_rn(v[itr].y, av[itr].y);
+                            v[itr].z = __fadd_rn(v[itr].z, av[itr].z); v[itr].w = __fadd_rn(v[itr].w, av[itr].w);
+                        }
+                    }
+                    if (g.d_x0) {
+                        float* p = g.d_x0 + rbase * g.ld_dx0 + col;
+                        const float al = g.alpha;
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            float4 x = make_float4(__fmul_rn(al, v[itr].x), __fmul_rn(al, v[itr].y),
+                                                   __fmul_rn(al, v[itr].z), __fmul_rn(al, v[itr].w));
+                            if (acc_x0) {
+                                x.x = __fadd_rn(av[itr].x, x.x); x.y = __fadd_rn(av[itr].y, x.y);
+                                x.z = __fadd_rn(av[itr].z, x.z); x.w = __fadd_rn(av[itr].w, x.w);
+                            }
+                            if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_dx0), x);
+                        }
+                    }
+                    if (g.mixed) {
+                        const float om = g.one_minus_alpha;
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            v[itr].x = __fmul_rn(om, v[itr].x); v[itr].y = __fmul_rn(om, v[itr].y);
+                            v[itr].z = __fmul_rn(om, v[itr].z); v[itr].w = __fmul_rn(om, v[itr].w);
+                        }
+                    }
+                    if (g.gate_u8) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const uint32_t m = gm[itr];
+                            v[itr].x = (m & 0xffu) ? v[itr].x : 0.f;       v[itr].y = (m & 0xff00u) ? v[itr].y : 0.f;
+                            v[itr].z = (m & 0xff0000u) ? v[itr].z : 0.f;   v[itr].w = (m & 0xff000000u) ? v[itr].w : 0.f;
+                        }
+                    } else if (g.gate_f32) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            v[itr].x = gy[itr].x > 0.f ? v[itr].x : 0.f; v[itr].y = gy[itr].y > 0.f ? v[itr].y : 0.f;
+                            v[itr].z = gy[itr].z > 0.f ? v[itr].z : 0.f; v[itr].w = gy[itr].w > 0.f ? v[itr].w : 0.f;
+                        }
+                    }
+                    if (g.col_partial) {
+                        if (nval < 8) {
+#pragma unroll
+                            for (int itr = 0; itr < 8; ++itr)
+                                if (itr >= nval) v[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        float4 cs = v[0];
+#pragma unroll
+                        for (int itr = 1; itr < 8; ++itr) {
+                            cs.x += v[itr].x; cs.y += v[itr].y; cs.z += v[itr].z; cs.w += v[itr].w;
+                        }
+                        // lanes with equal c4 (rsub = 0..3) are added in rsub order; lane rsub == 0 owns the
+                        // warp's running sum of those columns
+                        const float c_[4] = {cs.x, cs.y, cs.z, cs.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float t1 = __shfl_sync(0xffffffffu, c_[i], c4 + 8);
+                            const float t2 = __shfl_sync(0xffffffffu, c_[i], c4 + 16);
+                            const float t3 = __shfl_sync(0xffffffffu, c_[i], c4 + 24);
+                            if (rsub == 0) csw[j * 32 + c4 * 4 + i] += ((c_[i] + t1) + t2) + t3;
+                        }
+                    }
+                    if (g.post_scale) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const float p_ = psv[itr];
+                            v[itr].x = __fmul_rn(p_, v[itr].x); v[itr].y = __fmul_rn(p_, v[itr].y);
+                            v[itr].z = __fmul_rn(p_, v[itr].z); v[itr].w = __fmul_rn(p_, v[itr].w);
+                        }
+                    }
+                    {
+                        float* p = g.out + rbase * g.ld_out + col;
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_out), v[itr]);
+                    }
+                    __syncwarp();
+                    continue;
                 }
+                {
+                    // forward epilogue, same structure: v = act(rs*acc + bias + add); out = v; out2 = s2*v
+                    const int64_t rbase = row0 + rsub;
+                    const int64_t left = (g.M - rbase + 3) >> 2;
+                    const int nval = !col_ok || left <= 0 ? 0 : (left < 8 ? (int)left : 8);
+                    float4 av[8];
+                    float rsv[8], s2v[8];
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g.bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+                    if (g.add) {
+                        const float* p = g.add + rbase * g.ld_add + col;
 #pragma unroll
-                for (int itr = 0; itr < 8; ++itr) {
-                    const int rr = itr * 4 + rsub;
-                    const int64_t row = row0 + rr;
-                    float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + 4 * c4);
-                    if (row < g.M && col_ok) {
-                        if (g.row_scale) {
-                            const float rs = rsv[itr];
-                            v.x = __fmul_rn(v.x, rs); v.y = __fmul_rn(v.y, rs);
-                            v.z = __fmul_rn(v.z, rs); v.w = __fmul_rn(v.w, rs);
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nval) av[itr] = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)itr * 4 * g.ld_add));
+                    }
+                    if (g.row_scale) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nval) rsv[itr] = __ldg(g.row_scale + rbase + itr * 4);
+                    }
+                    if (g.out2) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nval) s2v[itr] = __ldg(g.out2_scale + rbase + itr * 4);
+                    }
+                    float4 v[8];
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        v[itr] = *reinterpret_cast<const float4*>(stg + (itr * 4 + rsub) * STG_LD + 4 * c4);
+                    if (g.row_scale) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const float r_ = rsv[itr];
+                            v[itr].x = __fmul_rn(v[itr].x, r_); v[itr].y = __fmul_rn(v[itr].y, r_);
+                            v[itr].z = __fmul_rn(v[itr].z, r_); v[itr].w = __fmul_rn(v[itr].w, r_);
                         }
-                        if (g.bias) {
-                            v.x = __fadd_rn(v.x, bv.x); v.y = __fadd_rn(v.y, bv.y);
-                            v.z = __fadd_rn(v.z, bv.z); v.w = __fadd_rn(v.w, bv.w);
+                    }
+                    if (g.bias) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            v[itr].x = __fadd_rn(v[itr].x, bv.x); v[itr].y = __fadd_rn(v[itr].y, bv.y);
+                            v[itr].z = __fadd_rn(v[itr].z, bv.z); v[itr].w = __fadd_rn(v[itr].w, bv.w);
                         }
-                        if (g.add) {
-                            const float4 e = ev[itr];
-                            v.x = __fadd_rn(v.x, e.x); v.y = __fadd_rn(v.y, e.y);
-                            v.z = __fadd_rn(v.z, e.z); v.w = __fadd_rn(v.w, e.w);
+                    }
+                    if (g.add) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            v[itr].x = __fadd_rn(v[itr].x, av[itr].x); v[itr].y = __fadd_rn(v[itr].y, av[itr].y);
+                            v[itr].z = __fadd_rn(v[itr].z, av[itr].z); v[itr].w = __fadd_rn(v[itr].w, av[itr].w);
                         }
-                        if (g.act == CB_ACT_RELU) {
-                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
-                            v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    }
+                    if (g.act == CB_ACT_RELU) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            v[itr].x = fmaxf(v[itr].x, 0.f); v[itr].y = fmaxf(v[itr].y, 0.f);
+                            v[itr].z = fmaxf(v[itr].z, 0.f); v[itr].w = fmaxf(v[itr].w, 0.f);
                         }
-                        if (g.out) __stcs(reinterpret_cast<float4*>(g.out + row * g.ld_out + col), v);
-                        if (g.out2) {
-                            const float s2 = s2v[itr];
-                            v.x = __fmul_rn(v.x, s2); v.y = __fmul_rn(v.y, s2);
-                            v.z = __fmul_rn(v.z, s2); v.w = __fmul_rn(v.w, s2);
-                            __stcs(reinterpret_cast<float4*>(g.out2 + row * g.ld_out2 + col), v);
+                    }
+                    if (g.out) {
+                        float* p = g.out + rbase * g.ld_out + col;
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_out), v[itr]);
+                    }
+                    if (g.out2) {
+                        float* p = g.out2 + rbase * g.ld_out2 + col;
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const float s_ = s2v[itr];
+                            const float4 w = make_float4(__fmul_rn(v[itr].x, s_), __fmul_rn(v[itr].y, s_),
+                                                         __fmul_rn(v[itr].z, s_), __fmul_rn(v[itr].w, s_));
+                            if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_out2), w);
                         }
                     }
                 }
                 __syncwarp();
+            }
+        }
+        if (GRAD && g.col_partial) {
+            // the four epilogue warps are added in quarter order: a fixed association
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+            const float* cs0 = reinterpret_cast<const float*>(smem_gen + STAGES * C::STAGE_BYTES + C::STG_BYTES);
+            const int et = threadIdx.x - 6 * 32;             // 0..127
+            for (int c = et; c < BN; c += 128) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) t += cs0[w * BN + c];
+                if (n0 + c < g.N) g.col_partial[(int64_t)blockIdx.x * g.N + n0 + c] = t;
             }
         }
     }
@@ -385,6 +604,16 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                      "r"((uint32_t)C::TMEM_COLS)
                      : "memory");
     }
+}
+
+// col_sum[c] = sum over the CTA partials, in CTA order
+__global__ void __launch_bounds__(256) k_col_final(const float* __restrict__ partial, int n_ctas, int n,
+                                                   float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    float t = 0.f;
+    for (int b = 0; b < n_ctas; ++b) t += partial[(int64_t)b * n + c];
+    out[c] = t;
 }
 
 // hi/lo TF32 split of the weight operand, optionally transposed:  dst[n, k] = src[n, k] or src[k, n]
@@ -440,18 +669,20 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     return CB_OK;
 }
 
-template <int BN>
+static int64_t gemm_grid_x(int64_t n_tiles_m) { return n_tiles_m < sm_count() ? n_tiles_m : sm_count(); }
+
+template <int BN, bool GRAD>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const GemmArgs& g,
                        cudaStream_t st) {
     using C = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        CB_CUDA(cudaFuncSetAttribute(k_gemm_rows<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        CB_CUDA(cudaFuncSetAttribute(k_gemm_rows<BN, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM_BYTES));
         configured = true;
     }
-    const int64_t gx = g.n_tiles_m < sm_count() ? g.n_tiles_m : sm_count();
-    dim3 grid((unsigned)gx, (unsigned)ceil_div(g.N, BN));
-    k_gemm_rows<BN><<<grid, THREADS, C::SMEM_BYTES, st>>>(ma, mh, ml, g);
+    dim3 grid((unsigned)gemm_grid_x(g.n_tiles_m), (unsigned)ceil_div(g.N, BN));
+    k_gemm_rows<BN, GRAD><<<grid, THREADS, C::SMEM_BYTES, st>>>(ma, mh, ml, g);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
@@ -792,9 +1023,67 @@ int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float*
     g.out = out; g.ld_out = ld_out; g.out2_scale = out2_scale; g.out2 = out2; g.ld_out2 = ld_out2;
     g.n_tiles_m = ceil_div(M, tc::BM);
     cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 64) return tc::launch_gemm<64>(ma, mh, ml, g, st);
-    if (bn == 128) return tc::launch_gemm<128>(ma, mh, ml, g, st);
-    return tc::launch_gemm<256>(ma, mh, ml, g, st);
+    if (bn == 64) return tc::launch_gemm<64, false>(ma, mh, ml, g, st);
+    if (bn == 128) return tc::launch_gemm<128, false>(ma, mh, ml, g, st);
+    return tc::launch_gemm<256, false>(ma, mh, ml, g, st);
+}
+
+int64_t cb_gemm_rows_grad_workspace_bytes(int64_t M, int64_t N) {
+    if (M <= 0 || N <= 0) return 0;
+    return cb::tc::gemm_grid_x(cb::ceil_div(M, cb::tc::BM)) * N * (int64_t)sizeof(float);
+}
+
+int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const float* Bt_hi, const float* Bt_lo,
+                      int64_t N, const float* row_scale, const float* add, int64_t ld_add, const uint8_t* gate_u8,
+                      const float* gate_f32, int64_t ld_gate, int mixed, double alpha, float* d_x0, int64_t ld_dx0,
+                      int accumulate_x0, const float* post_scale, float* out, int64_t ld_out, float* col_sum,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace cb;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    CB_REQUIRE(A && Bt_hi && Bt_lo && out, CB_E_INVALID, "cb_gemm_rows_grad: NULL operand");
+    CB_REQUIRE(!(gate_u8 && gate_f32), CB_E_INVALID, "cb_gemm_rows_grad: one gate at most");
+    CB_REQUIRE(!(add && d_x0 && accumulate_x0), CB_E_UNSUPPORTED,
+               "cb_gemm_rows_grad: `add` and an accumulating d_x0 cannot be combined");
+    CB_REQUIRE(cb_gemm_rows_supported(M, N, K), CB_E_UNSUPPORTED,
+               "cb_gemm_rows_grad: needs N % 4 == 0, K % 4 == 0 and M < 2^31");
+    CB_REQUIRE(lda >= K && lda % 4 == 0 && al16(A) && al16(Bt_hi) && al16(Bt_lo), CB_E_UNSUPPORTED,
+               "cb_gemm_rows_grad: operands must be 16-byte aligned with a row pitch that is a multiple of 4 floats");
+    CB_REQUIRE(al16(out) && ld_out % 4 == 0 && ld_out >= N && (!add || (al16(add) && ld_add % 4 == 0 && ld_add >= N)) &&
+                   (!d_x0 || (al16(d_x0) && ld_dx0 % 4 == 0 && ld_dx0 >= N)) &&
+                   (!gate_f32 || (al16(gate_f32) && ld_gate % 4 == 0 && ld_gate >= N)) &&
+                   (!gate_u8 || ((reinterpret_cast<uintptr_t>(gate_u8) & 3u) == 0 && ld_gate % 4 == 0 && ld_gate >= N)),
+               CB_E_UNSUPPORTED, "cb_gemm_rows_grad: epilogue buffers must be aligned, pitches multiples of 4");
+    CB_REQUIRE(!col_sum || (workspace && workspace_bytes >= cb_gemm_rows_grad_workspace_bytes(M, N)), CB_E_WORKSPACE,
+               "cb_gemm_rows_grad: workspace smaller than cb_gemm_rows_grad_workspace_bytes()");
+    const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    CUtensorMap ma, mh, ml;
+    int rc = tc::make_map(&ma, A, M, K, lda, tc::BM);
+    if (rc) return rc;
+    rc = tc::make_map(&mh, Bt_hi, N, K, K, bn);
+    if (rc) return rc;
+    rc = tc::make_map(&ml, Bt_lo, N, K, K, bn);
+    if (rc) return rc;
+    tc::GemmArgs g{};
+    g.M = M; g.N = (int)N; g.K = (int)K;
+    g.row_scale = row_scale; g.add = add; g.ld_add = ld_add;
+    g.out = out; g.ld_out = ld_out;
+    g.n_tiles_m = ceil_div(M, tc::BM);
+    g.gate_u8 = gate_u8; g.gate_f32 = gate_f32; g.ld_gate = ld_gate;
+    g.mixed = mixed; g.alpha = (float)alpha; g.one_minus_alpha = (float)(1.0 - alpha);
+    g.d_x0 = d_x0; g.ld_dx0 = ld_dx0; g.accumulate_x0 = d_x0 ? accumulate_x0 : 0;
+    g.post_scale = post_scale;
+    g.col_partial = col_sum ? (float*)workspace : nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = bn == 64 ? tc::launch_gemm<64, true>(ma, mh, ml, g, st)
+                  : (bn == 128 ? tc::launch_gemm<128, true>(ma, mh, ml, g, st)
+                               : tc::launch_gemm<256, true>(ma, mh, ml, g, st));
+    if (rc) return rc;
+    if (col_sum) {
+        tc::k_col_final<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>((const float*)workspace,
+                                                                    (int)tc::gemm_grid_x(g.n_tiles_m), (int)N, col_sum);
+        CB_LAUNCH_CHECK();
+    }
+    return CB_OK;
 }
 
 int cb_gemm_tn_supported(int64_t M, int64_t Ka, int64_t Nb) {

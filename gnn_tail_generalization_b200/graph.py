@@ -23,6 +23,8 @@ class _DevArray:
 class GraphHandle:
     """CSR-by-destination + CSR-by-source of one graph (or one node slice of it) in HBM."""
 
+    world = 1
+
     def __init__(self, edge_index, num_nodes, row_begin=0, row_end=None, hub_chunk=0):
         if not (torch.is_tensor(edge_index) and edge_index.is_cuda):
             raise ValueError('edge_index must be a CUDA tensor (this path has no CPU implementation)')

@@ -201,6 +201,34 @@ def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_s
     return (out, out2) if want_out2 else out
 
 
+def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=None, mixed=False, alpha=0.0,
+                       d_x0=None, accumulate_x0=False, want_x0=False, post_scale=None, want_col_sum=False):
+    """cb_gemm_rows_grad: the adjoint GEMM with the backward prologue of the layer below in its epilogue.
+    Returns (out, col_sum or None, d_x0 or None)."""
+    _need_cuda(A, row_scale, add, gate_u8, gate_f32, d_x0, post_scale)
+    A, row_scale, add, gate_f32, post_scale = _f32c(A), _f32c(row_scale), _f32c(add), _f32c(gate_f32), _f32c(post_scale)
+    M, K = A.shape
+    if K != wt.k:
+        raise ValueError(f'A is [{M},{K}] but the weight operand is [{wt.n},{wt.k}]')
+    N = wt.n
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    col_sum = torch.empty(N, dtype=torch.float32, device=A.device) if want_col_sum else None
+    if want_x0 and d_x0 is None:
+        d_x0, accumulate_x0 = torch.empty((M, N), dtype=torch.float32, device=A.device), False
+    gate = gate_u8 if gate_u8 is not None else gate_f32
+    ws_bytes = int(C.lib().cb_gemm_rows_grad_workspace_bytes(M, N)) if want_col_sum else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=A.device) if ws_bytes else None
+    alg = 4 * (M * K + 2 * N * K + M * N * (1 + int(add is not None) + int(gate_f32 is not None) +
+                                            int(d_x0 is not None) * (1 + int(bool(accumulate_x0))))) + \
+        (M * N if gate_u8 is not None else 0)
+    with torch.cuda.device(A.device), _Timed('gemm_rows_grad', alg, A.device, flops=6 * M * N * K):
+        C.call('cb_gemm_rows_grad', C.ptr(A), M, K, K, C.ptr(wt.hi), C.ptr(wt.lo), N, C.ptr(row_scale), C.ptr(add), N,
+               C.ptr(gate_u8), C.ptr(gate_f32), N if gate is not None else 0, int(bool(mixed)), float(alpha),
+               C.ptr(d_x0), N, int(bool(accumulate_x0)), C.ptr(post_scale), C.ptr(out), N, C.ptr(col_sum), C.ptr(ws),
+               ws_bytes, C.stream_ptr(A.device))
+    return out, col_sum, d_x0
+
+
 def gemm_tn_supported(M, Ka, Nb):
     return bool(C.lib().cb_gemm_tn_supported(int(M), int(Ka), int(Nb)))
 
@@ -290,6 +318,73 @@ class GradSink:
         return b
 
 
+_backward_fusion = True
+
+
+def set_backward_fusion(on):
+    """False: every backward prologue runs as its own kernel(s) (cb_agg_backward_prep, torch relu/bias
+    backward) instead of inside the neighbouring dX GEMM -- the A/B switch of tests and bench."""
+    global _backward_fusion
+    _backward_fusion = bool(on)
+
+
+def new_plan():
+    return BwdPlan() if (_backward_fusion and torch.is_grad_enabled()) else None
+
+
+class BwdPlan:
+    """Backward hand-off between two neighbouring autograd nodes.
+
+    The op that PRODUCED an activation y (a Linear+relu, or a fused aggregation) starts its backward with
+    an elementwise prologue on dL/dy (relu mask, residual split, degree scale, bias column sums).  When y
+    has exactly one consumer and that consumer's backward produces dL/dy with a GEMM, the prologue runs in
+    that GEMM's epilogue instead (cb_gemm_rows_grad): the producer fills the plan in its forward, the
+    consumer's backward executes it and leaves ``result``; the producer's backward then finds its prologue
+    already done.  The caller (TricksComb) creates a plan only where the single-consumer condition holds by
+    construction."""
+    __slots__ = ('kind', 'graph', 'gate_u8', 'gate_f32', 'relu', 'mixed', 'alpha', 'want_bias', 'want_x0',
+                 'x0_sink', 'slot', 'result')
+
+    def __init__(self):
+        self.kind = None       # 'relu_bias' (Linear + relu) | 'prep' (fused aggregation)
+        self.result = None     # set by the consumer's backward: {'d_bias': tensor or None}
+        self.graph = self.gate_u8 = self.gate_f32 = self.x0_sink = None
+        self.relu = self.mixed = self.want_bias = self.want_x0 = False
+        self.alpha = 0.0
+        self.slot = None       # 'out' | 'out_scaled': which output of the aggregation the consumer reads
+
+    def run(self, dtot_in, wb, row_scale, add):
+        """Called from the consumer's backward: dX GEMM + this plan's prologue.  ``row_scale``/``add`` are
+        the consumer's own epilogue terms (its out-degree scale, parked residual gradients)."""
+        if self.kind == 'relu_bias':
+            out, col, _ = gemm_rows_grad_raw(dtot_in, wb, row_scale=row_scale, add=add, gate_f32=self.gate_f32,
+                                             want_col_sum=self.want_bias)
+            self.result = {'d_bias': col}
+            return out
+        g = self.graph
+        rs = row_scale
+        if self.slot == 'out_scaled':      # dtot = dout^-1/2 * d(out_scaled)
+            if rs is not None:
+                raise RuntimeError('BwdPlan: a pre-scaled input cannot carry a second row scale')
+            rs = g.dout_inv_sqrt
+        sink = self.x0_sink if self.want_x0 else None
+        if add is not None and sink is not None and sink.buf is not None:
+            return None     # the kernel keeps one [M, N] epilogue input: the caller runs the two-kernel path
+        out, col, d_x0 = gemm_rows_grad_raw(
+            dtot_in, wb, row_scale=rs, add=add, gate_u8=self.gate_u8, gate_f32=self.gate_f32 if self.relu else None,
+            mixed=self.mixed, alpha=self.alpha, d_x0=sink.buf if sink is not None else None,
+            accumulate_x0=sink is not None and sink.buf is not None, want_x0=self.want_x0,
+            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias)
+        if sink is not None:
+            sink.buf, d_x0 = d_x0, None
+        self.result = {'d_bias': col, 'd_x0': d_x0}
+        return out
+
+    def take_result(self):
+        r, self.result = self.result, None
+        return r
+
+
 class _SinkHub(torch.autograd.Function):
     """Identity on the shared tensor; its backward adds whatever is still parked in the sink."""
 
@@ -346,8 +441,10 @@ def _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, 
 
 class _Dense(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, add, row_scale, out2_scale, layout, relu, want_out, want_out2, dx_sink):
+    def forward(ctx, x, weight, bias, add, row_scale, out2_scale, layout, relu, want_out, want_out2, dx_sink,
+                my_plan, dx_plan):
         ctx.dx_sink = dx_sink
+        ctx.my_plan, ctx.dx_plan = my_plan, dx_plan
         wt = split_weight(weight, transpose=(layout == 'kn'))
         res = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2)
         out, out2 = res if want_out2 else (res, None)
@@ -357,6 +454,12 @@ class _Dense(torch.autograd.Function):
         keep_y = (out if out is not None else out2) if (relu and need) else None
         ctx.save_for_backward(x if need else None, weight if need else None, row_scale, out2_scale, keep_y)
         ctx.set_materialize_grads(False)
+        if my_plan is not None:
+            my_plan.kind = None
+            if relu and want_out and not want_out2 and add is None and need:
+                # detached alias: a plan must not keep the autograd graph alive (the graph owns the plan)
+                my_plan.kind, my_plan.gate_f32 = 'relu_bias', out.detach()
+                my_plan.want_bias = bias is not None and ctx.needs_input_grad[2]
         empty = x.new_empty(0)
         return (out if out is not None else empty), (out2 if out2 is not None else empty)
 
@@ -368,23 +471,31 @@ class _Dense(torch.autograd.Function):
         if dy2 is not None and dy2.numel() == 0:
             dy2 = None
         if dy is None and dy2 is None:
-            return (None,) * 11
-        if dy2 is not None:
-            dy2 = dy2 * out2_scale[:, None]
-        dtot = dy2 if dy is None else (dy if dy2 is None else dy + dy2)
-        if ctx.relu:
-            dtot = torch.where(y > 0, dtot, torch.zeros((), dtype=dtot.dtype, device=dtot.device))
-        dtot = dtot.contiguous()
+            return (None,) * 13
+        done = ctx.my_plan.take_result() if ctx.my_plan is not None else None
+        if done is not None:
+            # the consumer's dX GEMM already applied the relu mask and summed the bias gradient
+            dtot, d_bias = dy.contiguous(), done['d_bias']
+        else:
+            if dy2 is not None:
+                dy2 = dy2 * out2_scale[:, None]
+            dtot = dy2 if dy is None else (dy if dy2 is None else dy + dy2)
+            if ctx.relu:
+                dtot = torch.where(y > 0, dtot, torch.zeros((), dtype=dtot.dtype, device=dtot.device))
+            dtot = dtot.contiguous()
+            d_bias = dtot.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         d_add = dtot if (ctx.has_add and ctx.needs_input_grad[3]) else None
-        d_bias = dtot.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         M, K = x.shape
         N = dtot.shape[1]
         dx = dw = None
         if ctx.needs_input_grad[0]:
             parked = ctx.dx_sink.take() if ctx.dx_sink is not None else None   # other consumers' share of dx
+            plan = ctx.dx_plan
             if gemm_supported(M, K, N):
                 wb = split_weight(weight, transpose=(ctx.layout == 'nk'))
-                dx = gemm_rows_raw(dtot, wb, row_scale=row_scale, add=parked)
+                dx = plan.run(dtot, wb, row_scale, parked) if (plan is not None and plan.kind is not None) else None
+                if dx is None:
+                    dx = gemm_rows_raw(dtot, wb, row_scale=row_scale, add=parked)
             else:
                 dx = dtot @ _w_as_kn(weight, ctx.layout).t()
                 if row_scale is not None:
@@ -398,21 +509,24 @@ class _Dense(torch.autograd.Function):
             else:
                 xs = x if row_scale is None else x * row_scale[:, None]
                 dw = xs.t() @ dtot if ctx.layout == 'kn' else dtot.t() @ xs
-        return dx, dw, d_bias, d_add, None, None, None, None, None, None, None
+        return dx, dw, d_bias, d_add, None, None, None, None, None, None, None, None, None
 
 
 def dense(x, weight, layout, bias=None, add=None, relu=False, row_scale=None, out2_scale=None, want_out=True,
-          want_out2=False, dx_sink=None):
+          want_out2=False, dx_sink=None, my_plan=None, dx_plan=None):
     """act(row_scale[:,None] * (x @ W) + bias + add); also out2_scale[:,None] * that when want_out2.
     layout 'kn': weight is [in, out] (GCNConv.weight, GCN.py:170); 'nk': [out, in] (nn.Linear.weight).
+    my_plan / dx_plan: BwdPlan of this op's own backward prologue / of the op that produced ``x``.
     Returns (out, out2); the one not asked for is None."""
     M, K = x.shape
     N = weight.shape[1] if layout == 'kn' else weight.shape[0]
     if _dense_backend == 'tcgen05' and x.is_cuda and M > 0 and gemm_supported(M, N, K):
         out, out2 = _Dense.apply(x, weight, bias, add, row_scale, out2_scale, layout, bool(relu), bool(want_out),
-                                 bool(want_out2), dx_sink)
+                                 bool(want_out2), dx_sink, my_plan, dx_plan)
         return (out if want_out else None), (out2 if want_out2 else None)
     _need_cuda(x)
+    if my_plan is not None:   # library GEMM path: no fused backward prologue
+        my_plan.kind = None
     return _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, want_out, want_out2)
 
 
@@ -424,8 +538,9 @@ class _FusedAggregate(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, H, bias, x0, graph, alpha, relu, want_out, want_scaled, x0_sink):
+    def forward(ctx, H, bias, x0, graph, alpha, relu, want_out, want_scaled, x0_sink, my_plan):
         ctx.x0_sink = x0_sink
+        ctx.my_plan = my_plan
         mixed = x0 is not None
         need_grad = any(ctx.needs_input_grad[:3])
         # relu mask source for backward: the plain relu output doubles as the mask when nothing was
@@ -438,6 +553,17 @@ class _FusedAggregate(torch.autograd.Function):
         ctx.has_bias, ctx.use_out_as_mask = bias is not None, use_out_as_mask
         ctx.save_for_backward(mask if want_mask else None, out if (use_out_as_mask and need_grad) else None)
         ctx.set_materialize_grads(False)
+        if my_plan is not None:
+            my_plan.kind = None
+            if need_grad and (want_out != want_scaled):
+                p = my_plan
+                p.kind, p.graph, p.slot = 'prep', graph, 'out' if want_out else 'out_scaled'
+                p.gate_u8 = mask if want_mask else None
+                p.gate_f32 = out.detach() if use_out_as_mask else None
+                p.relu, p.mixed, p.alpha = relu, mixed, alpha
+                p.want_bias = bias is not None and ctx.needs_input_grad[1]
+                p.want_x0 = mixed and ctx.needs_input_grad[2]
+                p.x0_sink = x0_sink
         if out is not None and out_scaled is not None:
             return out, out_scaled
         # a Function must return tensors; the unused slot gets an empty placeholder
@@ -453,28 +579,34 @@ class _FusedAggregate(torch.autograd.Function):
         if d_out_scaled is not None and d_out_scaled.numel() == 0:
             d_out_scaled = None
         if d_out is None and d_out_scaled is None:
-            return (None,) * 9
-        want_bias = ctx.has_bias and ctx.needs_input_grad[1]
-        want_x0 = ctx.mixed and ctx.needs_input_grad[2]
-        sink = ctx.x0_sink if want_x0 else None
-        G, d_bias, d_x0 = backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, ctx.relu, ctx.mixed,
-                                            ctx.alpha, want_bias, want_x0,
-                                            d_x0_accum=sink.buf if sink is not None else None)
-        if sink is not None:   # parked for the hub / the last consumer's GEMM epilogue
-            sink.buf, d_x0 = d_x0, None
+            return (None,) * 10
+        done = ctx.my_plan.take_result() if ctx.my_plan is not None else None
+        if done is not None:
+            # the consumer's dX GEMM ran the prologue in its epilogue: what arrived is G itself
+            G = (d_out if d_out is not None else d_out_scaled).contiguous()
+            d_bias, d_x0 = done['d_bias'], done['d_x0']
+        else:
+            want_bias = ctx.has_bias and ctx.needs_input_grad[1]
+            want_x0 = ctx.mixed and ctx.needs_input_grad[2]
+            sink = ctx.x0_sink if want_x0 else None
+            G, d_bias, d_x0 = backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, ctx.relu, ctx.mixed,
+                                                ctx.alpha, want_bias, want_x0,
+                                                d_x0_accum=sink.buf if sink is not None else None)
+            if sink is not None:   # parked for the hub / the last consumer's GEMM epilogue
+                sink.buf, d_x0 = d_x0, None
         dH = None
         if ctx.needs_input_grad[0]:
             dH = agg_gather_raw(graph, C.CB_BY_SRC, graph.exchange(G), None)
-        return dH, d_bias, d_x0, None, None, None, None, None, None
+        return dH, d_bias, d_x0, None, None, None, None, None, None, None
 
 
 def fused_aggregate(H, graph, bias=None, x0=None, alpha=0.0, relu=False, want_out=True, want_scaled=False,
-                    x0_sink=None):
+                    x0_sink=None, my_plan=None):
     """Returns (out, out_scaled); the one not asked for is None."""
     if not (want_out or want_scaled):
         raise ValueError('fused_aggregate: nothing requested')
     out, out_scaled = _FusedAggregate.apply(H, bias, x0, graph, float(alpha), bool(relu), bool(want_out),
-                                            bool(want_scaled), x0_sink)
+                                            bool(want_scaled), x0_sink, my_plan)
     return (out if want_out else None), (out_scaled if want_scaled else None)
 
 

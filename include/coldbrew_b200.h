@@ -189,6 +189,27 @@ int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float*
                  float* out, int64_t ld_out, const float* out2_scale, float* out2, int64_t ld_out2, void* stream);
 
 /*
+ * Adjoint transform with the backward prologue of the layer BELOW fused into its epilogue: one kernel
+ * instead of cb_gemm_rows followed by cb_agg_backward_prep (autograd of GCN.py:242-253, 127-128,
+ * res_tricks.py:23), or followed by the relu / bias backward of a Linear layer (GCN.py:104-106).
+ * Same operations in the same order as the two-kernel path, so G and d_x0 are bit-identical to it:
+ *   acc      = A[M,K] . Bt[N,K]^T                                   (dX = dH . W^T)
+ *   dtot     = (row_scale ? row_scale[m] : 1) * acc + (add ? add[m,n] : 0)
+ *   d_x0[m,n] (+)= alpha * dtot                                     (if d_x0; accumulate_x0: += vs =)
+ *   dz       = (mixed ? (1-alpha) : 1) * dtot * gate[m,n]           gate = gate_u8 != 0 | gate_f32 > 0 | 1
+ *   out[m,n] = (post_scale ? post_scale[m] : 1) * dz                (G of the layer below; [M, ld_out])
+ *   col_sum[n] = sum_m dz[m,n]                                       (bias gradient; per-CTA partials in
+ *                                                                     `workspace`, added in CTA order)
+ * workspace: cb_gemm_rows_grad_workspace_bytes(M, N), needed when col_sum != NULL.
+ */
+int64_t cb_gemm_rows_grad_workspace_bytes(int64_t M, int64_t N);
+int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const float* Bt_hi, const float* Bt_lo,
+                      int64_t N, const float* row_scale, const float* add, int64_t ld_add, const uint8_t* gate_u8,
+                      const float* gate_f32, int64_t ld_gate, int mixed, double alpha, float* d_x0, int64_t ld_dx0,
+                      int accumulate_x0, const float* post_scale, float* out, int64_t ld_out, float* col_sum,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Weight gradient on the tcgen05 tensor cores (3xTF32): out[Ka, Nb] = A[M, Ka]^T . B[M, Nb], the reduction
  * running over the M node rows (autograd of GCN.py:225: dW = (D X)^T dH; and of the Linear layers).
  * Split-K over the SMs with a fixed-order second pass, so the result is bit-stable from run to run.

@@ -119,3 +119,70 @@ def test_gemm_tn_same_sign_data_keeps_fp32_class_relative_error():
     rel = float(((out.double() - ref).abs() / ref.abs()).max())
     rel_cublas = float((((A.t() @ B).double() - ref).abs() / ref.abs()).max())
     assert rel <= 4e-5, (rel, rel_cublas)
+
+
+# ------------------------------------------------------------------------------------------------
+# cb_gemm_rows_grad: the dX GEMM with the backward prologue of the layer below in its epilogue must give
+# exactly what the two-kernel path gives (cb_gemm_rows, then cb_agg_backward_prep / torch relu backward)
+# ------------------------------------------------------------------------------------------------
+def _small_graph(n, seed):
+    from gnn_tail_generalization_b200 import graph
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n, (4 * n,), generator=g)
+    dst = torch.randint(0, n, (4 * n,), generator=g)
+    loops = torch.arange(n)
+    ei = torch.stack([torch.cat([src, loops]), torch.cat([dst, loops])])
+    return graph.GraphHandle(ei.cuda(), n)
+
+
+@pytest.mark.parametrize('M,K,N', [(300, 64, 64), (1000, 64, 256), (4097, 128, 128), (3000, 256, 256), (777, 256, 512)])
+@pytest.mark.parametrize('gate', ['u8', 'f32', 'none'])
+@pytest.mark.parametrize('slot', ['out', 'out_scaled'])
+def test_gemm_rows_grad_equals_gemm_then_prep(M, K, N, gate, slot):
+    ops = _ops()
+    gph = _small_graph(M, M + K)
+    g = torch.Generator(device='cuda').manual_seed(M + 3 * K + 5 * N)
+    dY = torch.randn(M, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) / K ** 0.5
+    act = torch.randn(M, N, device='cuda', generator=g)
+    mask = (act > 0).to(torch.uint8)
+    relu_out = act.clamp_min(0)
+    wt = ops.split_weight(W, transpose=False)
+    alpha, mixed = 0.1, True
+    relu = gate != 'none'
+    for accumulate in (False, True):
+        parked = torch.randn(M, N, device='cuda', generator=g) if accumulate else None
+        # two kernels
+        dx = ops.gemm_rows_raw(dY, wt)
+        G_ref, db_ref, dx0_ref = ops.backward_prep_raw(
+            gph, dx if slot == 'out' else None, dx if slot == 'out_scaled' else None,
+            mask if gate == 'u8' else None, relu_out if gate == 'f32' else None, relu, mixed, alpha, True, True,
+            d_x0_accum=parked.clone() if accumulate else None)
+        # one kernel
+        G, db, dx0 = ops.gemm_rows_grad_raw(
+            dY, wt, row_scale=gph.dout_inv_sqrt if slot == 'out_scaled' else None,
+            gate_u8=mask if gate == 'u8' else None, gate_f32=relu_out if gate == 'f32' else None, mixed=mixed,
+            alpha=alpha, d_x0=parked.clone() if accumulate else None, accumulate_x0=accumulate, want_x0=True,
+            post_scale=gph.din_inv_sqrt, want_col_sum=True)
+        assert torch.equal(G, G_ref)
+        assert torch.equal(dx0, dx0_ref)
+        scale = float(db_ref.abs().max()) + 1e-6
+        assert float((db - db_ref).abs().max()) <= 1e-5 * scale * max(1.0, (M / 1000) ** 0.5)
+
+
+def test_gemm_rows_grad_relu_bias_mode():
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(11)
+    M, K, N = 2500, 256, 256
+    dY = torch.randn(M, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) / 16
+    rs = torch.rand(M, device='cuda', generator=g) + 0.1
+    parked = torch.randn(M, N, device='cuda', generator=g)
+    y = torch.randn(M, N, device='cuda', generator=g).clamp_min(0)
+    wt = ops.split_weight(W, transpose=False)
+    dx = ops.gemm_rows_raw(dY, wt, row_scale=rs, add=parked)
+    want = torch.where(y > 0, dx, torch.zeros((), device='cuda'))
+    got, col, _ = ops.gemm_rows_grad_raw(dY, wt, row_scale=rs, add=parked, gate_f32=y, want_col_sum=True)
+    assert torch.equal(got, want)
+    ref = want.double().sum(0)
+    assert float((col.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())

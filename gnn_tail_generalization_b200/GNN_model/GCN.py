@@ -90,7 +90,8 @@ class GCNConv(nn.Module):
         (GCN.py:232-236).  One tcgen05 GEMM with the scale and the SE add in its epilogue."""
         le = self.le if self.whetherHasSE else None
         if weight is not None:
-            h, _ = _ops.dense(feat, weight, 'kn', add=le, row_scale=row_scale, dx_sink=dx_sink, dx_plan=dx_plan)
+            h, _ = _ops.dense(feat, weight, 'kn', add=le, row_scale=row_scale, dx_sink=dx_sink, dx_plan=dx_plan,
+                              push_graph=graph)
         else:
             h = feat if row_scale is None else _ops.row_scale(feat, row_scale)
             if le is not None:

@@ -20,6 +20,16 @@ Q_DST_ROWPTR, Q_DST_COL, Q_DST_PERM, Q_DST_NUM_HUB_CHUNKS = 10, 11, 12, 13
 Q_SRC_ROWPTR, Q_SRC_COL, Q_SRC_PERM, Q_SRC_NUM_HUB_CHUNKS, Q_SRC_NUM_EDGES = 20, 21, 22, 23, 24
 Q_DIN_INV_SQRT, Q_DOUT_INV_SQRT, Q_IN_DEGREE, Q_OUT_DEGREE = 30, 31, 32, 33
 
+CB_PEER_HANDLE_BYTES, CB_MAX_PEERS = 64, 7
+
+
+class PeerPush(ctypes.Structure):
+    """cb_peer_push_t: where the rows of a kernel output go besides its local `out`."""
+    _fields_ = [('n_peers', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('peer', ctypes.c_void_p * CB_MAX_PEERS), ('need', ctypes.c_void_p),
+                ('row0', ctypes.c_int64), ('ld', ctypes.c_int64)]
+
+
 # every symbol include/coldbrew_b200.h declares: name -> (restype, argtypes)
 _vp, _i64, _int, _dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
 SYMBOLS = {
@@ -41,10 +51,14 @@ SYMBOLS = {
     'cb_gemm_split_weight': (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp]),
     'cb_gemm_rows_supported': (_int, [_i64, _i64, _i64]),
     'cb_gemm_rows': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _int, _vp, _i64, _vp, _vp,
-                            _i64, _vp]),
+                            _i64, _vp, _vp]),
+    'cb_peer_alloc': (_int, [_i64, ctypes.POINTER(_vp), _vp]),
+    'cb_peer_open': (_int, [_vp, ctypes.POINTER(_vp)]),
+    'cb_peer_close': (_int, [_vp]),
+    'cb_peer_free': (_int, [_vp]),
     'cb_gemm_rows_grad_workspace_bytes': (_i64, [_i64, _i64]),
     'cb_gemm_rows_grad': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _int, _dbl,
-                                 _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+                                 _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     'cb_gemm_tn_supported': (_int, [_i64, _i64, _i64]),
     'cb_gemm_tn_workspace_bytes': (_i64, [_i64, _i64, _i64]),
     'cb_gemm_tn': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp, _i64, _vp, _i64, _vp]),

@@ -76,6 +76,8 @@ struct GemmArgs {
     int accumulate_x0;
     const float* post_scale;  // [M] scale of the stored value (din^-1/2), or null
     float* col_partial;       // [gridDim.x, N] per-CTA column sums of dz, or null
+    // ---- multi-GPU: rows of `out` are also stored into the peers that gather them (cb_peer_push_t) ----
+    cb_peer_push_t push;
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
@@ -185,6 +187,21 @@ __device__ __forceinline__ constexpr uint32_t instr_desc_tf32() {
            | (2u << 10)              // B format  = TF32
            | ((uint32_t)(BN >> 3) << 17)   // N >> 3
            | ((uint32_t)(BM >> 4) << 24);  // M >> 4   (A and B both K-major: bits 15/16 = 0)
+}
+
+// Stores the lane's 8 x float4 register tile (rows rbase + 4*itr, column col) into every peer whose bit is
+// set in need[row]: the exchange step of the node-sliced path, riding on the epilogue.
+__device__ __forceinline__ void push_to_peers(const cb_peer_push_t& ps, int64_t rbase, int col, int nval,
+                                              const float4 (&v)[8]) {
+    uint32_t nd[8];
+#pragma unroll
+    for (int itr = 0; itr < 8; ++itr) nd[itr] = itr < nval ? (uint32_t)__ldg(ps.need + rbase + itr * 4) : 0u;
+    for (int j = 0; j < ps.n_peers; ++j) {
+        float* p = ps.peer[j] + (ps.row0 + rbase) * ps.ld + col;
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr)
+            if ((nd[itr] >> j) & 1u) *reinterpret_cast<float4*>(p + (int64_t)itr * 4 * ps.ld) = v[itr];
+    }
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
@@ -501,6 +518,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         for (int itr = 0; itr < 8; ++itr)
                             if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_out), v[itr]);
                     }
+                    if (g.push.n_peers) push_to_peers(g.push, rbase, col, nval, v);
                     __syncwarp();
                     continue;
                 }
@@ -567,6 +585,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
                             if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_out), v[itr]);
+                        if (g.push.n_peers) push_to_peers(g.push, rbase, col, nval, v);
                     }
                     if (g.out2) {
                         float* p = g.out2 + rbase * g.ld_out2 + col;
@@ -994,8 +1013,12 @@ int cb_gemm_rows_supported(int64_t M, int64_t N, int64_t K) {
 
 int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float* Bt_hi, const float* Bt_lo,
                  int64_t N, const float* row_scale, const float* bias, const float* add, int64_t ld_add, int act,
-                 float* out, int64_t ld_out, const float* out2_scale, float* out2, int64_t ld_out2, void* stream) {
+                 float* out, int64_t ld_out, const float* out2_scale, float* out2, int64_t ld_out2,
+                 const cb_peer_push_t* push, void* stream) {
     using namespace cb;
+    CB_REQUIRE(!push || (push->n_peers >= 0 && push->n_peers <= CB_MAX_PEERS && (push->n_peers == 0 ||
+                         (out && push->need && push->ld >= N && push->ld % 4 == 0))), CB_E_INVALID,
+               "cb_gemm_rows: bad cb_peer_push_t");
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     CB_REQUIRE(A && Bt_hi && Bt_lo, CB_E_INVALID, "cb_gemm_rows: NULL operand");
     CB_REQUIRE(out || out2, CB_E_INVALID, "cb_gemm_rows: no output buffer");
@@ -1021,6 +1044,7 @@ int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float*
     g.M = M; g.N = (int)N; g.K = (int)K;
     g.row_scale = row_scale; g.bias = bias; g.add = add; g.ld_add = ld_add; g.act = act;
     g.out = out; g.ld_out = ld_out; g.out2_scale = out2_scale; g.out2 = out2; g.ld_out2 = ld_out2;
+    if (push) g.push = *push;
     g.n_tiles_m = ceil_div(M, tc::BM);
     cudaStream_t st = (cudaStream_t)stream;
     if (bn == 64) return tc::launch_gemm<64, false>(ma, mh, ml, g, st);
@@ -1037,8 +1061,11 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
                       int64_t N, const float* row_scale, const float* add, int64_t ld_add, const uint8_t* gate_u8,
                       const float* gate_f32, int64_t ld_gate, int mixed, double alpha, float* d_x0, int64_t ld_dx0,
                       int accumulate_x0, const float* post_scale, float* out, int64_t ld_out, float* col_sum,
-                      void* workspace, int64_t workspace_bytes, void* stream) {
+                      void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push, void* stream) {
     using namespace cb;
+    CB_REQUIRE(!push || (push->n_peers >= 0 && push->n_peers <= CB_MAX_PEERS && (push->n_peers == 0 ||
+                         (push->need && push->ld >= N && push->ld % 4 == 0))), CB_E_INVALID,
+               "cb_gemm_rows_grad: bad cb_peer_push_t");
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     CB_REQUIRE(A && Bt_hi && Bt_lo && out, CB_E_INVALID, "cb_gemm_rows_grad: NULL operand");
     CB_REQUIRE(!(gate_u8 && gate_f32), CB_E_INVALID, "cb_gemm_rows_grad: one gate at most");
@@ -1073,6 +1100,7 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
     g.d_x0 = d_x0; g.ld_dx0 = ld_dx0; g.accumulate_x0 = d_x0 ? accumulate_x0 : 0;
     g.post_scale = post_scale;
     g.col_partial = col_sum ? (float*)workspace : nullptr;
+    if (push) g.push = *push;
     cudaStream_t st = (cudaStream_t)stream;
     rc = bn == 64 ? tc::launch_gemm<64, true>(ma, mh, ml, g, st)
                   : (bn == 128 ? tc::launch_gemm<128, true>(ma, mh, ml, g, st)

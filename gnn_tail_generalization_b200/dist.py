@@ -14,10 +14,13 @@ Dense-parameter gradients are summed with one bucketed all-reduce; row-sharded p
 The functions that do not touch CUDA (bounds, exchange, gradient reduction, loss normalisation) also
 run on the gloo backend, which is how the CPU test-suite covers the world_size=2 path.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
-from .graph import GraphHandle
+from . import _cabi as C
+from .graph import GraphHandle, _DevArray
 
 ROW_SHARDED_SUFFIXES = ('.le', 'embs')
 
@@ -77,6 +80,132 @@ def allreduce_dense_grads(module, world, group=None):
     return flat.numel()
 
 
+def need_masks(col_needed, num_nodes, world, rank, group=None):
+    """Which local rows each peer gathers.
+
+    col_needed: bool/uint8 [per*world] on this rank, 1 where this rank's CSR holds that global column id.
+    Returns (mask uint8 [rows_per_rank]: bit j set = peer slot j gathers local row m, peers) where
+    ``peers`` lists the remote ranks in slot order."""
+    per = rows_per_rank(num_nodes, world)
+    mine = col_needed.to(torch.uint8).contiguous()
+    everyone = mine.new_empty((world, per * world))
+    if world > 1:
+        dist.all_gather_into_tensor(everyone, mine.reshape(1, -1), group=group)
+    else:
+        everyone[0] = mine
+    peers = [r for r in range(world) if r != rank]
+    lo = rank * per
+    mask = torch.zeros(per, dtype=torch.uint8, device=mine.device)
+    for j, r in enumerate(peers):
+        mask |= everyone[r, lo:lo + per] << j
+    return mask, peers
+
+
+class PushSlot:
+    """One use of an exchange buffer: the kernel producing this rank's [rows, d] block writes it into
+    ``local`` (its rows of ``full``) and, through ``desc`` (cb_peer_push_t), into the peers that gather it."""
+    __slots__ = ('full', 'local', 'desc', 'pushed_rows', 'keep')
+
+
+class PeerExchange:
+    """Peer-mapped exchange buffers of one rank (two, used alternately) and the per-row need masks.
+
+    Why two buffers are enough: the push into buffer b of exchange #i starts after the stream barrier of
+    exchange #i-1, which every rank enters only after its aggregation #i-2 -- the last reader of b -- is
+    complete (stream order)."""
+
+    def __init__(self, graph, max_d, group=None):
+        self.graph, self.group = graph, group
+        self.world, self.rank = graph.world, graph.rank
+        if not 2 <= self.world <= C.CB_MAX_PEERS + 1:
+            raise ValueError(f'PeerExchange supports 2..{C.CB_MAX_PEERS + 1} ranks, got {self.world}')
+        self.dev = graph.device
+        self.per = rows_per_rank(graph.num_nodes, self.world)
+        self.n_pad = self.per * self.world
+        self.max_d = int(max_d)
+        nbytes = self.n_pad * self.max_d * 4
+        self._mine, self._theirs, handles = [], [], []
+        with torch.cuda.device(self.dev):
+            for _ in range(2):
+                p = ctypes.c_void_p()
+                h = ctypes.create_string_buffer(C.CB_PEER_HANDLE_BYTES)
+                C.call('cb_peer_alloc', nbytes, ctypes.byref(p), h)
+                self._mine.append(p.value)
+                handles.append(bytes(h.raw))
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, handles, group=group)
+            self.peers = [r for r in range(self.world) if r != self.rank]
+            for b in range(2):
+                ptrs = []
+                for r in self.peers:
+                    q = ctypes.c_void_p()
+                    C.call('cb_peer_open', ctypes.create_string_buffer(everyone[r][b], C.CB_PEER_HANDLE_BYTES),
+                           ctypes.byref(q))
+                    ptrs.append(q.value)
+                self._theirs.append(ptrs)
+        # need masks: forward gathers sources (columns of the by-destination CSR), backward gathers
+        # destinations (columns of the by-source CSR)
+        self.need, self.pushed_rows = {}, {}
+        for side in (C.CB_BY_DST, C.CB_BY_SRC):
+            col = graph.csr(side)[1]
+            needed = torch.zeros(self.n_pad, dtype=torch.uint8, device=self.dev)
+            needed[col.long()] = 1
+            mask, peers = need_masks(needed, graph.num_nodes, self.world, self.rank, group)
+            assert peers == self.peers
+            self.need[side] = mask
+            rows = mask[:graph.rows].to(torch.int32)
+            self.pushed_rows[side] = int(sum(((rows >> j) & 1).sum() for j in range(len(peers))))
+        self._turn = 0
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self._pending, self._views = {}, {}
+        dist.barrier(group=group)   # every rank has mapped every buffer before the first push
+
+    def slot(self, side, d):
+        """The next exchange buffer, viewed as [n_pad, d]; None if d does not fit."""
+        if d > self.max_d or d % 4:
+            return None
+        b = self._turn & 1
+        self._turn += 1
+        s = PushSlot()
+        s.full = self._views.get((b, d))
+        if s.full is None:
+            s.full = torch.as_tensor(_DevArray(self._mine[b], self.n_pad * d, '<f4'), device=self.dev).view(self.n_pad, d)
+            self._views[(b, d)] = s.full
+        lo = self.graph.row_begin
+        s.local = s.full[lo:lo + self.graph.rows]
+        desc = C.PeerPush()
+        desc.n_peers = len(self.peers)
+        for j, q in enumerate(self._theirs[b]):
+            desc.peer[j] = q
+        desc.need = self.need[side].data_ptr()
+        desc.row0, desc.ld = lo, d
+        s.desc, s.pushed_rows, s.keep = desc, self.pushed_rows[side], self.need[side]
+        self._pending[s.local.data_ptr()] = s
+        return s
+
+    def take(self, local_rows):
+        """The pending slot whose local view ``local_rows`` is (the producing kernel already pushed it)."""
+        s = self._pending.pop(local_rows.data_ptr(), None)
+        if s is not None and tuple(s.local.shape) != tuple(local_rows.shape):
+            s = None
+        return s
+
+    def finish(self, s):
+        """Stream barrier over the ranks: afterwards every peer's pushes into this rank's copy are complete."""
+        dist.all_reduce(self._flag, op=dist.ReduceOp.SUM, group=self.group)
+        return s.full[:self.graph.num_nodes]
+
+    def close(self):
+        lib = C.lib()
+        for ptrs in self._theirs:
+            for q in ptrs:
+                lib.cb_peer_close(ctypes.c_void_p(q))
+        self._theirs = []
+        for p in self._mine:
+            lib.cb_peer_free(ctypes.c_void_p(p))
+        self._mine = []
+
+
 class SlicedGraph(GraphHandle):
     """This rank's slice of the graph; ``exchange`` is the per-aggregation halo step."""
 
@@ -85,8 +214,23 @@ class SlicedGraph(GraphHandle):
         super().__init__(edge_index, num_nodes, row_begin=lo, row_end=hi, hub_chunk=hub_chunk)
         self.rank, self.world, self.group = rank, world, group
         self.exchanged_bytes = 0
+        self.peer = None
+
+    def enable_push(self, max_d):
+        """Switch the exchange from an NCCL all-gather after the producing kernel to peer stores from
+        inside it (PeerExchange).  ``max_d``: widest matrix that will be exchanged."""
+        if self.world > 1 and self.peer is None:
+            self.peer = PeerExchange(self, max_d, self.group)
+        return self.peer
+
+    def push_slot(self, side, d):
+        return self.peer.slot(side, d) if self.peer is not None else None
 
     def exchange(self, local_rows):
+        s = self.peer.take(local_rows) if self.peer is not None else None
+        if s is not None:
+            self.exchanged_bytes += s.pushed_rows * local_rows.shape[1] * local_rows.element_size()
+            return self.peer.finish(s)
         full = exchange_rows(local_rows, self.num_nodes, self.world, self.group)
         if self.world > 1:
             self.exchanged_bytes += (self.world - 1) * rows_per_rank(self.num_nodes, self.world) * \

@@ -130,6 +130,10 @@ class GraphHandle:
         """Returns the matrix holding every source row the owned rows gather from."""
         return local_rows
 
+    def push_slot(self, side, d):
+        """Exchange buffer the producing kernel should write into (node-sliced graphs with peer pushes)."""
+        return None
+
     def allreduce_sum(self, t):
         """Sum of a small tensor over the ranks sharing the graph (identity for a whole graph)."""
         return t

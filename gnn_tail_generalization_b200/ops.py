@@ -3,6 +3,8 @@ called DGL (GNN_model/GCN.py:198-253) and elementwise PyTorch ops.
 
 Every function here requires CUDA tensors and raises otherwise; there is no CPU fallback.
 """
+import ctypes
+
 import torch
 
 from . import _cabi as C
@@ -179,30 +181,45 @@ def gemm_supported(M, N, K):
     return bool(C.lib().cb_gemm_rows_supported(int(M), int(N), int(K)))
 
 
+def _push_arg(push, M, N, out):
+    """(ctypes pointer or None, pushed bytes) for an exchange slot (dist.PushSlot) whose local view is ``out``."""
+    if push is None:
+        return None, 0
+    if out is None or out.data_ptr() != push.local.data_ptr() or tuple(out.shape) != (M, N):
+        raise ValueError('push: the kernel output must be the local view of the exchange slot')
+    return ctypes.byref(push.desc), push.pushed_rows * N * 4
+
+
 def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_scale=None, want_out=True,
-                  want_out2=False):
+                  want_out2=False, out=None, push=None):
     """act(row_scale * (A @ W^T) + bias + add) on the tcgen05 tensor cores (3xTF32, fp32-class accuracy).
-    Returns out, or (out, out2) when want_out2 (out2 = out2_scale[:,None] * out)."""
+    Returns out, or (out, out2) when want_out2 (out2 = out2_scale[:,None] * out).
+    out/push: write into the given [M, N] buffer (the local rows of an exchange slot) and store every row
+    also into the peers that gather it."""
     _need_cuda(A, row_scale, bias, add, out2_scale)
     A, row_scale, bias, add, out2_scale = _f32c(A), _f32c(row_scale), _f32c(bias), _f32c(add), _f32c(out2_scale)
     M, K = A.shape
     if K != wt.k:
         raise ValueError(f'A is [{M},{K}] but the weight operand is [{wt.n},{wt.k}]')
     N = wt.n
-    out = torch.empty((M, N), dtype=torch.float32, device=A.device) if want_out else None
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device) if want_out else None
     out2 = torch.empty((M, N), dtype=torch.float32, device=A.device) if want_out2 else None
     if M == 0:
         return (out, out2) if want_out2 else out
-    alg = 4 * (M * K + 2 * N * K + M * N * (int(want_out) + int(want_out2) + int(add is not None)))
-    with torch.cuda.device(A.device), _Timed('gemm_rows', alg, A.device, flops=6 * M * N * K):
+    parg, pushed = _push_arg(push, M, N, out)
+    alg = 4 * (M * K + 2 * N * K + M * N * (int(want_out) + int(want_out2) + int(add is not None))) + pushed
+    with torch.cuda.device(A.device), _Timed('gemm_rows_push' if push is not None else 'gemm_rows', alg, A.device,
+                                             flops=6 * M * N * K):
         C.call('cb_gemm_rows', C.ptr(A), M, K, K, C.ptr(wt.hi), C.ptr(wt.lo), N, C.ptr(row_scale), C.ptr(bias),
                C.ptr(add), N, C.CB_ACT_RELU if relu else C.CB_ACT_NONE, C.ptr(out), N, C.ptr(out2_scale),
-               C.ptr(out2), N, C.stream_ptr(A.device))
+               C.ptr(out2), N, parg, C.stream_ptr(A.device))
     return (out, out2) if want_out2 else out
 
 
 def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=None, mixed=False, alpha=0.0,
-                       d_x0=None, accumulate_x0=False, want_x0=False, post_scale=None, want_col_sum=False):
+                       d_x0=None, accumulate_x0=False, want_x0=False, post_scale=None, want_col_sum=False,
+                       out=None, push=None):
     """cb_gemm_rows_grad: the adjoint GEMM with the backward prologue of the layer below in its epilogue.
     Returns (out, col_sum or None, d_x0 or None)."""
     _need_cuda(A, row_scale, add, gate_u8, gate_f32, d_x0, post_scale)
@@ -211,7 +228,9 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
     if K != wt.k:
         raise ValueError(f'A is [{M},{K}] but the weight operand is [{wt.n},{wt.k}]')
     N = wt.n
-    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    parg, pushed = _push_arg(push, M, N, out)
     col_sum = torch.empty(N, dtype=torch.float32, device=A.device) if want_col_sum else None
     if want_x0 and d_x0 is None:
         d_x0, accumulate_x0 = torch.empty((M, N), dtype=torch.float32, device=A.device), False
@@ -220,12 +239,13 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=A.device) if ws_bytes else None
     alg = 4 * (M * K + 2 * N * K + M * N * (1 + int(add is not None) + int(gate_f32 is not None) +
                                             int(d_x0 is not None) * (1 + int(bool(accumulate_x0))))) + \
-        (M * N if gate_u8 is not None else 0)
-    with torch.cuda.device(A.device), _Timed('gemm_rows_grad', alg, A.device, flops=6 * M * N * K):
+        (M * N if gate_u8 is not None else 0) + pushed
+    with torch.cuda.device(A.device), _Timed('gemm_rows_grad_push' if push is not None else 'gemm_rows_grad', alg,
+                                             A.device, flops=6 * M * N * K):
         C.call('cb_gemm_rows_grad', C.ptr(A), M, K, K, C.ptr(wt.hi), C.ptr(wt.lo), N, C.ptr(row_scale), C.ptr(add), N,
                C.ptr(gate_u8), C.ptr(gate_f32), N if gate is not None else 0, int(bool(mixed)), float(alpha),
                C.ptr(d_x0), N, int(bool(accumulate_x0)), C.ptr(post_scale), C.ptr(out), N, C.ptr(col_sum), C.ptr(ws),
-               ws_bytes, C.stream_ptr(A.device))
+               ws_bytes, parg, C.stream_ptr(A.device))
     return out, col_sum, d_x0
 
 
@@ -370,11 +390,13 @@ class BwdPlan:
         sink = self.x0_sink if self.want_x0 else None
         if add is not None and sink is not None and sink.buf is not None:
             return None     # the kernel keeps one [M, N] epilogue input: the caller runs the two-kernel path
+        slot = g.push_slot(C.CB_BY_SRC, wb.n)    # G is what the transposed aggregation gathers
         out, col, d_x0 = gemm_rows_grad_raw(
             dtot_in, wb, row_scale=rs, add=add, gate_u8=self.gate_u8, gate_f32=self.gate_f32 if self.relu else None,
             mixed=self.mixed, alpha=self.alpha, d_x0=sink.buf if sink is not None else None,
             accumulate_x0=sink is not None and sink.buf is not None, want_x0=self.want_x0,
-            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias)
+            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias,
+            out=slot.local if slot is not None else None, push=slot)
         if sink is not None:
             sink.buf, d_x0 = d_x0, None
         self.result = {'d_bias': col, 'd_x0': d_x0}
@@ -442,11 +464,15 @@ def _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, 
 class _Dense(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, add, row_scale, out2_scale, layout, relu, want_out, want_out2, dx_sink,
-                my_plan, dx_plan):
+                my_plan, dx_plan, push_graph):
         ctx.dx_sink = dx_sink
         ctx.my_plan, ctx.dx_plan = my_plan, dx_plan
         wt = split_weight(weight, transpose=(layout == 'kn'))
-        res = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2)
+        # multi-GPU: the output is what the next aggregation gathers -> write it into the exchange buffer and
+        # into the peers from the epilogue (graph.exchange() then only has to wait for everyone's pushes)
+        slot = push_graph.push_slot(C.CB_BY_DST, wt.n) if (push_graph is not None and want_out) else None
+        res = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2,
+                            out=slot.local if slot is not None else None, push=slot)
         out, out2 = res if want_out2 else (res, None)
         ctx.layout, ctx.relu = layout, relu
         ctx.has_bias, ctx.has_add = bias is not None, add is not None
@@ -471,7 +497,7 @@ class _Dense(torch.autograd.Function):
         if dy2 is not None and dy2.numel() == 0:
             dy2 = None
         if dy is None and dy2 is None:
-            return (None,) * 13
+            return (None,) * 14
         done = ctx.my_plan.take_result() if ctx.my_plan is not None else None
         if done is not None:
             # the consumer's dX GEMM already applied the relu mask and summed the bias gradient
@@ -509,20 +535,21 @@ class _Dense(torch.autograd.Function):
             else:
                 xs = x if row_scale is None else x * row_scale[:, None]
                 dw = xs.t() @ dtot if ctx.layout == 'kn' else dtot.t() @ xs
-        return dx, dw, d_bias, d_add, None, None, None, None, None, None, None, None, None
+        return dx, dw, d_bias, d_add, None, None, None, None, None, None, None, None, None, None
 
 
 def dense(x, weight, layout, bias=None, add=None, relu=False, row_scale=None, out2_scale=None, want_out=True,
-          want_out2=False, dx_sink=None, my_plan=None, dx_plan=None):
+          want_out2=False, dx_sink=None, my_plan=None, dx_plan=None, push_graph=None):
     """act(row_scale[:,None] * (x @ W) + bias + add); also out2_scale[:,None] * that when want_out2.
     layout 'kn': weight is [in, out] (GCNConv.weight, GCN.py:170); 'nk': [out, in] (nn.Linear.weight).
     my_plan / dx_plan: BwdPlan of this op's own backward prologue / of the op that produced ``x``.
+    push_graph: node-sliced graph whose next aggregation gathers ``out`` (the exchange rides on the epilogue).
     Returns (out, out2); the one not asked for is None."""
     M, K = x.shape
     N = weight.shape[1] if layout == 'kn' else weight.shape[0]
     if _dense_backend == 'tcgen05' and x.is_cuda and M > 0 and gemm_supported(M, N, K):
         out, out2 = _Dense.apply(x, weight, bias, add, row_scale, out2_scale, layout, bool(relu), bool(want_out),
-                                 bool(want_out2), dx_sink, my_plan, dx_plan)
+                                 bool(want_out2), dx_sink, my_plan, dx_plan, push_graph)
         return (out if want_out else None), (out2 if want_out2 else None)
     _need_cuda(x)
     if my_plan is not None:   # library GEMM path: no fused backward prologue

@@ -164,6 +164,33 @@ int cb_sumsq(const float* x, int64_t n, float* out, void* workspace, int64_t wor
              void* stream);
 
 /*
+ * Multi-GPU exchange (1-D node partition, one process per GPU on one node; no counterpart in the
+ * single-device reference).  Every aggregation needs the source rows its owned rows gather from.  Instead
+ * of an all-gather after the kernel that produced the local row block, that kernel stores each finished
+ * row into its own copy AND into the copy of every peer that gathers it, through NVLink peer memory:
+ *
+ *   cb_peer_alloc / cb_peer_open   a device buffer other processes can map (CUDA IPC; the 64-byte handle is
+ *                                  what the ranks exchange).  cb_peer_close unmaps, cb_peer_free releases.
+ *   cb_peer_push_t                 where the rows of a [M, N] kernel output go besides `out`:
+ *                                  peer[j] + (row0 + m) * ld + n   for every j with bit j of need[m] set.
+ * The caller orders "all pushes done" before "anyone gathers" with a barrier on the stream (NCCL).
+ */
+#define CB_PEER_HANDLE_BYTES 64
+#define CB_MAX_PEERS 7
+typedef struct {
+    int32_t n_peers;             /* 0 .. CB_MAX_PEERS */
+    int32_t reserved;
+    float* peer[CB_MAX_PEERS];   /* peer-mapped base of each remote [N_global, ld] buffer */
+    const uint8_t* need;         /* [M] device: bit j set = remote j gathers local row m */
+    int64_t row0;                /* global index of local row 0 */
+    int64_t ld;                  /* row pitch of the remote buffers, floats */
+} cb_peer_push_t;
+int cb_peer_alloc(int64_t bytes, void** ptr, void* handle_out /* CB_PEER_HANDLE_BYTES */);
+int cb_peer_open(const void* handle, void** ptr);
+int cb_peer_close(void* ptr);
+int cb_peer_free(void* ptr);
+
+/*
  * Dense transform on the tcgen05 tensor cores, fp32 in / fp32 out, "3xTF32" split operands (fp32-class
  * accuracy; the reference GEMM is th.matmul in fp32 with TF32 off, GCN.py:225).
  *
@@ -186,7 +213,8 @@ int cb_gemm_split_weight(const float* W, int64_t n_rows, int64_t k_cols, int tra
 int cb_gemm_rows_supported(int64_t M, int64_t N, int64_t K);
 int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float* Bt_hi, const float* Bt_lo,
                  int64_t N, const float* row_scale, const float* bias, const float* add, int64_t ld_add, int act,
-                 float* out, int64_t ld_out, const float* out2_scale, float* out2, int64_t ld_out2, void* stream);
+                 float* out, int64_t ld_out, const float* out2_scale, float* out2, int64_t ld_out2,
+                 const cb_peer_push_t* push /* rows of `out` also go to the peers; NULL on one GPU */, void* stream);
 
 /*
  * Adjoint transform with the backward prologue of the layer BELOW fused into its epilogue: one kernel
@@ -207,7 +235,7 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
                       int64_t N, const float* row_scale, const float* add, int64_t ld_add, const uint8_t* gate_u8,
                       const float* gate_f32, int64_t ld_gate, int mixed, double alpha, float* d_x0, int64_t ld_dx0,
                       int accumulate_x0, const float* post_scale, float* out, int64_t ld_out, float* col_sum,
-                      void* workspace, int64_t workspace_bytes, void* stream);
+                      void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push, void* stream);
 
 /*
  * Weight gradient on the tcgen05 tensor cores (3xTF32): out[Ka, Nb] = A[M, Ka]^T . B[M, Nb], the reduction

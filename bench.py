@@ -43,6 +43,10 @@ def parse():
     p.add_argument('--se', default='000', help='whetherHasSE flags (BASELINE configs[3] has no SE)')
     p.add_argument('--exchange', default='push', choices=['push', 'nccl'],
                    help='N>1: rows pushed to the peers from the producing GEMM epilogue (default) or NCCL all-gather')
+    p.add_argument('--panels', type=int, default=0,
+                   help='N>1, push: column panels the exchange is pipelined in against the aggregation '
+                        '(0 = auto: 4 at 8 GPUs where the push dominates, else 1; measured, see DESIGN.md 7)')
+    p.add_argument('--push-ctas', type=int, default=64, help='N>1, panels>1: grid cap of a pushing GEMM')
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--cpu-nodes', type=int, default=1_000_000, help='sample size of the CPU baseline / reference arm')
@@ -217,8 +221,10 @@ def run_ours(a):
     E = ei.shape[1]
     graph = cbdist.SlicedGraph(ei, N, rank, world)
     del ei
+    if a.panels <= 0:
+        a.panels = 4 if world >= 8 else 1
     if world > 1 and a.exchange == 'push':
-        graph.enable_push(d)
+        graph.enable_push(d, a.panels, a.push_ctas)
     torch.cuda.empty_cache()
     lo, hi = graph.row_begin, graph.row_end
     rows = hi - lo
@@ -382,7 +388,8 @@ def run_ours(a):
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': workload_name(a), 'edges': E, 'edges_aggregated_per_step': 2 * L * E,
                            'l2': 'inputs exceed L2 (feature matrix %.1f GB vs 126 MB)' % (N * d * 4 / 1e9),
-                           'parallelism': (f'node-slice x{world}, exchange={a.exchange}' if world > 1 else 'single GPU'),
+                           'parallelism': (f'node-slice x{world}, exchange={a.exchange}, panels={a.panels}' if world > 1
+                                           else 'single GPU'),
                            'gemm': 'tcgen05 3xTF32 split (fp32-class accuracy), fp32 accumulate in TMEM'},
                 'roofline': roofline, 'roofline_kernels': kernels, 'cpu_baseline': cpu, 'e2e': e2e,
                 'clocks': clk.summary(), 'gpu_launches': launches,

@@ -25,7 +25,7 @@ CB_PEER_HANDLE_BYTES, CB_MAX_PEERS = 64, 7
 
 class PeerPush(ctypes.Structure):
     """cb_peer_push_t: where the rows of a kernel output go besides its local `out`."""
-    _fields_ = [('n_peers', ctypes.c_int32), ('reserved', ctypes.c_int32),
+    _fields_ = [('n_peers', ctypes.c_int32), ('max_ctas', ctypes.c_int32),
                 ('peer', ctypes.c_void_p * CB_MAX_PEERS), ('need', ctypes.c_void_p),
                 ('row0', ctypes.c_int64), ('ld', ctypes.c_int64)]
 
@@ -40,8 +40,8 @@ SYMBOLS = {
     'cb_graph_destroy': (_int, [_vp]),
     'cb_graph_query': (_int, [_vp, _int, _vp]),
     'cb_graph_workspace_bytes': (_i64, [_vp, _int, _i64]),
-    'cb_agg_forward': (_int, [_vp, _vp, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _vp, _i64, _vp]),
-    'cb_agg_gather': (_int, [_vp, _int, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    'cb_agg_forward': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    'cb_agg_gather': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_prep_workspace_bytes': (_i64, [_i64, _i64]),
     'cb_agg_backward_prep': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _dbl, _vp, _vp, _vp, _int, _vp,
                                     _i64, _vp]),

@@ -27,8 +27,10 @@ struct AggArgs {
     const int64_t* chunk_beg;
     int64_t n_chunks;
     int hub_chunk;
-    const float* X;      // [n_src, d]
-    int64_t d;           // row pitch of X and of every output, in floats
+    const float* X;      // [n_src, x_ld]
+    int64_t d;           // columns aggregated (logical width)
+    int64_t x_ld;        // row pitch of X, floats
+    int64_t o_ld;        // row pitch of x0 / out / out2 / mask, floats (bytes for mask)
     int64_t col0;        // first column handled by this launch
     float* partial;      // [n_chunks, d]
     // epilogue
@@ -79,7 +81,7 @@ struct Vec<1> {
 // elementwise ops (GCN.py:250,253; res_tricks.py:14,23).
 template <int VEC>
 __device__ __forceinline__ void epilogue_store(const AggArgs& a, int64_t row, int64_t c, float (&acc)[VEC]) {
-    const int64_t off = row * a.d + c;
+    const int64_t off = row * a.o_ld + c;
     float z[VEC], o[VEC];
     const float rs = a.row_scale ? __ldg(a.row_scale + row) : 1.f;
     float b[VEC], x0[VEC];
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
             for (int u = 0; u < UNROLL; ++u) {
                 const int s = __shfl_sync(gmask, my, (k + u) & (LPR - 1), LPR);
                 if (k + u < n) {
-                    const float* xr = a.X + (int64_t)s * a.d;
+                    const float* xr = a.X + (int64_t)s * a.x_ld;
 #pragma unroll
                     for (int ch = 0; ch < NCH; ++ch)
                         if (cval[ch]) Vec<VEC>::load(v[u][ch], xr + cofs[ch]);
@@ -274,7 +276,7 @@ static int run_agg(const cb_graph* g, int side_id, AggArgs a, void* workspace, i
     const int64_t need = s.n_chunks * a.d * (int64_t)sizeof(float);
     CB_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need), CB_E_WORKSPACE,
                "aggregation workspace missing or smaller than cb_graph_workspace_bytes()");
-    const bool vec4 = (a.d % 4 == 0) && aligned16(a.X) && aligned16(a.out) && aligned16(a.out2) &&
+    const bool vec4 = (a.d % 4 == 0) && (a.x_ld % 4 == 0) && (a.o_ld % 4 == 0) && aligned16(a.X) && aligned16(a.out) && aligned16(a.out2) &&
                       aligned16(a.x0) && aligned16(a.bias) && aligned16(a.partial) &&
                       (reinterpret_cast<uintptr_t>(a.mask) & 3u) == 0;
     return vec4 ? launch_vec<4>(a, st) : launch_vec<1>(a, st);
@@ -290,18 +292,22 @@ int64_t cb_graph_workspace_bytes(const cb_graph_t* g, int side, int64_t d) {
     return s.n_chunks * d * (int64_t)sizeof(float);
 }
 
-int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t d, const float* bias, const float* x0,
-                   double alpha, int act, float* out, float* out_scaled, uint8_t* mask, void* workspace,
-                   int64_t workspace_bytes, void* stream) {
+int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t ld_h, int64_t d, const float* bias, const float* x0,
+                   double alpha, int act, float* out, float* out_scaled, uint8_t* mask, int64_t ld_out,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
     using namespace cb;
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_forward: graph is NULL");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_forward: d must be positive");
     CB_REQUIRE(g->rows == 0 || H != nullptr, CB_E_INVALID, "cb_agg_forward: H is NULL");
     CB_REQUIRE(out != nullptr || out_scaled != nullptr, CB_E_INVALID, "cb_agg_forward: no output buffer");
     CB_REQUIRE(act == CB_ACT_NONE || act == CB_ACT_RELU, CB_E_INVALID, "cb_agg_forward: unknown activation");
+    CB_REQUIRE((ld_h == 0 || ld_h >= d) && (ld_out == 0 || ld_out >= d), CB_E_INVALID,
+               "cb_agg_forward: a row pitch is smaller than d");
     AggArgs a{};
     a.X = H;
     a.d = d;
+    a.x_ld = ld_h ? ld_h : d;
+    a.o_ld = ld_out ? ld_out : d;
     a.row_scale = g->din_is;
     a.bias = bias;
     a.x0 = x0;
@@ -315,16 +321,20 @@ int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t d, const float* 
     return run_agg(g, CB_BY_DST, a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t d, const float* row_scale,
-                  float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, int64_t d, const float* row_scale,
+                  float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream) {
     using namespace cb;
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_gather: graph is NULL");
     CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_agg_gather: unknown side");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_gather: d must be positive");
     CB_REQUIRE(g->rows == 0 || (X != nullptr && out != nullptr), CB_E_INVALID, "cb_agg_gather: NULL buffer");
+    CB_REQUIRE((ld_x == 0 || ld_x >= d) && (ld_out == 0 || ld_out >= d), CB_E_INVALID,
+               "cb_agg_gather: a row pitch is smaller than d");
     AggArgs a{};
     a.X = X;
     a.d = d;
+    a.x_ld = ld_x ? ld_x : d;
+    a.o_ld = ld_out ? ld_out : d;
     a.row_scale = row_scale;
     a.act = CB_ACT_NONE;
     a.out = out;

@@ -688,7 +688,10 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     return CB_OK;
 }
 
-static int64_t gemm_grid_x(int64_t n_tiles_m) { return n_tiles_m < sm_count() ? n_tiles_m : sm_count(); }
+static int64_t gemm_grid_x(int64_t n_tiles_m, int max_ctas = 0) {
+    int64_t g = n_tiles_m < sm_count() ? n_tiles_m : sm_count();
+    return (max_ctas > 0 && max_ctas < g) ? max_ctas : g;
+}
 
 template <int BN, bool GRAD>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const GemmArgs& g,
@@ -700,7 +703,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mh, const CUten
                                      C::SMEM_BYTES));
         configured = true;
     }
-    dim3 grid((unsigned)gemm_grid_x(g.n_tiles_m), (unsigned)ceil_div(g.N, BN));
+    dim3 grid((unsigned)gemm_grid_x(g.n_tiles_m, g.push.max_ctas), (unsigned)ceil_div(g.N, BN));
     k_gemm_rows<BN, GRAD><<<grid, THREADS, C::SMEM_BYTES, st>>>(ma, mh, ml, g);
     CB_LAUNCH_CHECK();
     return CB_OK;
@@ -1107,8 +1110,8 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
                                : tc::launch_gemm<256, true>(ma, mh, ml, g, st));
     if (rc) return rc;
     if (col_sum) {
-        tc::k_col_final<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>((const float*)workspace,
-                                                                    (int)tc::gemm_grid_x(g.n_tiles_m), (int)N, col_sum);
+        tc::k_col_final<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(
+            (const float*)workspace, (int)tc::gemm_grid_x(g.n_tiles_m, g.push.max_ctas), (int)N, col_sum);
         CB_LAUNCH_CHECK();
     }
     return CB_OK;

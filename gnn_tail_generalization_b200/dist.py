@@ -102,9 +102,30 @@ def need_masks(col_needed, num_nodes, world, rank, group=None):
 
 
 class PushSlot:
-    """One use of an exchange buffer: the kernel producing this rank's [rows, d] block writes it into
-    ``local`` (its rows of ``full``) and, through ``desc`` (cb_peer_push_t), into the peers that gather it."""
-    __slots__ = ('full', 'local', 'desc', 'pushed_rows', 'keep')
+    """One use of an exchange buffer.  The kernel producing this rank's [rows, width] block writes it, one
+    column panel per launch, into ``panel_local[p]`` (its rows of the [n_pad, panel_width] panel) and, through
+    ``descs[p]`` (cb_peer_push_t), into the peers that gather those rows; ``pushed(p)`` then queues the stream
+    barrier after which panel p is complete on every rank (``events[p]``).  Panels let the aggregation of
+    panel p (HBM-bound, side stream) run while panel p+1 is still crossing NVLink.
+
+    ``local`` is what the producer hands to autograd: [rows, width] for one panel, else the
+    [rows, n_panels, panel_width] view of the panel-major buffer."""
+    __slots__ = ('owner', 'width', 'local_rows', 'n_panels', 'panel_width', 'panel_full', 'panel_local', 'descs',
+                 'local', 'events', 'pushed_rows', 'keep')
+
+    def pushed(self, p):
+        dist.all_reduce(self.owner._flag, op=dist.ReduceOp.SUM, group=self.owner.group)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.owner.dev))
+        self.events[p] = ev
+
+    @property
+    def side_stream(self):
+        return self.owner.side_stream
+
+    def rows(self, p, n):
+        """Panel p of the exchanged matrix: [n, panel_width], every rank's rows."""
+        return self.panel_full[p][:n]
 
 
 class PeerExchange:
@@ -112,9 +133,9 @@ class PeerExchange:
 
     Why two buffers are enough: the push into buffer b of exchange #i starts after the stream barrier of
     exchange #i-1, which every rank enters only after its aggregation #i-2 -- the last reader of b -- is
-    complete (stream order)."""
+    complete (the compute stream waits for the side stream that ran it)."""
 
-    def __init__(self, graph, max_d, group=None):
+    def __init__(self, graph, max_d, group=None, panels=1, push_ctas=0):
         self.graph, self.group = graph, group
         self.world, self.rank = graph.world, graph.rank
         if not 2 <= self.world <= C.CB_MAX_PEERS + 1:
@@ -123,6 +144,7 @@ class PeerExchange:
         self.per = rows_per_rank(graph.num_nodes, self.world)
         self.n_pad = self.per * self.world
         self.max_d = int(max_d)
+        self.panels, self.push_ctas = max(1, int(panels)), int(push_ctas)
         nbytes = self.n_pad * self.max_d * 4
         self._mine, self._theirs, handles = [], [], []
         with torch.cuda.device(self.dev):
@@ -143,6 +165,7 @@ class PeerExchange:
                            ctypes.byref(q))
                     ptrs.append(q.value)
                 self._theirs.append(ptrs)
+            self.side_stream = torch.cuda.Stream(device=self.dev)
         # need masks: forward gathers sources (columns of the by-destination CSR), backward gathers
         # destinations (columns of the by-source CSR)
         self.need, self.pushed_rows = {}, {}
@@ -161,39 +184,45 @@ class PeerExchange:
         dist.barrier(group=group)   # every rank has mapped every buffer before the first push
 
     def slot(self, side, d):
-        """The next exchange buffer, viewed as [n_pad, d]; None if d does not fit."""
+        """The next exchange buffer laid out for a [., d] matrix; None if d does not fit."""
         if d > self.max_d or d % 4:
             return None
         b = self._turn & 1
         self._turn += 1
+        np_ = self.panels if (d % self.panels == 0 and (d // self.panels) % 4 == 0) else 1
+        pw = d // np_
+        lo, rows = self.graph.row_begin, self.graph.rows
         s = PushSlot()
-        s.full = self._views.get((b, d))
-        if s.full is None:
-            s.full = torch.as_tensor(_DevArray(self._mine[b], self.n_pad * d, '<f4'), device=self.dev).view(self.n_pad, d)
-            self._views[(b, d)] = s.full
-        lo = self.graph.row_begin
-        s.local = s.full[lo:lo + self.graph.rows]
-        desc = C.PeerPush()
-        desc.n_peers = len(self.peers)
-        for j, q in enumerate(self._theirs[b]):
-            desc.peer[j] = q
-        desc.need = self.need[side].data_ptr()
-        desc.row0, desc.ld = lo, d
-        s.desc, s.pushed_rows, s.keep = desc, self.pushed_rows[side], self.need[side]
+        s.owner, s.width, s.local_rows, s.n_panels, s.panel_width = self, d, rows, np_, pw
+        full3 = self._views.get((b, d, np_))
+        if full3 is None:
+            full3 = torch.as_tensor(_DevArray(self._mine[b], self.n_pad * d, '<f4'), device=self.dev)
+            full3 = full3.view(np_, self.n_pad, pw)      # panel-major
+            self._views[(b, d, np_)] = full3
+        s.panel_full = [full3[p] for p in range(np_)]
+        s.panel_local = [full3[p, lo:lo + rows] for p in range(np_)]
+        s.local = s.panel_local[0] if np_ == 1 else full3[:, lo:lo + rows].permute(1, 0, 2)
+        s.descs = []
+        for p in range(np_):
+            desc = C.PeerPush()
+            desc.n_peers = len(self.peers)
+            desc.max_ctas = self.push_ctas if np_ > 1 else 0
+            for j, q in enumerate(self._theirs[b]):
+                desc.peer[j] = q + p * self.n_pad * pw * 4
+            desc.need = self.need[side].data_ptr()
+            desc.row0, desc.ld = lo, pw
+            s.descs.append(desc)
+        s.events = [None] * np_
+        s.pushed_rows, s.keep = self.pushed_rows[side], self.need[side]
         self._pending[s.local.data_ptr()] = s
         return s
 
     def take(self, local_rows):
         """The pending slot whose local view ``local_rows`` is (the producing kernel already pushed it)."""
         s = self._pending.pop(local_rows.data_ptr(), None)
-        if s is not None and tuple(s.local.shape) != tuple(local_rows.shape):
+        if s is not None and (local_rows.shape[0] != s.local_rows or local_rows.numel() != s.local_rows * s.width):
             s = None
         return s
-
-    def finish(self, s):
-        """Stream barrier over the ranks: afterwards every peer's pushes into this rank's copy are complete."""
-        dist.all_reduce(self._flag, op=dist.ReduceOp.SUM, group=self.group)
-        return s.full[:self.graph.num_nodes]
 
     def close(self):
         lib = C.lib()
@@ -216,21 +245,28 @@ class SlicedGraph(GraphHandle):
         self.exchanged_bytes = 0
         self.peer = None
 
-    def enable_push(self, max_d):
+    def enable_push(self, max_d, panels=1, push_ctas=0):
         """Switch the exchange from an NCCL all-gather after the producing kernel to peer stores from
-        inside it (PeerExchange).  ``max_d``: widest matrix that will be exchanged."""
+        inside it (PeerExchange).  ``max_d``: widest matrix that will be exchanged; ``panels`` > 1 pipelines
+        the exchange by column panels against the aggregation, ``push_ctas`` caps the grid of a pushing
+        kernel so that the aggregation of the previous panel finds free SMs."""
         if self.world > 1 and self.peer is None:
-            self.peer = PeerExchange(self, max_d, self.group)
+            self.peer = PeerExchange(self, max_d, self.group, panels, push_ctas)
         return self.peer
 
     def push_slot(self, side, d):
         return self.peer.slot(side, d) if self.peer is not None else None
 
     def exchange(self, local_rows):
+        """[N, d] tensor of every rank's rows, or -- when the producer pushed them panel by panel -- the
+        PushSlot whose panels become valid at its events."""
         s = self.peer.take(local_rows) if self.peer is not None else None
         if s is not None:
-            self.exchanged_bytes += s.pushed_rows * local_rows.shape[1] * local_rows.element_size()
-            return self.peer.finish(s)
+            self.exchanged_bytes += s.pushed_rows * s.width * 4
+            # one panel: its barrier is already queued on this stream, stream order is enough
+            return s.rows(0, self.num_nodes) if s.n_panels == 1 else s
+        if local_rows.dim() == 3:
+            local_rows = local_rows.reshape(local_rows.shape[0], -1)
         full = exchange_rows(local_rows, self.num_nodes, self.world, self.group)
         if self.world > 1:
             self.exchanged_bytes += (self.world - 1) * rows_per_rank(self.num_nodes, self.world) * \

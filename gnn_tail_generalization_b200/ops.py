@@ -4,6 +4,7 @@ called DGL (GNN_model/GCN.py:198-253) and elementwise PyTorch ops.
 Every function here requires CUDA tensors and raises otherwise; there is no CPU fallback.
 """
 import ctypes
+import os
 
 import torch
 
@@ -70,40 +71,62 @@ def _f32c(t):
 # raw (non-differentiable) kernel calls
 # ---------------------------------------------------------------------------------------------
 
+def _pofs(t, elems):
+    """Device address of element ``elems`` of a tensor (None stays NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr() + elems * t.element_size())
+
+
 def agg_forward_raw(graph, H, bias=None, x0=None, alpha=0.0, relu=False, want_out=True, want_scaled=False,
-                    want_mask=False):
-    """One fused forward aggregation over the owned rows.  H holds every source row ([N_global, d])."""
+                    want_mask=False, outs=None, panel=None):
+    """One fused forward aggregation over the owned rows.  H holds every source row ([N_global, d]).
+
+    panel=(c0, w): H is the [N_global, w] column panel c0..c0+w of a wider matrix; bias / x0 / the outputs are
+    the full-width [.., D] tensors (``outs`` = (out, out_scaled, mask) preallocated) and only their columns
+    c0..c0+w are read / written."""
     _need_cuda(H, bias, x0)
     H, bias, x0 = _f32c(H), _f32c(bias), _f32c(x0)
     d = H.shape[1]
     if H.shape[0] != graph.num_nodes:
         raise ValueError(f'H has {H.shape[0]} rows, the graph has {graph.num_nodes} nodes')
-    out = torch.empty((graph.rows, d), dtype=torch.float32, device=H.device) if want_out else None
-    out_scaled = torch.empty((graph.rows, d), dtype=torch.float32, device=H.device) if want_scaled else None
-    mask = torch.empty((graph.rows, d), dtype=torch.uint8, device=H.device) if want_mask else None
+    c0, D = (panel[0], None) if panel is not None else (0, d)
+    if outs is not None:
+        out, out_scaled, mask = outs
+        D = (out if out is not None else out_scaled).shape[1]
+    else:
+        if panel is not None:
+            raise ValueError('a column panel needs preallocated full-width outputs')
+        out = torch.empty((graph.rows, d), dtype=torch.float32, device=H.device) if want_out else None
+        out_scaled = torch.empty((graph.rows, d), dtype=torch.float32, device=H.device) if want_scaled else None
+        mask = torch.empty((graph.rows, d), dtype=torch.uint8, device=H.device) if want_mask else None
     ws, ws_bytes = graph.workspace(C.CB_BY_DST, d)
-    alg = gather_alg_bytes(graph, C.CB_BY_DST, d, int(want_out) + int(want_scaled), 1 + int(x0 is not None),
-                           want_mask, 1 + int(want_scaled))
+    alg = gather_alg_bytes(graph, C.CB_BY_DST, d, int(out is not None) + int(out_scaled is not None),
+                           1 + int(x0 is not None), mask is not None, 1 + int(out_scaled is not None))
     with torch.cuda.device(H.device), _Timed('agg_forward', alg, H.device):
-        C.call('cb_agg_forward', graph.handle, C.ptr(H), d, C.ptr(bias), C.ptr(x0), float(alpha),
-               C.CB_ACT_RELU if relu else C.CB_ACT_NONE, C.ptr(out), C.ptr(out_scaled), C.ptr(mask),
+        C.call('cb_agg_forward', graph.handle, C.ptr(H), d, d, _pofs(bias, c0), _pofs(x0, c0), float(alpha),
+               C.CB_ACT_RELU if relu else C.CB_ACT_NONE, _pofs(out, c0), _pofs(out_scaled, c0), _pofs(mask, c0), D,
                C.ptr(ws), ws_bytes, C.stream_ptr(H.device))
     return out, out_scaled, mask
 
 
-def agg_gather_raw(graph, side, X, row_scale=None):
-    """out[r] = row_scale[r] * sum_{j in row r} X[col[j]]  over one CSR side of the graph."""
+def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None):
+    """out[r] = row_scale[r] * sum_{j in row r} X[col[j]]  over one CSR side of the graph.
+    panel=(c0, w): X is a [N_global, w] column panel; ``out`` is the preallocated full-width result."""
     _need_cuda(X, row_scale)
     X, row_scale = _f32c(X), _f32c(row_scale)
     d = X.shape[1]
     if X.shape[0] != graph.num_nodes:
         raise ValueError(f'X has {X.shape[0]} rows, the graph has {graph.num_nodes} nodes')
-    out = torch.empty((graph.rows, d), dtype=torch.float32, device=X.device)
+    c0 = panel[0] if panel is not None else 0
+    if out is None:
+        if panel is not None:
+            raise ValueError('a column panel needs a preallocated full-width output')
+        out = torch.empty((graph.rows, d), dtype=torch.float32, device=X.device)
+    D = out.shape[1]
     ws, ws_bytes = graph.workspace(side, d)
     alg = gather_alg_bytes(graph, side, d, 1, 1, False, int(row_scale is not None))
     with torch.cuda.device(X.device), _Timed('agg_gather_dst' if side == C.CB_BY_DST else 'agg_gather_src', alg,
                                              X.device):
-        C.call('cb_agg_gather', graph.handle, side, C.ptr(X), d, C.ptr(row_scale), C.ptr(out), C.ptr(ws),
+        C.call('cb_agg_gather', graph.handle, side, C.ptr(X), d, d, C.ptr(row_scale), _pofs(out, c0), D, C.ptr(ws),
                ws_bytes, C.stream_ptr(X.device))
     return out
 
@@ -181,71 +204,87 @@ def gemm_supported(M, N, K):
     return bool(C.lib().cb_gemm_rows_supported(int(M), int(N), int(K)))
 
 
-def _push_arg(push, M, N, out):
-    """(ctypes pointer or None, pushed bytes) for an exchange slot (dist.PushSlot) whose local view is ``out``."""
-    if push is None:
-        return None, 0
-    if out is None or out.data_ptr() != push.local.data_ptr() or tuple(out.shape) != (M, N):
-        raise ValueError('push: the kernel output must be the local view of the exchange slot')
-    return ctypes.byref(push.desc), push.pushed_rows * N * 4
-
-
 def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_scale=None, want_out=True,
-                  want_out2=False, out=None, push=None):
+                  want_out2=False, push=None):
     """act(row_scale * (A @ W^T) + bias + add) on the tcgen05 tensor cores (3xTF32, fp32-class accuracy).
     Returns out, or (out, out2) when want_out2 (out2 = out2_scale[:,None] * out).
-    out/push: write into the given [M, N] buffer (the local rows of an exchange slot) and store every row
-    also into the peers that gather it."""
+
+    push (dist.PushSlot, multi-GPU): ``out`` is written into the exchange buffer -- one launch per column
+    panel of the slot, each storing its rows also into the peers that gather them and followed by the
+    slot's stream barrier -- and the slot's local view is returned ([M, N], or [M, panels, N/panels])."""
     _need_cuda(A, row_scale, bias, add, out2_scale)
     A, row_scale, bias, add, out2_scale = _f32c(A), _f32c(row_scale), _f32c(bias), _f32c(add), _f32c(out2_scale)
     M, K = A.shape
     if K != wt.k:
         raise ValueError(f'A is [{M},{K}] but the weight operand is [{wt.n},{wt.k}]')
     N = wt.n
-    if out is None:
-        out = torch.empty((M, N), dtype=torch.float32, device=A.device) if want_out else None
+    if push is not None and (not want_out or push.width != N or push.local_rows != M):
+        raise ValueError('push: the exchange slot does not match the kernel output')
+    out = None
+    if push is None and want_out:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
     out2 = torch.empty((M, N), dtype=torch.float32, device=A.device) if want_out2 else None
+    act = C.CB_ACT_RELU if relu else C.CB_ACT_NONE
     if M == 0:
+        out = push.local if push is not None else out
         return (out, out2) if want_out2 else out
-    parg, pushed = _push_arg(push, M, N, out)
-    alg = 4 * (M * K + 2 * N * K + M * N * (int(want_out) + int(want_out2) + int(add is not None))) + pushed
-    with torch.cuda.device(A.device), _Timed('gemm_rows_push' if push is not None else 'gemm_rows', alg, A.device,
-                                             flops=6 * M * N * K):
-        C.call('cb_gemm_rows', C.ptr(A), M, K, K, C.ptr(wt.hi), C.ptr(wt.lo), N, C.ptr(row_scale), C.ptr(bias),
-               C.ptr(add), N, C.CB_ACT_RELU if relu else C.CB_ACT_NONE, C.ptr(out), N, C.ptr(out2_scale),
-               C.ptr(out2), N, parg, C.stream_ptr(A.device))
-    return (out, out2) if want_out2 else out
+    if push is None:
+        alg = 4 * (M * K + 2 * N * K + M * N * (int(want_out) + int(want_out2) + int(add is not None)))
+        with torch.cuda.device(A.device), _Timed('gemm_rows', alg, A.device, flops=6 * M * N * K):
+            C.call('cb_gemm_rows', C.ptr(A), M, K, K, C.ptr(wt.hi), C.ptr(wt.lo), N, C.ptr(row_scale), C.ptr(bias),
+                   C.ptr(add), N, act, C.ptr(out), N, C.ptr(out2_scale), C.ptr(out2), N, None,
+                   C.stream_ptr(A.device))
+        return (out, out2) if want_out2 else out
+    pw = push.panel_width
+    for p in range(push.n_panels):
+        c0 = p * pw
+        alg = 4 * (M * K + 2 * pw * K + M * pw * (1 + int(want_out2) + int(add is not None))) + push.pushed_rows * pw * 4
+        with torch.cuda.device(A.device), _Timed('gemm_rows_push', alg, A.device, flops=6 * M * pw * K):
+            C.call('cb_gemm_rows', C.ptr(A), M, K, K, _pofs(wt.hi, c0 * K), _pofs(wt.lo, c0 * K), pw,
+                   C.ptr(row_scale), _pofs(bias, c0), _pofs(add, c0), N, act, C.ptr(push.panel_local[p]), pw,
+                   C.ptr(out2_scale), _pofs(out2, c0), N, ctypes.byref(push.descs[p]), C.stream_ptr(A.device))
+        push.pushed(p)
+    return (push.local, out2) if want_out2 else push.local
 
 
 def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=None, mixed=False, alpha=0.0,
                        d_x0=None, accumulate_x0=False, want_x0=False, post_scale=None, want_col_sum=False,
-                       out=None, push=None):
+                       push=None):
     """cb_gemm_rows_grad: the adjoint GEMM with the backward prologue of the layer below in its epilogue.
-    Returns (out, col_sum or None, d_x0 or None)."""
+    Returns (out, col_sum or None, d_x0 or None); with ``push`` the output goes to the exchange slot
+    (see gemm_rows_raw) and its local view is returned."""
     _need_cuda(A, row_scale, add, gate_u8, gate_f32, d_x0, post_scale)
     A, row_scale, add, gate_f32, post_scale = _f32c(A), _f32c(row_scale), _f32c(add), _f32c(gate_f32), _f32c(post_scale)
     M, K = A.shape
     if K != wt.k:
         raise ValueError(f'A is [{M},{K}] but the weight operand is [{wt.n},{wt.k}]')
     N = wt.n
-    if out is None:
-        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
-    parg, pushed = _push_arg(push, M, N, out)
+    if push is not None and (push.width != N or push.local_rows != M):
+        raise ValueError('push: the exchange slot does not match the kernel output')
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device) if push is None else push.local
     col_sum = torch.empty(N, dtype=torch.float32, device=A.device) if want_col_sum else None
     if want_x0 and d_x0 is None:
         d_x0, accumulate_x0 = torch.empty((M, N), dtype=torch.float32, device=A.device), False
     gate = gate_u8 if gate_u8 is not None else gate_f32
     ws_bytes = int(C.lib().cb_gemm_rows_grad_workspace_bytes(M, N)) if want_col_sum else 0
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=A.device) if ws_bytes else None
-    alg = 4 * (M * K + 2 * N * K + M * N * (1 + int(add is not None) + int(gate_f32 is not None) +
-                                            int(d_x0 is not None) * (1 + int(bool(accumulate_x0))))) + \
-        (M * N if gate_u8 is not None else 0) + pushed
-    with torch.cuda.device(A.device), _Timed('gemm_rows_grad_push' if push is not None else 'gemm_rows_grad', alg,
-                                             A.device, flops=6 * M * N * K):
-        C.call('cb_gemm_rows_grad', C.ptr(A), M, K, K, C.ptr(wt.hi), C.ptr(wt.lo), N, C.ptr(row_scale), C.ptr(add), N,
-               C.ptr(gate_u8), C.ptr(gate_f32), N if gate is not None else 0, int(bool(mixed)), float(alpha),
-               C.ptr(d_x0), N, int(bool(accumulate_x0)), C.ptr(post_scale), C.ptr(out), N, C.ptr(col_sum), C.ptr(ws),
-               ws_bytes, parg, C.stream_ptr(A.device))
+    extra = int(add is not None) + int(gate_f32 is not None) + int(d_x0 is not None) * (1 + int(bool(accumulate_x0)))
+    if M == 0:
+        return out, (col_sum.zero_() if col_sum is not None else None), d_x0
+    panels = [(0, N, None, out)] if push is None else \
+        [(p * push.panel_width, push.panel_width, push.descs[p], push.panel_local[p]) for p in range(push.n_panels)]
+    for p, (c0, w, desc, dst) in enumerate(panels):
+        alg = 4 * (M * K + 2 * w * K + M * w * (1 + extra)) + (M * w if gate_u8 is not None else 0) + \
+            (push.pushed_rows * w * 4 if push is not None else 0)
+        with torch.cuda.device(A.device), _Timed('gemm_rows_grad_push' if push is not None else 'gemm_rows_grad', alg,
+                                                 A.device, flops=6 * M * w * K):
+            C.call('cb_gemm_rows_grad', C.ptr(A), M, K, K, _pofs(wt.hi, c0 * K), _pofs(wt.lo, c0 * K), w,
+                   C.ptr(row_scale), _pofs(add, c0), N, _pofs(gate_u8, c0), _pofs(gate_f32, c0),
+                   N if gate is not None else 0, int(bool(mixed)), float(alpha), _pofs(d_x0, c0), N,
+                   int(bool(accumulate_x0)), C.ptr(post_scale), C.ptr(dst), dst.shape[1], _pofs(col_sum, c0), C.ptr(ws),
+                   ws_bytes, ctypes.byref(desc) if desc is not None else None, C.stream_ptr(A.device))
+        if push is not None:
+            push.pushed(p)
     return out, col_sum, d_x0
 
 
@@ -395,11 +434,13 @@ class BwdPlan:
             dtot_in, wb, row_scale=rs, add=add, gate_u8=self.gate_u8, gate_f32=self.gate_f32 if self.relu else None,
             mixed=self.mixed, alpha=self.alpha, d_x0=sink.buf if sink is not None else None,
             accumulate_x0=sink is not None and sink.buf is not None, want_x0=self.want_x0,
-            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias,
-            out=slot.local if slot is not None else None, push=slot)
+            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot)
         if sink is not None:
             sink.buf, d_x0 = d_x0, None
-        self.result = {'d_bias': col, 'd_x0': d_x0}
+        self.result = {'d_bias': col, 'd_x0': d_x0, 'G': out}
+        if out.dim() == 3:
+            # a panelled slot cannot be viewed as [M, N]: G travels in the plan, autograd gets a placeholder
+            return out.new_zeros(()).expand(dtot_in.shape[0], wb.n)
         return out
 
     def take_result(self):
@@ -471,8 +512,7 @@ class _Dense(torch.autograd.Function):
         # multi-GPU: the output is what the next aggregation gathers -> write it into the exchange buffer and
         # into the peers from the epilogue (graph.exchange() then only has to wait for everyone's pushes)
         slot = push_graph.push_slot(C.CB_BY_DST, wt.n) if (push_graph is not None and want_out) else None
-        res = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2,
-                            out=slot.local if slot is not None else None, push=slot)
+        res = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2, push=slot)
         out, out2 = res if want_out2 else (res, None)
         ctx.layout, ctx.relu = layout, relu
         ctx.has_bias, ctx.has_add = bias is not None, add is not None
@@ -492,6 +532,8 @@ class _Dense(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, dy2):
         x, weight, row_scale, out2_scale, y = ctx.saved_tensors
+        if dy is not None and dy.dim() == 3:      # the output was a panelled exchange slot [M, panels, N/panels]
+            dy = dy.reshape(dy.shape[0], -1)
         if dy is not None and dy.numel() == 0:
             dy = None
         if dy2 is not None and dy2.numel() == 0:
@@ -557,6 +599,59 @@ def dense(x, weight, layout, bias=None, add=None, relu=False, row_scale=None, ou
     return _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, want_out, want_out2)
 
 
+def _panelled(graph, ex, make_outputs, run_panel):
+    """Runs ``run_panel(p, rows_of_panel_p, outputs)`` for every panel of an exchange slot on its side stream,
+    each as soon as that panel's barrier has passed, while the compute stream goes on pushing the next panels.
+
+    The outputs are allocated ON the side stream: a block the compute-stream allocator hands out may still
+    be read by kernels queued there (e.g. the weight-gradient GEMM of the layer above reading the previous
+    dH), and the side stream deliberately does not wait for those."""
+    cur = torch.cuda.current_stream(graph.device)
+    side = ex.side_stream
+    if os.environ.get('CB_PANEL_SERIAL'):       # debugging aid: no overlap, everything on the compute stream
+        outputs = make_outputs()
+        for p in range(ex.n_panels):
+            run_panel(p, ex.rows(p, graph.num_nodes), outputs)
+        return outputs
+    with torch.cuda.stream(side):
+        outputs = make_outputs()
+        for p in range(ex.n_panels):
+            side.wait_event(ex.events[p])
+            run_panel(p, ex.rows(p, graph.num_nodes), outputs)
+    cur.wait_stream(side)
+    for t in outputs:
+        if t is not None:
+            t.record_stream(cur)
+    return outputs
+
+
+def aggregate_forward(graph, H, bias, x0, alpha, relu, want_out, want_scaled, want_mask):
+    """Exchange + fused forward aggregation; panel-pipelined when H was pushed in column panels."""
+    ex = graph.exchange(H)
+    if torch.is_tensor(ex):
+        return agg_forward_raw(graph, ex, bias, x0, alpha, relu, want_out, want_scaled, want_mask)
+    shape, dev, pw = (graph.rows, ex.width), graph.device, ex.panel_width
+
+    def make():
+        return (torch.empty(shape, dtype=torch.float32, device=dev) if want_out else None,
+                torch.empty(shape, dtype=torch.float32, device=dev) if want_scaled else None,
+                torch.empty(shape, dtype=torch.uint8, device=dev) if want_mask else None)
+
+    return _panelled(graph, ex, make, lambda p, Hp, outs: agg_forward_raw(
+        graph, Hp, bias, x0, alpha, relu, outs=outs, panel=(p * pw, pw)))
+
+
+def aggregate_gather(graph, side, X, row_scale=None):
+    """Exchange + plain gather-reduce over one side; panel-pipelined when X was pushed in column panels."""
+    ex = graph.exchange(X)
+    if torch.is_tensor(ex):
+        return agg_gather_raw(graph, side, ex, row_scale)
+    pw = ex.panel_width
+    (out,) = _panelled(graph, ex, lambda: (torch.empty((graph.rows, ex.width), dtype=torch.float32, device=graph.device),),
+                       lambda p, Xp, outs: agg_gather_raw(graph, side, Xp, row_scale, out=outs[0], panel=(p * pw, pw)))
+    return out
+
+
 class _FusedAggregate(torch.autograd.Function):
     """out = mix(act(din^-1/2 * A^T-sum(H) + b), x0), optionally also dout^-1/2 * out.
 
@@ -574,8 +669,8 @@ class _FusedAggregate(torch.autograd.Function):
         # mixed into it, otherwise a byte mask is written by the kernel
         use_out_as_mask = relu and not mixed and want_out
         want_mask = relu and need_grad and not use_out_as_mask
-        Hfull = graph.exchange(H)
-        out, out_scaled, mask = agg_forward_raw(graph, Hfull, bias, x0, alpha, relu, want_out, want_scaled, want_mask)
+        out, out_scaled, mask = aggregate_forward(graph, H, bias, x0, alpha, relu, want_out, want_scaled, want_mask)
+        ctx.h_shape = H.shape
         ctx.graph, ctx.alpha, ctx.relu, ctx.mixed = graph, alpha, relu, mixed
         ctx.has_bias, ctx.use_out_as_mask = bias is not None, use_out_as_mask
         ctx.save_for_backward(mask if want_mask else None, out if (use_out_as_mask and need_grad) else None)
@@ -610,7 +705,9 @@ class _FusedAggregate(torch.autograd.Function):
         done = ctx.my_plan.take_result() if ctx.my_plan is not None else None
         if done is not None:
             # the consumer's dX GEMM ran the prologue in its epilogue: what arrived is G itself
-            G = (d_out if d_out is not None else d_out_scaled).contiguous()
+            G = done.get('G')
+            if G is None:
+                G = (d_out if d_out is not None else d_out_scaled).contiguous()
             d_bias, d_x0 = done['d_bias'], done['d_x0']
         else:
             want_bias = ctx.has_bias and ctx.needs_input_grad[1]
@@ -623,7 +720,7 @@ class _FusedAggregate(torch.autograd.Function):
                 sink.buf, d_x0 = d_x0, None
         dH = None
         if ctx.needs_input_grad[0]:
-            dH = agg_gather_raw(graph, C.CB_BY_SRC, graph.exchange(G), None)
+            dH = aggregate_gather(graph, C.CB_BY_SRC, G).view(ctx.h_shape)
         return dH, d_bias, d_x0, None, None, None, None, None, None, None
 
 
@@ -642,12 +739,12 @@ class _CopySum(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, H, graph):
-        ctx.graph = graph
-        return agg_gather_raw(graph, C.CB_BY_DST, graph.exchange(H), None)
+        ctx.graph, ctx.h_shape = graph, H.shape
+        return aggregate_gather(graph, C.CB_BY_DST, H)
 
     @staticmethod
     def backward(ctx, d):
-        return agg_gather_raw(ctx.graph, C.CB_BY_SRC, ctx.graph.exchange(d.contiguous()), None), None
+        return aggregate_gather(ctx.graph, C.CB_BY_SRC, d.contiguous()).view(ctx.h_shape), None
 
 
 def copy_sum(H, graph):

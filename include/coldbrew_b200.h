@@ -120,21 +120,22 @@ int64_t cb_graph_workspace_bytes(const cb_graph_t* g, int side, int64_t d);
  *   out_scaled[v,:] = dout^-1/2[v] * out[v,:]                        (if out_scaled != NULL)
  *   mask[v,c] = z[v,c] > 0                                            (if mask != NULL; 1 byte each)
  *
- *   H          [N_global, d]: every source row (after the halo exchange on a sliced graph)
- *   bias       [d] or NULL;  x0, out, out_scaled, mask: [rows, d] local;  any of out/out_scaled may be
- *              NULL but not both.
+ *   H          [N_global, d]: every source row (after the halo exchange on a sliced graph), row pitch ld_h
+ *   bias       [d] or NULL;  x0, out, out_scaled, mask: [rows, d] local, row pitch ld_out (elements);  any of
+ *              out/out_scaled may be NULL but not both.  A pitch of 0 means d.  Pitches wider than d let the
+ *              caller aggregate one column panel of wider matrices (pointers pre-offset to the panel).
  */
-int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t d, const float* bias,
+int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t ld_h, int64_t d, const float* bias,
                    const float* x0, double alpha, int act, float* out, float* out_scaled,
-                   uint8_t* mask, void* workspace, int64_t workspace_bytes, void* stream);
+                   uint8_t* mask, int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Plain gather-reduce over one side of the graph, optional per-row scale of the result:
  *   out[r,:] = (row_scale ? row_scale[r] : 1) * sum_{j in row r} X[col[j],:]
  * side = CB_BY_SRC is the autograd transpose of GCN.py:238 (dH[u] = sum_{(u->v)} G[v]).
  */
-int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t d, const float* row_scale,
-                  float* out, void* workspace, int64_t workspace_bytes, void* stream);
+int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, int64_t d, const float* row_scale,
+                  float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Backward prologue of cb_agg_forward: from the gradient(s) arriving at the layer output build the
@@ -179,7 +180,8 @@ int cb_sumsq(const float* x, int64_t n, float* out, void* workspace, int64_t wor
 #define CB_MAX_PEERS 7
 typedef struct {
     int32_t n_peers;             /* 0 .. CB_MAX_PEERS */
-    int32_t reserved;
+    int32_t max_ctas;            /* > 0: cap the kernel's grid (a pushing kernel is NVLink-bound; the SMs it
+                                    leaves free run the aggregation of the previous column panel) */
     float* peer[CB_MAX_PEERS];   /* peer-mapped base of each remote [N_global, ld] buffer */
     const uint8_t* need;         /* [M] device: bit j set = remote j gathers local row m */
     int64_t row0;                /* global index of local row 0 */

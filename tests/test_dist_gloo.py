@@ -72,3 +72,37 @@ def test_slice_bounds_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert cbdist.is_row_sharded('model.model.layers_GCN.0.le') and not cbdist.is_row_sharded('x.weight')
+
+
+def _need_worker(rank, world, port, n, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        ei = O.powerlaw_graph(n, 3 * n, seed=1)
+        # drop some edges so that not every row is needed everywhere
+        ei = ei[:, torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(0))[: 2 * n]]
+        src, dst = ei
+        per = cbdist.rows_per_rank(n, world)
+        lo, hi = cbdist.slice_bounds(n, world, rank)
+        # forward: this rank gathers the sources of the in-edges of its rows
+        needed = torch.zeros(per * world, dtype=torch.uint8)
+        needed[src[(dst >= lo) & (dst < hi)]] = 1
+        mask, peers = cbdist.need_masks(needed, n, world, rank)
+        assert peers == [r for r in range(world) if r != rank] and mask.shape == (per,)
+        # brute force: bit j of mask[m] <=> some edge (lo+m -> v) has v owned by peers[j]
+        owner = torch.div(dst, per, rounding_mode='floor')
+        for j, r in enumerate(peers):
+            want = torch.zeros(per, dtype=torch.bool)
+            sel = (owner == r) & (src >= lo) & (src < hi)
+            want[src[sel] - lo] = True
+            assert torch.equal(((mask >> j) & 1).bool(), want), (rank, r)
+        open(os.path.join(out_dir, f'need{rank}'), 'w').close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n', [(2, 501), (3, 1000)])
+def test_need_masks_match_brute_force(tmp_path, world, n):
+    """Host logic of the fused exchange: which local rows each peer gathers (dist.need_masks)."""
+    mp.spawn(_need_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f'need{r}') for r in range(world))

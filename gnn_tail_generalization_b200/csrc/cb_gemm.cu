@@ -32,22 +32,16 @@ namespace cb {
 namespace tc {
 
 constexpr int BM = 128;
-// k-chunk of the rows kernel (template parameter BK): 32 fp32 = 128 bytes = one SWIZZLE_128B row, 2 stages at
-// BN = 256; or 16 fp32 = one SWIZZLE_64B row, half the bytes per stage and twice the stages (more TMA loads in
-// flight for the same shared memory: the weight operand is re-streamed from L2 for every tile)
+constexpr int BK = 32;     // fp32 per k-chunk = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;  // K of one tcgen05.mma.kind::tf32
 constexpr int THREADS = 320;
 constexpr int STG_LD = 36;  // floats per staging row (32 + 4 pad: 16-byte aligned, conflict-free)
 
-// TWO: CTA pair (cluster of 2, tcgen05 cta_group::2).  The pair computes a 256-row tile per MMA; each CTA stages
-// its own 128 rows of A and HALF of the weight chunk (BN/2 rows of Bt), so the weight re-stream from L2 -- the
-// dominant L2->SM traffic of the kernel -- is halved per SM and a third stage fits.
-template <int BN, int BK, bool TWO = false>
+template <int BN>
 struct Cfg {
-    static constexpr int B_ROWS = TWO ? BN / 2 : BN;
-    static constexpr int STAGES = TWO ? 3 : (BN >= 256 ? 2 : (BN >= 128 ? 3 : 4)) * (32 / BK);
-    static constexpr int A_BYTES = BM * BK * 4;   // 16 KB at BK = 32
-    static constexpr int B_BYTES = B_ROWS * BK * 4;
+    static constexpr int STAGES = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
+    static constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+    static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
     static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
@@ -148,39 +142,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_tf32_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// commit of a CTA pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(bar), "h"((uint16_t)3)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at shared offset `bar` of CTA `rank` of this cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-        ::"r"(bar), "r"(rank)
-        : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -209,16 +170,13 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
 }
 
-// K-major, swizzled shared-memory matrix descriptor: rows of ROW_BYTES (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B),
-// 8-row swizzle atoms of 8 * ROW_BYTES
-template <int ROW_BYTES>
-__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr) {
-    static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "swizzle span");
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms of 1024 bytes)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
     uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;     // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61; // SWIZZLE_128B / SWIZZLE_64B
+    d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
     return d;
 }
 
@@ -247,18 +205,12 @@ __device__ __forceinline__ void push_to_peers(const cb_peer_push_t& ps, int64_t 
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int BN, int BK, bool GRAD, bool TWO>
+template <int BN, bool GRAD>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
             const __grid_constant__ CUtensorMap map_blo, const GemmArgs g) {
-    using C = Cfg<BN, BK, TWO>;
+    using C = Cfg<BN>;
     constexpr int STAGES = C::STAGES;
-    // CTA pair: rank 0 (the leader) issues the MMAs of both; tile t of the pair loop covers rows
-    // (2 t + rank) * 128 ..; single CTA: rank 0, stride gridDim.x
-    const uint32_t rank = TWO ? cluster_ctarank() : 0u;
-    const int64_t tile0 = TWO ? (int64_t)(blockIdx.x >> 1) * 2 + rank : (int64_t)blockIdx.x;
-    const int64_t tile_step = TWO ? (int64_t)(gridDim.x >> 1) * 2 : (int64_t)gridDim.x;
-    const int64_t tile_end = TWO ? ((g.n_tiles_m + 1) >> 1) * 2 : g.n_tiles_m;   // both CTAs of a pair iterate alike
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -286,31 +238,23 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             tma_prefetch_desc(&map_blo);
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(full_bar(s), 1);
-                mbar_init(ready_bar(s), TWO ? 8 : 4);     // pair: the split warps of both CTAs report to the leader
+                mbar_init(ready_bar(s), 4);
                 mbar_init(empty_bar(s), 1);
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(tfull_bar(a), 1);
-                mbar_init(tempty_bar(a), TWO ? 8 : 4);    // pair: the epilogue warps of both CTAs
+                mbar_init(tempty_bar(a), 4);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        if (TWO) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                         "r"((uint32_t)C::TMEM_COLS)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                         "r"((uint32_t)C::TMEM_COLS)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
-    if (TWO) cluster_sync_all();     // the peer's barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -320,8 +264,8 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (warp == 0) {
         // ===== TMA producer =====
         uint32_t it = 0;
-        for (int64_t tile = tile0; tile < tile_end; tile += tile_step) {
-            if (tile < g.n_tiles_m) {   // epilogue operands of this tile -> L2 (the epilogue reads them about one tile later)
+        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x) {
+            {   // epilogue operands of this tile -> L2 (the epilogue reads them about one tile later)
                 const int64_t r0 = tile * BM;
                 const int nr = (int)(g.M - r0 < BM ? g.M - r0 : BM);
                 const int nc = g.N - n0 < BN ? g.N - n0 : BN;
@@ -338,19 +282,18 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 if (lane == 0) {
                     mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
-                    tma_load_2d(a_hi(s), &map_a, full_bar(s), kc * BK, (int)(tile * BM));   // rows >= M: zero fill
-                    tma_load_2d(b_hi(s), &map_bhi, full_bar(s), kc * BK, n0 + (int)rank * C::B_ROWS);
-                    tma_load_2d(b_lo(s), &map_blo, full_bar(s), kc * BK, n0 + (int)rank * C::B_ROWS);
+                    tma_load_2d(a_hi(s), &map_a, full_bar(s), kc * BK, (int)(tile * BM));
+                    tma_load_2d(b_hi(s), &map_bhi, full_bar(s), kc * BK, n0);
+                    tma_load_2d(b_lo(s), &map_blo, full_bar(s), kc * BK, n0);
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (pair: the leader only; M = 256 spans both CTAs) =====
-        constexpr uint32_t idesc = TWO ? ((instr_desc_tf32<BN>() & ~(0x1Fu << 24)) | ((uint32_t)(2 * BM >> 4) << 24))
-                                       : instr_desc_tf32<BN>();
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = instr_desc_tf32<BN>();
         uint32_t it = 0, tl = 0;
-        for (int64_t tile = tile0; tile < tile_end && rank == 0; tile += tile_step, ++tl) {
+        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x, ++tl) {
             const int acc = tl & 1u;
             const uint32_t aph = (tl >> 1) & 1u;
             mbar_wait(tempty_bar(acc), aph ^ 1u);
@@ -359,28 +302,14 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             for (int kc = 0; kc < nk; ++kc, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
-                if (!TWO) mbar_wait(full_bar(s), ph);   // pair: implied by ready (every split warp waited for its CTA's)
+                mbar_wait(full_bar(s), ph);
                 mbar_wait(ready_bar(s), ph);
                 tc_fence_after();
-                if (lane == 0 && TWO) {
-                    const uint64_t dah = smem_desc_kmajor<BK * 4>(a_hi(s));
-                    const uint64_t dal = smem_desc_kmajor<BK * 4>(a_lo(s));
-                    const uint64_t dbh = smem_desc_kmajor<BK * 4>(b_hi(s));
-                    const uint64_t dbl = smem_desc_kmajor<BK * 4>(b_lo(s));
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-                        umma_tf32_2cta(d_tmem, dal + adv, dbh + adv, idesc, (kc | k) != 0);
-                        umma_tf32_2cta(d_tmem, dah + adv, dbl + adv, idesc, 1u);
-                        umma_tf32_2cta(d_tmem, dah + adv, dbh + adv, idesc, 1u);
-                    }
-                    umma_commit_2cta(empty_bar(s));
-                    if (kc == nk - 1) umma_commit_2cta(tfull_bar(acc));
-                } else if (lane == 0) {
-                    const uint64_t dah = smem_desc_kmajor<BK * 4>(a_hi(s));
-                    const uint64_t dal = smem_desc_kmajor<BK * 4>(a_lo(s));
-                    const uint64_t dbh = smem_desc_kmajor<BK * 4>(b_hi(s));
-                    const uint64_t dbl = smem_desc_kmajor<BK * 4>(b_lo(s));
+                if (lane == 0) {
+                    const uint64_t dah = smem_desc_sw128(a_hi(s));
+                    const uint64_t dal = smem_desc_sw128(a_lo(s));
+                    const uint64_t dbh = smem_desc_sw128(b_hi(s));
+                    const uint64_t dbl = smem_desc_sw128(b_lo(s));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // 32 bytes per k-step
@@ -398,7 +327,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // ===== split warps: raw fp32 A chunk -> TF32 hi (in place) + lo =====
         const int t = threadIdx.x - 64;
         uint32_t it = 0;
-        for (int64_t tile = tile0; tile < tile_end; tile += tile_step) {
+        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x) {
             for (int kc = 0; kc < nk; ++kc, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
@@ -406,7 +335,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 uint8_t* hi_p = smem_gen + (size_t)s * C::STAGE_BYTES;
                 uint8_t* lo_p = hi_p + C::A_BYTES;
 #pragma unroll
-                for (int i = 0; i < C::A_BYTES / 16 / 128; ++i) {   // 8 (BK = 32) or 4 (BK = 16) float4 per thread
+                for (int i = 0; i < C::A_BYTES / 16 / 128; ++i) {
                     const int idx = t + 128 * i;
                     const float4 v = *reinterpret_cast<const float4*>(hi_p + 16 * idx);
                     uint4 h, l;
@@ -419,10 +348,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
-                    if (TWO && rank != 0) mbar_arrive_remote(ready_bar(s), 0);
-                    else mbar_arrive(ready_bar(s));
-                }
+                if (lane == 0) mbar_arrive(ready_bar(s));
             }
         }
     } else {
@@ -438,7 +364,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             __syncwarp();
         }
         uint32_t tl = 0;
-        for (int64_t tile = tile0; tile < tile_end; tile += tile_step, ++tl) {
+        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x, ++tl) {
             const int acc = tl & 1u;
             const uint32_t aph = (tl >> 1) & 1u;
             mbar_wait(tfull_bar(acc), aph);
@@ -452,10 +378,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 if (j == n_slabs - 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) {
-                        if (TWO && rank != 0) mbar_arrive_remote(tempty_bar(acc), 0);
-                        else mbar_arrive(tempty_bar(acc));
-                    }
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -694,17 +617,11 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     tc_fence_before();
     __syncthreads();
-    if (TWO) cluster_sync_all();     // the peer may still be reading tensor memory written by the leader's MMAs
     if (warp == 0) {
         tc_fence_after();
-        if (TWO)
-            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                         "r"((uint32_t)C::TMEM_COLS)
-                         : "memory");
-        else
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                         "r"((uint32_t)C::TMEM_COLS)
-                         : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
     }
 }
 
@@ -754,17 +671,15 @@ static EncodeTiledFn encode_fn() {
 }
 
 // [rows, cols] fp32 row-major with a row pitch of ld floats; box = box_rows x 32 floats, SWIZZLE_128B
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                    int bk) {
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     CB_REQUIRE(fn != nullptr, CB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
-                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
@@ -773,70 +688,25 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     return CB_OK;
 }
 
-// k-chunk width of the rows kernel: 32 (default) or 16 (CB_GEMM_BK=16)
-static int gemm_bk() {
-    static const int bk = (getenv("CB_GEMM_BK") && atoi(getenv("CB_GEMM_BK")) == 16) ? 16 : 32;
-    return bk;
-}
-// CTA pairs (cta_group::2) for the 256-wide tile: on unless CB_GEMM_2CTA=0
-static bool gemm_two_enabled() {
-    static const bool on = !(getenv("CB_GEMM_2CTA") && atoi(getenv("CB_GEMM_2CTA")) == 0);
-    return on;
-}
-static bool gemm_use_two(int64_t n_tiles_m, int bn) { return gemm_two_enabled() && bn == 256 && gemm_bk() == 32 && n_tiles_m >= 2; }
-
-// grid.x of the persistent rows kernel (CTAs; pairs count twice)
-static int64_t gemm_grid_x(int64_t n_tiles_m, int bn, int max_ctas = 0) {
-    const int64_t sms = sm_count();
-    if (gemm_use_two(n_tiles_m, bn)) {
-        int64_t pairs = (n_tiles_m + 1) / 2;
-        if (pairs > sms / 2) pairs = sms / 2;
-        if (max_ctas > 1 && max_ctas / 2 < pairs) pairs = max_ctas / 2;
-        return 2 * pairs;
-    }
-    int64_t g = n_tiles_m < sms ? n_tiles_m : sms;
+static int64_t gemm_grid_x(int64_t n_tiles_m, int max_ctas = 0) {
+    int64_t g = n_tiles_m < sm_count() ? n_tiles_m : sm_count();
     return (max_ctas > 0 && max_ctas < g) ? max_ctas : g;
-}
-
-template <int BN, int BK, bool GRAD, bool TWO>
-static int launch_gemm_cfg(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const GemmArgs& g,
-                           cudaStream_t st) {
-    using C = Cfg<BN, BK, TWO>;
-    static bool configured = false;
-    if (!configured) {
-        CB_CUDA(cudaFuncSetAttribute(k_gemm_rows<BN, BK, GRAD, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     C::SMEM_BYTES));
-        configured = true;
-    }
-    dim3 grid((unsigned)gemm_grid_x(g.n_tiles_m, BN, g.push.max_ctas), (unsigned)ceil_div(g.N, BN));
-    if (TWO) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(THREADS);
-        cfg.dynamicSmemBytes = C::SMEM_BYTES;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        CB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_rows<BN, BK, GRAD, TWO>, ma, mh, ml, g));
-        count_launch();
-        return CB_OK;
-    }
-    k_gemm_rows<BN, BK, GRAD, TWO><<<grid, THREADS, C::SMEM_BYTES, st>>>(ma, mh, ml, g);
-    CB_LAUNCH_CHECK();
-    return CB_OK;
 }
 
 template <int BN, bool GRAD>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const GemmArgs& g,
                        cudaStream_t st) {
-    if (BN == 256 && gemm_use_two(g.n_tiles_m, BN)) return launch_gemm_cfg<256, 32, GRAD, true>(ma, mh, ml, g, st);
-    return gemm_bk() == 32 ? launch_gemm_cfg<BN, 32, GRAD, false>(ma, mh, ml, g, st)
-                           : launch_gemm_cfg<BN, 16, GRAD, false>(ma, mh, ml, g, st);
+    using C = Cfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        CB_CUDA(cudaFuncSetAttribute(k_gemm_rows<BN, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((unsigned)gemm_grid_x(g.n_tiles_m, g.push.max_ctas), (unsigned)ceil_div(g.N, BN));
+    k_gemm_rows<BN, GRAD><<<grid, THREADS, C::SMEM_BYTES, st>>>(ma, mh, ml, g);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
 }
 
 
@@ -1167,13 +1037,11 @@ int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float*
                CB_E_UNSUPPORTED, "cb_gemm_rows: epilogue buffers must be 16-byte aligned, pitches multiples of 4");
     const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
     CUtensorMap ma, mh, ml;
-    const int bk = tc::gemm_bk();
-    const int b_rows = tc::gemm_use_two(ceil_div(M, tc::BM), bn) ? bn / 2 : bn;   // a CTA pair stages half each
-    int rc = tc::make_map(&ma, A, M, K, lda, tc::BM, bk);
+    int rc = tc::make_map(&ma, A, M, K, lda, tc::BM);
     if (rc) return rc;
-    rc = tc::make_map(&mh, Bt_hi, N, K, K, b_rows, bk);
+    rc = tc::make_map(&mh, Bt_hi, N, K, K, bn);
     if (rc) return rc;
-    rc = tc::make_map(&ml, Bt_lo, N, K, K, b_rows, bk);
+    rc = tc::make_map(&ml, Bt_lo, N, K, K, bn);
     if (rc) return rc;
     tc::GemmArgs g{};
     g.M = M; g.N = (int)N; g.K = (int)K;
@@ -1189,7 +1057,7 @@ int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float*
 
 int64_t cb_gemm_rows_grad_workspace_bytes(int64_t M, int64_t N) {
     if (M <= 0 || N <= 0) return 0;
-    return (int64_t)cb::sm_count() * N * (int64_t)sizeof(float);   // one row of N column sums per CTA, any grid
+    return cb::tc::gemm_grid_x(cb::ceil_div(M, cb::tc::BM)) * N * (int64_t)sizeof(float);
 }
 
 int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const float* Bt_hi, const float* Bt_lo,
@@ -1219,13 +1087,11 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
                "cb_gemm_rows_grad: workspace smaller than cb_gemm_rows_grad_workspace_bytes()");
     const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
     CUtensorMap ma, mh, ml;
-    const int bk = tc::gemm_bk();
-    const int b_rows = tc::gemm_use_two(ceil_div(M, tc::BM), bn) ? bn / 2 : bn;   // a CTA pair stages half each
-    int rc = tc::make_map(&ma, A, M, K, lda, tc::BM, bk);
+    int rc = tc::make_map(&ma, A, M, K, lda, tc::BM);
     if (rc) return rc;
-    rc = tc::make_map(&mh, Bt_hi, N, K, K, b_rows, bk);
+    rc = tc::make_map(&mh, Bt_hi, N, K, K, bn);
     if (rc) return rc;
-    rc = tc::make_map(&ml, Bt_lo, N, K, K, b_rows, bk);
+    rc = tc::make_map(&ml, Bt_lo, N, K, K, bn);
     if (rc) return rc;
     tc::GemmArgs g{};
     g.M = M; g.N = (int)N; g.K = (int)K;
@@ -1245,7 +1111,7 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
     if (rc) return rc;
     if (col_sum) {
         tc::k_col_final<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(
-            (const float*)workspace, (int)tc::gemm_grid_x(g.n_tiles_m, bn, g.push.max_ctas), (int)N, col_sum);
+            (const float*)workspace, (int)tc::gemm_grid_x(g.n_tiles_m, g.push.max_ctas), (int)N, col_sum);
         CB_LAUNCH_CHECK();
     }
     return CB_OK;

@@ -258,6 +258,8 @@ class TricksComb(nn.Module):
                 (last and self.has_residual_MLP and not AcontainsB(trick, ['Jumping']) and
                  (mix_fused or not mixes) and ((not self.training) or self.args.dropout == 0)))
             my_plan = _ops.new_plan() if single_consumer else None
+            if my_plan is not None and last:
+                my_plan.row_sparse_hint = True     # the layer under the output head (see ops.BwdPlan)
             dx_plan = prev_plan if (xs_next is not None or (x_in is not None and x_in is x)) else None
             out, out_scaled, se_reg = layer.fused(
                 graph, xs_next if xs_next is not None else x_in, prescaled=xs_next is not None,

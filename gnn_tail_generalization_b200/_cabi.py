@@ -41,7 +41,7 @@ SYMBOLS = {
     'cb_graph_query': (_int, [_vp, _int, _vp]),
     'cb_graph_workspace_bytes': (_i64, [_vp, _int, _i64]),
     'cb_agg_forward': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
-    'cb_agg_gather': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
+    'cb_agg_gather': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_prep_workspace_bytes': (_i64, [_i64, _i64]),
     'cb_agg_backward_prep': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _dbl, _vp, _vp, _vp, _int, _vp,
                                     _i64, _vp]),
@@ -58,7 +58,7 @@ SYMBOLS = {
     'cb_peer_free': (_int, [_vp]),
     'cb_gemm_rows_grad_workspace_bytes': (_i64, [_i64, _i64]),
     'cb_gemm_rows_grad': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _int, _dbl,
-                                 _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
+                                 _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
     'cb_gemm_tn_supported': (_int, [_i64, _i64, _i64]),
     'cb_gemm_tn_workspace_bytes': (_i64, [_i64, _i64, _i64]),
     'cb_gemm_tn': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp, _i64, _vp, _i64, _vp]),

@@ -43,6 +43,7 @@ struct AggArgs {
     const float* out2_scale;  // [rows]
     float* out2;              // [rows, d] or null
     uint8_t* mask;            // [rows, d] or null
+    const uint8_t* live;      // [n_src] or null: rows of X with live[s] == 0 are all-zero and are not gathered
 };
 
 template <int VEC>
@@ -107,7 +108,9 @@ __device__ __forceinline__ void epilogue_store(const AggArgs& a, int64_t row, in
     if (a.mask) Vec<VEC>::store_mask(a.mask + off, z);
 }
 
-template <int VEC, int LPR, int NCH, int UNROLL>
+// LIVE: X is row-sparse (e.g. the gradient arriving from a loss over the train rows only); a.live says which
+// source rows can be non-zero.  Skipping an all-zero row leaves every fp32 sum unchanged (x + 0 = x).
+template <int VEC, int LPR, int NCH, int UNROLL, bool LIVE>
 __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
     constexpr int GROUPS = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -146,13 +149,16 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
 
     for (int64_t base = beg; base < end; base += LPR) {
         const int n = (int)(end - base < LPR ? end - base : LPR);
-        const int my = sub < n ? __ldg(a.col + base + sub) : 0;
+        int my = sub < n ? __ldg(a.col + base + sub) : 0;
+        if (LIVE && sub < n && __ldg(a.live + my) == 0) my |= (int)0x80000000;   // N < 2^31: the sign bit is free
         for (int k = 0; k < n; k += UNROLL) {
             float v[UNROLL][NCH][VEC];
+            bool on[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int s = __shfl_sync(gmask, my, (k + u) & (LPR - 1), LPR);
-                if (k + u < n) {
+                on[u] = (k + u < n) && (!LIVE || s >= 0);
+                if (on[u]) {
                     const float* xr = a.X + (int64_t)s * a.x_ld;
 #pragma unroll
                     for (int ch = 0; ch < NCH; ++ch)
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                if (k + u < n) {
+                if (on[u]) {
 #pragma unroll
                     for (int ch = 0; ch < NCH; ++ch)
                         if (cval[ch]) {
@@ -226,7 +232,10 @@ static int launch_cfg(const AggArgs& a, cudaStream_t st) {
     if (tasks > 0) {
         const int64_t blocks = ceil_div(tasks, (int64_t)WARPS * GROUPS);
         CB_REQUIRE(blocks < (int64_t)INT32_MAX, CB_E_UNSUPPORTED, "aggregation grid too large");
-        k_agg<VEC, LPR, NCH, U><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+        if (a.live)
+            k_agg<VEC, LPR, NCH, U, true><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+        else
+            k_agg<VEC, LPR, NCH, U, false><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
         CB_LAUNCH_CHECK();
     }
     if (a.n_chunks > 0) {
@@ -322,7 +331,8 @@ int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t ld_h, int64_t d,
 }
 
 int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, int64_t d, const float* row_scale,
-                  float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream) {
+                  const uint8_t* row_live, float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes,
+                  void* stream) {
     using namespace cb;
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_gather: graph is NULL");
     CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_agg_gather: unknown side");
@@ -338,6 +348,7 @@ int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, i
     a.row_scale = row_scale;
     a.act = CB_ACT_NONE;
     a.out = out;
+    a.live = row_live;
     return run_agg(g, side, a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

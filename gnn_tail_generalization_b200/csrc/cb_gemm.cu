@@ -76,6 +76,7 @@ struct GemmArgs {
     int accumulate_x0;
     const float* post_scale;  // [M] scale of the stored value (din^-1/2), or null
     float* col_partial;       // [gridDim.x, N] per-CTA column sums of dz, or null
+    uint8_t* row_live;        // [M] set to 1 where the stored row has a non-zero element, or null
     // ---- multi-GPU: rows of `out` are also stored into the peers that gather them (cb_peer_push_t) ----
     cb_peer_push_t push;
 };
@@ -519,6 +520,16 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                             if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_out), v[itr]);
                     }
                     if (g.push.n_peers) push_to_peers(g.push, rbase, col, nval, v);
+                    if (g.row_live) {
+                        // a row's 32 columns of this slab sit in the 8 lanes with equal rsub: one ballot per row group
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const uint32_t bits = (__float_as_uint(v[itr].x) | __float_as_uint(v[itr].y) |
+                                                   __float_as_uint(v[itr].z) | __float_as_uint(v[itr].w)) << 1;  // -0 is 0
+                            const uint32_t b = __ballot_sync(0xffffffffu, itr < nval && bits != 0u);
+                            if (c4 == 0 && ((b >> (rsub * 8)) & 0xffu)) g.row_live[rbase + itr * 4] = 1;
+                        }
+                    }
                     __syncwarp();
                     continue;
                 }
@@ -1064,7 +1075,8 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
                       int64_t N, const float* row_scale, const float* add, int64_t ld_add, const uint8_t* gate_u8,
                       const float* gate_f32, int64_t ld_gate, int mixed, double alpha, float* d_x0, int64_t ld_dx0,
                       int accumulate_x0, const float* post_scale, float* out, int64_t ld_out, float* col_sum,
-                      void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push, void* stream) {
+                      uint8_t* row_live, void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push,
+                      void* stream) {
     using namespace cb;
     CB_REQUIRE(!push || (push->n_peers >= 0 && push->n_peers <= CB_MAX_PEERS && (push->n_peers == 0 ||
                          (push->need && push->ld >= N && push->ld % 4 == 0))), CB_E_INVALID,
@@ -1103,6 +1115,7 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
     g.d_x0 = d_x0; g.ld_dx0 = ld_dx0; g.accumulate_x0 = d_x0 ? accumulate_x0 : 0;
     g.post_scale = post_scale;
     g.col_partial = col_sum ? (float*)workspace : nullptr;
+    g.row_live = row_live;
     if (push) g.push = *push;
     cudaStream_t st = (cudaStream_t)stream;
     rc = bn == 64 ? tc::launch_gemm<64, true>(ma, mh, ml, g, st)

@@ -273,6 +273,18 @@ class SlicedGraph(GraphHandle):
                 local_rows.shape[1] * local_rows.element_size()
         return full
 
+    def exchange_flags(self, local_flags):
+        if self.world == 1:
+            return local_flags
+        per = rows_per_rank(self.num_nodes, self.world)
+        send = local_flags
+        if local_flags.shape[0] != per:
+            send = local_flags.new_zeros(per)
+            send[:local_flags.shape[0]] = local_flags
+        full = local_flags.new_empty(per * self.world)
+        dist.all_gather_into_tensor(full, send.contiguous(), group=self.group)
+        return full[:self.num_nodes]
+
     def allreduce_sum(self, t):
         return allreduce_scalar_sum(t, self.world, self.group)
 

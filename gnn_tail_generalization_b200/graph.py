@@ -130,6 +130,10 @@ class GraphHandle:
         """Returns the matrix holding every source row the owned rows gather from."""
         return local_rows
 
+    def exchange_flags(self, local_flags):
+        """Per-row byte flags of every rank's rows (identity on a whole graph)."""
+        return local_flags
+
     def push_slot(self, side, d):
         """Exchange buffer the producing kernel should write into (node-sliced graphs with peer pushes)."""
         return None

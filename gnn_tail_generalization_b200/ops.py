@@ -108,9 +108,10 @@ def agg_forward_raw(graph, H, bias=None, x0=None, alpha=0.0, relu=False, want_ou
     return out, out_scaled, mask
 
 
-def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None):
+def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None, live=None):
     """out[r] = row_scale[r] * sum_{j in row r} X[col[j]]  over one CSR side of the graph.
-    panel=(c0, w): X is a [N_global, w] column panel; ``out`` is the preallocated full-width result."""
+    panel=(c0, w): X is a [N_global, w] column panel; ``out`` is the preallocated full-width result.
+    live: uint8 [N_global], 0 where the row of X is known to be all-zero (not gathered)."""
     _need_cuda(X, row_scale)
     X, row_scale = _f32c(X), _f32c(row_scale)
     d = X.shape[1]
@@ -124,10 +125,12 @@ def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None):
     D = out.shape[1]
     ws, ws_bytes = graph.workspace(side, d)
     alg = gather_alg_bytes(graph, side, d, 1, 1, False, int(row_scale is not None))
-    with torch.cuda.device(X.device), _Timed('agg_gather_dst' if side == C.CB_BY_DST else 'agg_gather_src', alg,
-                                             X.device):
-        C.call('cb_agg_gather', graph.handle, side, C.ptr(X), d, d, C.ptr(row_scale), _pofs(out, c0), D, C.ptr(ws),
-               ws_bytes, C.stream_ptr(X.device))
+    if live is not None and (live.dtype != torch.uint8 or live.numel() != graph.num_nodes):
+        raise ValueError('live must be uint8 [num_nodes]')
+    name = ('agg_gather_dst' if side == C.CB_BY_DST else 'agg_gather_src') + ('_rowsparse' if live is not None else '')
+    with torch.cuda.device(X.device), _Timed(name, alg, X.device):
+        C.call('cb_agg_gather', graph.handle, side, C.ptr(X), d, d, C.ptr(row_scale), C.ptr(live), _pofs(out, c0), D,
+               C.ptr(ws), ws_bytes, C.stream_ptr(X.device))
     return out
 
 
@@ -249,10 +252,11 @@ def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_s
 
 def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=None, mixed=False, alpha=0.0,
                        d_x0=None, accumulate_x0=False, want_x0=False, post_scale=None, want_col_sum=False,
-                       push=None):
+                       push=None, row_live=None):
     """cb_gemm_rows_grad: the adjoint GEMM with the backward prologue of the layer below in its epilogue.
     Returns (out, col_sum or None, d_x0 or None); with ``push`` the output goes to the exchange slot
-    (see gemm_rows_raw) and its local view is returned."""
+    (see gemm_rows_raw) and its local view is returned.  row_live: zeroed uint8 [M] that receives 1 for
+    every output row holding a non-zero element."""
     _need_cuda(A, row_scale, add, gate_u8, gate_f32, d_x0, post_scale)
     A, row_scale, add, gate_f32, post_scale = _f32c(A), _f32c(row_scale), _f32c(add), _f32c(gate_f32), _f32c(post_scale)
     M, K = A.shape
@@ -281,8 +285,9 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
             C.call('cb_gemm_rows_grad', C.ptr(A), M, K, K, _pofs(wt.hi, c0 * K), _pofs(wt.lo, c0 * K), w,
                    C.ptr(row_scale), _pofs(add, c0), N, _pofs(gate_u8, c0), _pofs(gate_f32, c0),
                    N if gate is not None else 0, int(bool(mixed)), float(alpha), _pofs(d_x0, c0), N,
-                   int(bool(accumulate_x0)), C.ptr(post_scale), C.ptr(dst), dst.shape[1], _pofs(col_sum, c0), C.ptr(ws),
-                   ws_bytes, ctypes.byref(desc) if desc is not None else None, C.stream_ptr(A.device))
+                   int(bool(accumulate_x0)), C.ptr(post_scale), C.ptr(dst), dst.shape[1], _pofs(col_sum, c0),
+                   C.ptr(row_live), C.ptr(ws), ws_bytes, ctypes.byref(desc) if desc is not None else None,
+                   C.stream_ptr(A.device))
         if push is not None:
             push.pushed(p)
     return out, col_sum, d_x0
@@ -402,7 +407,7 @@ class BwdPlan:
     already done.  The caller (TricksComb) creates a plan only where the single-consumer condition holds by
     construction."""
     __slots__ = ('kind', 'graph', 'gate_u8', 'gate_f32', 'relu', 'mixed', 'alpha', 'want_bias', 'want_x0',
-                 'x0_sink', 'slot', 'result')
+                 'x0_sink', 'slot', 'result', 'row_sparse_hint')
 
     def __init__(self):
         self.kind = None       # 'relu_bias' (Linear + relu) | 'prep' (fused aggregation)
@@ -411,6 +416,9 @@ class BwdPlan:
         self.relu = self.mixed = self.want_bias = self.want_x0 = False
         self.alpha = 0.0
         self.slot = None       # 'out' | 'out_scaled': which output of the aggregation the consumer reads
+        # set by the caller for the layer under the output head: its gradient is row-sparse when the loss reads
+        # the train rows only, so the GEMM also records which rows of G are non-zero and the gather skips the rest
+        self.row_sparse_hint = False
 
     def run(self, dtot_in, wb, row_scale, add):
         """Called from the consumer's backward: dX GEMM + this plan's prologue.  ``row_scale``/``add`` are
@@ -430,14 +438,15 @@ class BwdPlan:
         if add is not None and sink is not None and sink.buf is not None:
             return None     # the kernel keeps one [M, N] epilogue input: the caller runs the two-kernel path
         slot = g.push_slot(C.CB_BY_SRC, wb.n)    # G is what the transposed aggregation gathers
+        live = torch.zeros(dtot_in.shape[0], dtype=torch.uint8, device=dtot_in.device) if self.row_sparse_hint else None
         out, col, d_x0 = gemm_rows_grad_raw(
             dtot_in, wb, row_scale=rs, add=add, gate_u8=self.gate_u8, gate_f32=self.gate_f32 if self.relu else None,
             mixed=self.mixed, alpha=self.alpha, d_x0=sink.buf if sink is not None else None,
             accumulate_x0=sink is not None and sink.buf is not None, want_x0=self.want_x0,
-            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot)
+            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot, row_live=live)
         if sink is not None:
             sink.buf, d_x0 = d_x0, None
-        self.result = {'d_bias': col, 'd_x0': d_x0, 'G': out}
+        self.result = {'d_bias': col, 'd_x0': d_x0, 'G': out, 'live': live}
         if out.dim() == 3:
             # a panelled slot cannot be viewed as [M, N]: G travels in the plan, autograd gets a placeholder
             return out.new_zeros(()).expand(dtot_in.shape[0], wb.n)
@@ -641,14 +650,18 @@ def aggregate_forward(graph, H, bias, x0, alpha, relu, want_out, want_scaled, wa
         graph, Hp, bias, x0, alpha, relu, outs=outs, panel=(p * pw, pw)))
 
 
-def aggregate_gather(graph, side, X, row_scale=None):
-    """Exchange + plain gather-reduce over one side; panel-pipelined when X was pushed in column panels."""
+def aggregate_gather(graph, side, X, row_scale=None, live=None):
+    """Exchange + plain gather-reduce over one side; panel-pipelined when X was pushed in column panels.
+    live: uint8 [rows] flags of the local rows of X (0 = all-zero row), exchanged like the rows themselves."""
+    if live is not None:
+        live = graph.exchange_flags(live)
     ex = graph.exchange(X)
     if torch.is_tensor(ex):
-        return agg_gather_raw(graph, side, ex, row_scale)
+        return agg_gather_raw(graph, side, ex, row_scale, live=live)
     pw = ex.panel_width
     (out,) = _panelled(graph, ex, lambda: (torch.empty((graph.rows, ex.width), dtype=torch.float32, device=graph.device),),
-                       lambda p, Xp, outs: agg_gather_raw(graph, side, Xp, row_scale, out=outs[0], panel=(p * pw, pw)))
+                       lambda p, Xp, outs: agg_gather_raw(graph, side, Xp, row_scale, out=outs[0], panel=(p * pw, pw),
+                                                          live=live))
     return out
 
 
@@ -708,8 +721,9 @@ class _FusedAggregate(torch.autograd.Function):
             G = done.get('G')
             if G is None:
                 G = (d_out if d_out is not None else d_out_scaled).contiguous()
-            d_bias, d_x0 = done['d_bias'], done['d_x0']
+            d_bias, d_x0, live = done['d_bias'], done['d_x0'], done.get('live')
         else:
+            live = None
             want_bias = ctx.has_bias and ctx.needs_input_grad[1]
             want_x0 = ctx.mixed and ctx.needs_input_grad[2]
             sink = ctx.x0_sink if want_x0 else None
@@ -720,7 +734,7 @@ class _FusedAggregate(torch.autograd.Function):
                 sink.buf, d_x0 = d_x0, None
         dH = None
         if ctx.needs_input_grad[0]:
-            dH = aggregate_gather(graph, C.CB_BY_SRC, G).view(ctx.h_shape)
+            dH = aggregate_gather(graph, C.CB_BY_SRC, G, live=live).view(ctx.h_shape)
         return dH, d_bias, d_x0, None, None, None, None, None, None, None
 
 

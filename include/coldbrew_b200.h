@@ -133,9 +133,13 @@ int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t ld_h, int64_t d,
  * Plain gather-reduce over one side of the graph, optional per-row scale of the result:
  *   out[r,:] = (row_scale ? row_scale[r] : 1) * sum_{j in row r} X[col[j],:]
  * side = CB_BY_SRC is the autograd transpose of GCN.py:238 (dH[u] = sum_{(u->v)} G[v]).
+ * row_live [N_global] bytes or NULL: X rows with row_live[s] == 0 are known to be all-zero and are skipped (the
+ * gradient of a loss over the train rows only is row-sparse after the output head; x + 0 = x, so the sums are
+ * unchanged).  cb_gemm_rows_grad can produce the flags of its output.
  */
 int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, int64_t d, const float* row_scale,
-                  float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
+                  const uint8_t* row_live, float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes,
+                  void* stream);
 
 /*
  * Backward prologue of cb_agg_forward: from the gradient(s) arriving at the layer output build the
@@ -230,6 +234,8 @@ int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float*
  *   out[m,n] = (post_scale ? post_scale[m] : 1) * dz                (G of the layer below; [M, ld_out])
  *   col_sum[n] = sum_m dz[m,n]                                       (bias gradient; per-CTA partials in
  *                                                                     `workspace`, added in CTA order)
+ *   row_live[m] = 1 if any out[m,:] != 0                             (if row_live; the caller zeroes it first;
+ *                                                                     feeds cb_agg_gather's row_live)
  * workspace: cb_gemm_rows_grad_workspace_bytes(M, N), needed when col_sum != NULL.
  */
 int64_t cb_gemm_rows_grad_workspace_bytes(int64_t M, int64_t N);
@@ -237,7 +243,8 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
                       int64_t N, const float* row_scale, const float* add, int64_t ld_add, const uint8_t* gate_u8,
                       const float* gate_f32, int64_t ld_gate, int mixed, double alpha, float* d_x0, int64_t ld_dx0,
                       int accumulate_x0, const float* post_scale, float* out, int64_t ld_out, float* col_sum,
-                      void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push, void* stream);
+                      uint8_t* row_live, void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push,
+                      void* stream);
 
 /*
  * Weight gradient on the tcgen05 tensor cores (3xTF32): out[Ka, Nb] = A[M, Ka]^T . B[M, Nb], the reduction

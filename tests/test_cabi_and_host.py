@@ -55,7 +55,7 @@ def test_argument_validation_without_gpu(built_lib):
     assert lib.cb_graph_create_sliced(None, 0, 10, 4, 2, 0, None, ctypes.byref(out)) == -1
     assert lib.cb_graph_create(None, 0, 2 ** 31, 0, None, ctypes.byref(out)) == -4
     assert lib.cb_agg_forward(None, None, 4, 4, None, None, 0.0, 0, None, None, None, 4, None, 0, None) == -1
-    assert lib.cb_agg_gather(None, 0, None, 4, 4, None, None, 4, None, 0, None) == -1
+    assert lib.cb_agg_gather(None, 0, None, 4, 4, None, None, None, 4, None, 0, None) == -1
     assert lib.cb_row_scale(None, None, 3, 0, None, None) == -1
     assert lib.cb_row_scale(None, None, 0, 4, None, None) == 0          # empty input: nothing to do
     assert lib.cb_graph_destroy(None) == 0

@@ -186,3 +186,32 @@ def test_gemm_rows_grad_relu_bias_mode():
     assert torch.equal(got, want)
     ref = want.double().sum(0)
     assert float((col.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_gemm_rows_grad_row_live_flags_and_sparse_gather():
+    """row_live marks exactly the non-zero output rows, and a gather that skips the unmarked rows is bit-identical."""
+    from gnn_tail_generalization_b200 import _cabi as C
+    ops = _ops()
+    M, K, N = 3000, 64, 256
+    gph = _small_graph(M, 3)
+    g = torch.Generator(device='cuda').manual_seed(21)
+    dY = torch.randn(M, K, device='cuda', generator=g)
+    dY[M // 5:] = 0                                   # loss over the first rows only
+    dY[7] = 0
+    W = torch.randn(N, K, device='cuda', generator=g) / 8
+    mask = (torch.rand(M, N, device='cuda', generator=g) > 0.3).to(torch.uint8)
+    mask[11] = 0                                      # a live input row whose output is gated to zero
+    wt = ops.split_weight(W, transpose=False)
+    live = torch.zeros(M, dtype=torch.uint8, device='cuda')
+    G, _, _ = ops.gemm_rows_grad_raw(dY, wt, gate_u8=mask, mixed=True, alpha=0.1, post_scale=gph.din_inv_sqrt,
+                                     row_live=live)
+    want = (G != 0).any(1)
+    assert torch.equal(live.bool(), want)
+    assert 0 < int(want.sum()) < M // 5
+    dense = ops.agg_gather_raw(gph, C.CB_BY_SRC, G)
+    sparse = ops.agg_gather_raw(gph, C.CB_BY_SRC, G, live=live)
+    assert torch.equal(dense, sparse)
+    # flags that wrongly kill a live row change the result (the kernel really skips)
+    wrong = live.clone()
+    wrong[int(want.nonzero()[0])] = 0
+    assert not torch.equal(ops.agg_gather_raw(gph, C.CB_BY_SRC, G, live=wrong), dense)

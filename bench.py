@@ -224,7 +224,12 @@ def run_ours(a):
     if a.panels <= 0:
         a.panels = 4 if world >= 8 else 1
     if world > 1 and a.exchange == 'push':
-        graph.enable_push(d, a.panels, a.push_ctas)
+        try:
+            graph.enable_push(d, a.panels, a.push_ctas)
+        except RuntimeError as e:   # raised on every rank together (PeerExchange); reported in config.parallelism
+            if rank == 0:
+                print(f'bench: {e}; using the NCCL all-gather exchange', file=sys.stderr, flush=True)
+            a.exchange = 'nccl (peer buffers unavailable)'
     torch.cuda.empty_cache()
     lo, hi = graph.row_begin, graph.row_end
     rows = hi - lo

@@ -147,24 +147,43 @@ class PeerExchange:
         self.panels, self.push_ctas = max(1, int(panels)), int(push_ctas)
         nbytes = self.n_pad * self.max_d * 4
         self._mine, self._theirs, handles = [], [], []
+        # Every rank goes through both collectives below whatever happened locally, so that a rank whose
+        # allocation or mapping failed (no peer access, IPC disabled in the container ...) takes the whole
+        # group to one clean error instead of leaving the others waiting in a collective.
+        failure = None
         with torch.cuda.device(self.dev):
-            for _ in range(2):
-                p = ctypes.c_void_p()
-                h = ctypes.create_string_buffer(C.CB_PEER_HANDLE_BYTES)
-                C.call('cb_peer_alloc', nbytes, ctypes.byref(p), h)
-                self._mine.append(p.value)
-                handles.append(bytes(h.raw))
+            try:
+                for _ in range(2):
+                    p = ctypes.c_void_p()
+                    h = ctypes.create_string_buffer(C.CB_PEER_HANDLE_BYTES)
+                    C.call('cb_peer_alloc', nbytes, ctypes.byref(p), h)
+                    self._mine.append(p.value)
+                    handles.append(bytes(h.raw))
+            except Exception as e:      # noqa: BLE001 - reported to every rank below
+                failure, handles = e, None
             everyone = [None] * self.world
             dist.all_gather_object(everyone, handles, group=group)
             self.peers = [r for r in range(self.world) if r != self.rank]
-            for b in range(2):
-                ptrs = []
-                for r in self.peers:
-                    q = ctypes.c_void_p()
-                    C.call('cb_peer_open', ctypes.create_string_buffer(everyone[r][b], C.CB_PEER_HANDLE_BYTES),
-                           ctypes.byref(q))
-                    ptrs.append(q.value)
-                self._theirs.append(ptrs)
+            if failure is None and all(h is not None for h in everyone):
+                try:
+                    for b in range(2):
+                        ptrs = []
+                        self._theirs.append(ptrs)
+                        for r in self.peers:
+                            q = ctypes.c_void_p()
+                            C.call('cb_peer_open', ctypes.create_string_buffer(everyone[r][b], C.CB_PEER_HANDLE_BYTES),
+                                   ctypes.byref(q))
+                            ptrs.append(q.value)
+                except Exception as e:  # noqa: BLE001
+                    failure = e
+            elif failure is None:
+                failure = RuntimeError('a peer could not allocate its exchange buffers')
+            ok = torch.tensor([0 if failure is not None else 1], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok) == 0:
+                self.close()
+                raise RuntimeError(f'peer-mapped exchange buffers are not available on this node '
+                                   f'(rank {self.rank}: {failure or "a peer failed"})')
             self.side_stream = torch.cuda.Stream(device=self.dev)
         # need masks: forward gathers sources (columns of the by-destination CSR), backward gathers
         # destinations (columns of the by-source CSR)

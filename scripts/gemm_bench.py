@@ -1,5 +1,5 @@
-import torch, time, sys
-sys.path.insert(0, '/root/repo')
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gnn_tail_generalization_b200 import ops
 torch.backends.cuda.matmul.allow_tf32 = False
 def t(fn, n=5):

@@ -42,6 +42,8 @@ SYMBOLS = {
     'cb_graph_workspace_bytes': (_i64, [_vp, _int, _i64]),
     'cb_agg_forward': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_agg_gather': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    'cb_agg_forward_bf16': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    'cb_agg_gather_bf16': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_prep_workspace_bytes': (_i64, [_i64, _i64]),
     'cb_agg_backward_prep': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _dbl, _vp, _vp, _vp, _int, _vp,
                                     _i64, _vp]),

@@ -15,6 +15,8 @@
 //
 // The neighbour ids of a task are read LPR at a time with one coalesced load and handed round with
 // warp shuffles; UNROLL independent row loads are in flight per group before the first add.
+#include <cuda_bf16.h>
+
 #include "cb_internal.cuh"
 
 namespace cb {
@@ -27,21 +29,21 @@ struct AggArgs {
     const int64_t* chunk_beg;
     int64_t n_chunks;
     int hub_chunk;
-    const float* X;      // [n_src, x_ld]
+    const void* X;       // [n_src, x_ld], fp32 or bf16 (the kernel's storage type S)
     int64_t d;           // columns aggregated (logical width)
-    int64_t x_ld;        // row pitch of X, floats
-    int64_t o_ld;        // row pitch of x0 / out / out2 / mask, floats (bytes for mask)
+    int64_t x_ld;        // row pitch of X, elements
+    int64_t o_ld;        // row pitch of x0 / out / out2 / mask, elements
     int64_t col0;        // first column handled by this launch
     float* partial;      // [n_chunks, d]
     // epilogue
     const float* row_scale;   // [rows] or null
     const float* bias;        // [d] or null
-    const float* x0;          // [rows, d] or null
+    const void* x0;           // [rows, d] or null (storage type S)
     float alpha, one_minus_alpha;
     int act;
-    float* out;               // [rows, d] or null
+    void* out;                // [rows, d] or null (storage type S)
     const float* out2_scale;  // [rows]
-    float* out2;              // [rows, d] or null
+    void* out2;               // [rows, d] or null (storage type S)
     uint8_t* mask;            // [rows, d] or null
     const uint8_t* live;      // [n_src] or null: rows of X with live[s] == 0 are all-zero and are not gathered
 };
@@ -77,17 +79,110 @@ struct Vec<1> {
     static __device__ __forceinline__ void store_mask(uint8_t* p, const float (&z)[1]) { *p = z[0] > 0.f; }
 };
 
+template <>
+struct Vec<8> {   // eight fp32 values (bias, hub partials) beside a bf16x8 feature access
+    static __device__ __forceinline__ void load(float (&v)[8], const float* p) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void load_plain(float (&v)[8], const float* p) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    static __device__ __forceinline__ void store_mask(uint8_t* p, const float (&z)[8]) {
+        uint2 m;
+        m.x = (z[0] > 0.f ? 1u : 0u) | (z[1] > 0.f ? 0x100u : 0u) | (z[2] > 0.f ? 0x10000u : 0u) | (z[3] > 0.f ? 0x1000000u : 0u);
+        m.y = (z[4] > 0.f ? 1u : 0u) | (z[5] > 0.f ? 0x100u : 0u) | (z[6] > 0.f ? 0x10000u : 0u) | (z[7] > 0.f ? 0x1000000u : 0u);
+        *reinterpret_cast<uint2*>(p) = m;
+    }
+};
+
+// Feature-matrix access in the storage type S: fp32 (VEC = 4 or 1 per access) or bf16 (VEC = 8 or 1).  bf16 rows
+// are widened to fp32 on load -- every sum and the whole epilogue stay fp32 -- and rounded to nearest-even on store.
+template <typename S, int VEC>
+struct Elem;
+template <int VEC>
+struct Elem<float, VEC> {
+    struct Raw { float f[VEC]; };
+    static __device__ __forceinline__ void load_raw(Raw& r, const void* base, int64_t off) {
+        Vec<VEC>::load(r.f, reinterpret_cast<const float*>(base) + off);
+    }
+    static __device__ __forceinline__ void add(float (&acc)[VEC], const Raw& r) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] += r.f[i];
+    }
+    static __device__ __forceinline__ void load(float (&v)[VEC], const void* base, int64_t off) {
+        Vec<VEC>::load(v, reinterpret_cast<const float*>(base) + off);
+    }
+    static __device__ __forceinline__ void store(void* base, int64_t off, const float (&v)[VEC]) {
+        Vec<VEC>::store(reinterpret_cast<float*>(base) + off, v);
+    }
+};
+template <>
+struct Elem<__nv_bfloat16, 8> {
+    // gathered rows stay packed (4 registers per 16-byte load) until they are added, so that eight loads per lane
+    // can be in flight
+    struct Raw { uint4 u; };
+    static __device__ __forceinline__ void load_raw(Raw& r, const void* base, int64_t off) {
+        r.u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+    }
+    static __device__ __forceinline__ void widen(float (&v)[8], const uint4& t) {
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void add(float (&acc)[8], const Raw& r) {
+        float v[8];
+        widen(v, r.u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+    static __device__ __forceinline__ void load(float (&v)[8], const void* base, int64_t off) {
+        widen(v, __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off)));
+    }
+    static __device__ __forceinline__ void store(void* base, int64_t off, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+template <>
+struct Elem<__nv_bfloat16, 1> {
+    struct Raw { float f; };
+    static __device__ __forceinline__ void load_raw(Raw& r, const void* base, int64_t off) {
+        r.f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]);
+    }
+    static __device__ __forceinline__ void add(float (&acc)[1], const Raw& r) { acc[0] += r.f; }
+    static __device__ __forceinline__ void load(float (&v)[1], const void* base, int64_t off) {
+        v[0] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]);
+    }
+    static __device__ __forceinline__ void store(void* base, int64_t off, const float (&v)[1]) {
+        reinterpret_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(v[0]);
+    }
+};
+
 // z = rs*acc + b ; r = act(z) ; out = (1-a) r + a x0 ; out2 = s2 * out ; mask = z > 0
 // Every product and sum is rounded separately (no FMA contraction), like the reference's chain of
 // elementwise ops (GCN.py:250,253; res_tricks.py:14,23).
-template <int VEC>
+template <typename S, int VEC>
 __device__ __forceinline__ void epilogue_store(const AggArgs& a, int64_t row, int64_t c, float (&acc)[VEC]) {
     const int64_t off = row * a.o_ld + c;
     float z[VEC], o[VEC];
     const float rs = a.row_scale ? __ldg(a.row_scale + row) : 1.f;
     float b[VEC], x0[VEC];
     if (a.bias) Vec<VEC>::load(b, a.bias + c);
-    if (a.x0) Vec<VEC>::load(x0, a.x0 + off);
+    if (a.x0) Elem<S, VEC>::load(x0, a.x0, off);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         float t = a.row_scale ? __fmul_rn(acc[i], rs) : acc[i];
@@ -97,20 +192,20 @@ __device__ __forceinline__ void epilogue_store(const AggArgs& a, int64_t row, in
         if (a.x0) r = __fadd_rn(__fmul_rn(a.one_minus_alpha, r), __fmul_rn(a.alpha, x0[i]));
         o[i] = r;
     }
-    if (a.out) Vec<VEC>::store(a.out + off, o);
+    if (a.out) Elem<S, VEC>::store(a.out, off, o);
     if (a.out2) {
         const float s2 = __ldg(a.out2_scale + row);
         float o2[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) o2[i] = __fmul_rn(o[i], s2);
-        Vec<VEC>::store(a.out2 + off, o2);
+        Elem<S, VEC>::store(a.out2, off, o2);
     }
     if (a.mask) Vec<VEC>::store_mask(a.mask + off, z);
 }
 
 // LIVE: X is row-sparse (e.g. the gradient arriving from a loss over the train rows only); a.live says which
 // source rows can be non-zero.  Skipping an all-zero row leaves every fp32 sum unchanged (x + 0 = x).
-template <int VEC, int LPR, int NCH, int UNROLL, bool LIVE>
+template <typename S, int VEC, int LPR, int NCH, int UNROLL, bool LIVE>
 __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
     constexpr int GROUPS = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -152,17 +247,17 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
         int my = sub < n ? __ldg(a.col + base + sub) : 0;
         if (LIVE && sub < n && __ldg(a.live + my) == 0) my |= (int)0x80000000;   // N < 2^31: the sign bit is free
         for (int k = 0; k < n; k += UNROLL) {
-            float v[UNROLL][NCH][VEC];
+            typename Elem<S, VEC>::Raw v[UNROLL][NCH];
             bool on[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int s = __shfl_sync(gmask, my, (k + u) & (LPR - 1), LPR);
                 on[u] = (k + u < n) && (!LIVE || s >= 0);
                 if (on[u]) {
-                    const float* xr = a.X + (int64_t)s * a.x_ld;
+                    const int64_t xr = (int64_t)s * a.x_ld;
 #pragma unroll
                     for (int ch = 0; ch < NCH; ++ch)
-                        if (cval[ch]) Vec<VEC>::load(v[u][ch], xr + cofs[ch]);
+                        if (cval[ch]) Elem<S, VEC>::load_raw(v[u][ch], a.X, xr + cofs[ch]);
                 }
             }
 #pragma unroll
@@ -170,10 +265,7 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
                 if (on[u]) {
 #pragma unroll
                     for (int ch = 0; ch < NCH; ++ch)
-                        if (cval[ch]) {
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) acc[ch][i] += v[u][ch][i];
-                        }
+                        if (cval[ch]) Elem<S, VEC>::add(acc[ch], v[u][ch]);
                 }
             }
         }
@@ -187,12 +279,12 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
     } else {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch)
-            if (cval[ch]) epilogue_store<VEC>(a, row, cofs[ch], acc[ch]);
+            if (cval[ch]) epilogue_store<S, VEC>(a, row, cofs[ch], acc[ch]);
     }
 }
 
 // Adds the chunk partials of every hub row in chunk order and applies the epilogue.
-template <int VEC, int LPR, int NCH>
+template <typename S, int VEC, int LPR, int NCH>
 __global__ void __launch_bounds__(256) k_combine(const AggArgs a) {
     constexpr int GROUPS = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -218,51 +310,51 @@ __global__ void __launch_bounds__(256) k_combine(const AggArgs a) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] += v[i];
         }
-        epilogue_store<VEC>(a, row, co, acc);
+        epilogue_store<S, VEC>(a, row, co, acc);
     }
 }
 
-template <int VEC, int LPR, int NCH>
+template <typename S, int VEC, int LPR, int NCH>
 static int launch_cfg(const AggArgs& a, cudaStream_t st) {
     constexpr int GROUPS = 32 / LPR;
     constexpr int WARPS = 8;
-    constexpr int UNROLL = (VEC * NCH >= 8) ? 4 : 8;
+    constexpr int UNROLL = NCH >= 2 ? 4 : 8;   // >= 128 bytes of gathered rows in flight per lane
     constexpr int U = UNROLL < LPR ? UNROLL : LPR;
     const int64_t tasks = a.n_rows + a.n_chunks;
     if (tasks > 0) {
         const int64_t blocks = ceil_div(tasks, (int64_t)WARPS * GROUPS);
         CB_REQUIRE(blocks < (int64_t)INT32_MAX, CB_E_UNSUPPORTED, "aggregation grid too large");
         if (a.live)
-            k_agg<VEC, LPR, NCH, U, true><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+            k_agg<S, VEC, LPR, NCH, U, true><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
         else
-            k_agg<VEC, LPR, NCH, U, false><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+            k_agg<S, VEC, LPR, NCH, U, false><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
         CB_LAUNCH_CHECK();
     }
     if (a.n_chunks > 0) {
         const int64_t blocks = ceil_div(a.n_chunks, (int64_t)WARPS * GROUPS);
-        k_combine<VEC, LPR, NCH><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+        k_combine<S, VEC, LPR, NCH><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
         CB_LAUNCH_CHECK();
     }
     return CB_OK;
 }
 
-template <int VEC>
+template <typename S, int VEC>
 static int launch_vec(AggArgs a, cudaStream_t st) {
     const int64_t units = ceil_div(a.d, VEC);
-    if (units <= 1) return launch_cfg<VEC, 1, 1>(a, st);
-    if (units <= 2) return launch_cfg<VEC, 2, 1>(a, st);
-    if (units <= 4) return launch_cfg<VEC, 4, 1>(a, st);
-    if (units <= 8) return launch_cfg<VEC, 8, 1>(a, st);
-    if (units <= 16) return launch_cfg<VEC, 16, 1>(a, st);
-    if (units <= 32) return launch_cfg<VEC, 32, 1>(a, st);
-    if (units <= 64) return launch_cfg<VEC, 32, 2>(a, st);
+    if (units <= 1) return launch_cfg<S, VEC, 1, 1>(a, st);
+    if (units <= 2) return launch_cfg<S, VEC, 2, 1>(a, st);
+    if (units <= 4) return launch_cfg<S, VEC, 4, 1>(a, st);
+    if (units <= 8) return launch_cfg<S, VEC, 8, 1>(a, st);
+    if (units <= 16) return launch_cfg<S, VEC, 16, 1>(a, st);
+    if (units <= 32) return launch_cfg<S, VEC, 32, 1>(a, st);
+    if (units <= 64) return launch_cfg<S, VEC, 32, 2>(a, st);
     // wider rows: column blocks of 128 vector slots, the neighbour list is walked once per block
     for (int64_t u0 = 0; u0 < units; u0 += 128) {
         a.col0 = u0 * VEC;
         const int64_t left = units - u0;
-        int rc = left <= 32   ? launch_cfg<VEC, 32, 1>(a, st)
-                 : left <= 64 ? launch_cfg<VEC, 32, 2>(a, st)
-                              : launch_cfg<VEC, 32, 4>(a, st);
+        int rc = left <= 32   ? launch_cfg<S, VEC, 32, 1>(a, st)
+                 : left <= 64 ? launch_cfg<S, VEC, 32, 2>(a, st)
+                              : launch_cfg<S, VEC, 32, 4>(a, st);
         if (rc) return rc;
     }
     return CB_OK;
@@ -270,7 +362,7 @@ static int launch_vec(AggArgs a, cudaStream_t st) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int run_agg(const cb_graph* g, int side_id, AggArgs a, void* workspace, int64_t workspace_bytes,
+static int run_agg(const cb_graph* g, int side_id, int dtype, AggArgs a, void* workspace, int64_t workspace_bytes,
                    cudaStream_t st) {
     const Side& s = side_id == CB_BY_DST ? g->by_dst : g->by_src;
     a.rowptr = s.rowptr;
@@ -285,26 +377,21 @@ static int run_agg(const cb_graph* g, int side_id, AggArgs a, void* workspace, i
     const int64_t need = s.n_chunks * a.d * (int64_t)sizeof(float);
     CB_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need), CB_E_WORKSPACE,
                "aggregation workspace missing or smaller than cb_graph_workspace_bytes()");
-    const bool vec4 = (a.d % 4 == 0) && (a.x_ld % 4 == 0) && (a.o_ld % 4 == 0) && aligned16(a.X) && aligned16(a.out) && aligned16(a.out2) &&
-                      aligned16(a.x0) && aligned16(a.bias) && aligned16(a.partial) &&
+    const bool al = aligned16(a.X) && aligned16(a.out) && aligned16(a.out2) && aligned16(a.x0) && aligned16(a.bias) &&
+                    aligned16(a.partial);
+    if (dtype == CB_BF16) {
+        const bool vec8 = (a.d % 8 == 0) && (a.x_ld % 8 == 0) && (a.o_ld % 8 == 0) && al &&
+                          (reinterpret_cast<uintptr_t>(a.mask) & 7u) == 0;
+        return vec8 ? launch_vec<__nv_bfloat16, 8>(a, st) : launch_vec<__nv_bfloat16, 1>(a, st);
+    }
+    const bool vec4 = (a.d % 4 == 0) && (a.x_ld % 4 == 0) && (a.o_ld % 4 == 0) && al &&
                       (reinterpret_cast<uintptr_t>(a.mask) & 3u) == 0;
-    return vec4 ? launch_vec<4>(a, st) : launch_vec<1>(a, st);
+    return vec4 ? launch_vec<float, 4>(a, st) : launch_vec<float, 1>(a, st);
 }
 
-}  // namespace cb
-
-extern "C" {
-
-int64_t cb_graph_workspace_bytes(const cb_graph_t* g, int side, int64_t d) {
-    if (!g || d <= 0) return 0;
-    const cb::Side& s = side == CB_BY_DST ? g->by_dst : g->by_src;
-    return s.n_chunks * d * (int64_t)sizeof(float);
-}
-
-int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t ld_h, int64_t d, const float* bias, const float* x0,
-                   double alpha, int act, float* out, float* out_scaled, uint8_t* mask, int64_t ld_out,
-                   void* workspace, int64_t workspace_bytes, void* stream) {
-    using namespace cb;
+static int agg_forward_impl(const cb_graph* g, int dtype, const void* H, int64_t ld_h, int64_t d, const float* bias,
+                            const void* x0, double alpha, int act, void* out, void* out_scaled, uint8_t* mask,
+                            int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream) {
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_forward: graph is NULL");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_forward: d must be positive");
     CB_REQUIRE(g->rows == 0 || H != nullptr, CB_E_INVALID, "cb_agg_forward: H is NULL");
@@ -327,13 +414,12 @@ int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t ld_h, int64_t d,
     a.out2_scale = g->dout_is;
     a.out2 = out_scaled;
     a.mask = mask;
-    return run_agg(g, CB_BY_DST, a, workspace, workspace_bytes, (cudaStream_t)stream);
+    return run_agg(g, CB_BY_DST, dtype, a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, int64_t d, const float* row_scale,
-                  const uint8_t* row_live, float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes,
-                  void* stream) {
-    using namespace cb;
+static int agg_gather_impl(const cb_graph* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
+                           const float* row_scale, const uint8_t* row_live, void* out, int64_t ld_out, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_gather: graph is NULL");
     CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_agg_gather: unknown side");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_gather: d must be positive");
@@ -349,7 +435,45 @@ int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, i
     a.act = CB_ACT_NONE;
     a.out = out;
     a.live = row_live;
-    return run_agg(g, side, a, workspace, workspace_bytes, (cudaStream_t)stream);
+    return run_agg(g, side, dtype, a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // namespace cb
+
+extern "C" {
+
+int64_t cb_graph_workspace_bytes(const cb_graph_t* g, int side, int64_t d) {
+    if (!g || d <= 0) return 0;
+    const cb::Side& s = side == CB_BY_DST ? g->by_dst : g->by_src;
+    return s.n_chunks * d * (int64_t)sizeof(float);
+}
+
+int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t ld_h, int64_t d, const float* bias, const float* x0,
+                   double alpha, int act, float* out, float* out_scaled, uint8_t* mask, int64_t ld_out,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
+    return cb::agg_forward_impl(g, CB_F32, H, ld_h, d, bias, x0, alpha, act, out, out_scaled, mask, ld_out, workspace,
+                                workspace_bytes, stream);
+}
+
+int cb_agg_forward_bf16(const cb_graph_t* g, const uint16_t* H, int64_t ld_h, int64_t d, const float* bias,
+                        const uint16_t* x0, double alpha, int act, uint16_t* out, uint16_t* out_scaled, uint8_t* mask,
+                        int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream) {
+    return cb::agg_forward_impl(g, CB_BF16, H, ld_h, d, bias, x0, alpha, act, out, out_scaled, mask, ld_out, workspace,
+                                workspace_bytes, stream);
+}
+
+int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, int64_t d, const float* row_scale,
+                  const uint8_t* row_live, float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes,
+                  void* stream) {
+    return cb::agg_gather_impl(g, side, CB_F32, X, ld_x, d, row_scale, row_live, out, ld_out, workspace,
+                               workspace_bytes, stream);
+}
+
+int cb_agg_gather_bf16(const cb_graph_t* g, int side, const uint16_t* X, int64_t ld_x, int64_t d,
+                       const float* row_scale, const uint8_t* row_live, uint16_t* out, int64_t ld_out, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+    return cb::agg_gather_impl(g, side, CB_BF16, X, ld_x, d, row_scale, row_live, out, ld_out, workspace,
+                               workspace_bytes, stream);
 }
 
 }  // extern "C"

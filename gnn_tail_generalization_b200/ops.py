@@ -42,12 +42,12 @@ class _Timed:
         return False
 
 
-def gather_alg_bytes(graph, side, d, n_out_mats=1, n_in_mats=1, mask=False, scales=1):
+def gather_alg_bytes(graph, side, d, n_out_mats=1, n_in_mats=1, mask=False, scales=1, elem=4):
     """Algorithmic bytes of one aggregation launch: every feature matrix once, the CSR once."""
     e = graph.num_edges if side == C.CB_BY_DST else graph.num_edges_by_src
-    b = graph.num_nodes * d * 4                       # gathered matrix, read once
-    b += (n_in_mats - 1) * graph.rows * d * 4         # x0
-    b += n_out_mats * graph.rows * d * 4              # outputs
+    b = graph.num_nodes * d * elem                    # gathered matrix, read once
+    b += (n_in_mats - 1) * graph.rows * d * elem      # x0
+    b += n_out_mats * graph.rows * d * elem           # outputs
     b += graph.rows * d if mask else 0
     b += e * 4 + (graph.rows + 1) * 8 + scales * graph.rows * 4 + d * 4
     return b
@@ -71,6 +71,15 @@ def _f32c(t):
 # raw (non-differentiable) kernel calls
 # ---------------------------------------------------------------------------------------------
 
+def _featc(t, dtype):
+    """Feature-matrix operand in the aggregation's storage type (fp32 or bf16), contiguous."""
+    if t is None:
+        return None
+    if t.dtype != dtype:
+        raise TypeError(f'expected {dtype}, got {t.dtype}')
+    return t.contiguous()
+
+
 def _pofs(t, elems):
     """Device address of element ``elems`` of a tensor (None stays NULL)."""
     return None if t is None else ctypes.c_void_p(t.data_ptr() + elems * t.element_size())
@@ -80,11 +89,16 @@ def agg_forward_raw(graph, H, bias=None, x0=None, alpha=0.0, relu=False, want_ou
                     want_mask=False, outs=None, panel=None):
     """One fused forward aggregation over the owned rows.  H holds every source row ([N_global, d]).
 
+    H fp32 -> cb_agg_forward; H bf16 -> cb_agg_forward_bf16 (x0 and the outputs are then bf16 too; the sums, the
+    bias and the epilogue stay fp32).
     panel=(c0, w): H is the [N_global, w] column panel c0..c0+w of a wider matrix; bias / x0 / the outputs are
     the full-width [.., D] tensors (``outs`` = (out, out_scaled, mask) preallocated) and only their columns
     c0..c0+w are read / written."""
     _need_cuda(H, bias, x0)
-    H, bias, x0 = _f32c(H), _f32c(bias), _f32c(x0)
+    if H.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f'H must be float32 or bfloat16, got {H.dtype}')
+    st = H.dtype
+    H, bias, x0 = H.contiguous(), _f32c(bias), _featc(x0, st)
     d = H.shape[1]
     if H.shape[0] != graph.num_nodes:
         raise ValueError(f'H has {H.shape[0]} rows, the graph has {graph.num_nodes} nodes')
@@ -95,25 +109,30 @@ def agg_forward_raw(graph, H, bias=None, x0=None, alpha=0.0, relu=False, want_ou
     else:
         if panel is not None:
             raise ValueError('a column panel needs preallocated full-width outputs')
-        out = torch.empty((graph.rows, d), dtype=torch.float32, device=H.device) if want_out else None
-        out_scaled = torch.empty((graph.rows, d), dtype=torch.float32, device=H.device) if want_scaled else None
+        out = torch.empty((graph.rows, d), dtype=st, device=H.device) if want_out else None
+        out_scaled = torch.empty((graph.rows, d), dtype=st, device=H.device) if want_scaled else None
         mask = torch.empty((graph.rows, d), dtype=torch.uint8, device=H.device) if want_mask else None
     ws, ws_bytes = graph.workspace(C.CB_BY_DST, d)
+    es = H.element_size()
     alg = gather_alg_bytes(graph, C.CB_BY_DST, d, int(out is not None) + int(out_scaled is not None),
-                           1 + int(x0 is not None), mask is not None, 1 + int(out_scaled is not None))
-    with torch.cuda.device(H.device), _Timed('agg_forward', alg, H.device):
-        C.call('cb_agg_forward', graph.handle, C.ptr(H), d, d, _pofs(bias, c0), _pofs(x0, c0), float(alpha),
+                           1 + int(x0 is not None), mask is not None, 1 + int(out_scaled is not None), es)
+    fn, name = ('cb_agg_forward', 'agg_forward') if st == torch.float32 else ('cb_agg_forward_bf16', 'agg_forward_bf16')
+    with torch.cuda.device(H.device), _Timed(name, alg, H.device):
+        C.call(fn, graph.handle, C.ptr(H), d, d, _pofs(bias, c0), _pofs(x0, c0), float(alpha),
                C.CB_ACT_RELU if relu else C.CB_ACT_NONE, _pofs(out, c0), _pofs(out_scaled, c0), _pofs(mask, c0), D,
                C.ptr(ws), ws_bytes, C.stream_ptr(H.device))
     return out, out_scaled, mask
 
 
 def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None, live=None):
-    """out[r] = row_scale[r] * sum_{j in row r} X[col[j]]  over one CSR side of the graph.
+    """out[r] = row_scale[r] * sum_{j in row r} X[col[j]]  over one CSR side of the graph (X fp32 or bf16).
     panel=(c0, w): X is a [N_global, w] column panel; ``out`` is the preallocated full-width result.
     live: uint8 [N_global], 0 where the row of X is known to be all-zero (not gathered)."""
     _need_cuda(X, row_scale)
-    X, row_scale = _f32c(X), _f32c(row_scale)
+    if X.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f'X must be float32 or bfloat16, got {X.dtype}')
+    st = X.dtype
+    X, row_scale = X.contiguous(), _f32c(row_scale)
     d = X.shape[1]
     if X.shape[0] != graph.num_nodes:
         raise ValueError(f'X has {X.shape[0]} rows, the graph has {graph.num_nodes} nodes')
@@ -121,16 +140,19 @@ def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None, live=No
     if out is None:
         if panel is not None:
             raise ValueError('a column panel needs a preallocated full-width output')
-        out = torch.empty((graph.rows, d), dtype=torch.float32, device=X.device)
+        out = torch.empty((graph.rows, d), dtype=st, device=X.device)
+    elif out.dtype != st:
+        raise TypeError('out must have the storage type of X')
     D = out.shape[1]
     ws, ws_bytes = graph.workspace(side, d)
-    alg = gather_alg_bytes(graph, side, d, 1, 1, False, int(row_scale is not None))
+    alg = gather_alg_bytes(graph, side, d, 1, 1, False, int(row_scale is not None), X.element_size())
     if live is not None and (live.dtype != torch.uint8 or live.numel() != graph.num_nodes):
         raise ValueError('live must be uint8 [num_nodes]')
-    name = ('agg_gather_dst' if side == C.CB_BY_DST else 'agg_gather_src') + ('_rowsparse' if live is not None else '')
+    name = ('agg_gather_dst' if side == C.CB_BY_DST else 'agg_gather_src') + ('_rowsparse' if live is not None else '') + \
+        ('' if st == torch.float32 else '_bf16')
     with torch.cuda.device(X.device), _Timed(name, alg, X.device):
-        C.call('cb_agg_gather', graph.handle, side, C.ptr(X), d, d, C.ptr(row_scale), C.ptr(live), _pofs(out, c0), D,
-               C.ptr(ws), ws_bytes, C.stream_ptr(X.device))
+        C.call('cb_agg_gather' if st == torch.float32 else 'cb_agg_gather_bf16', graph.handle, side, C.ptr(X), d, d,
+               C.ptr(row_scale), C.ptr(live), _pofs(out, c0), D, C.ptr(ws), ws_bytes, C.stream_ptr(X.device))
     return out
 
 

@@ -39,6 +39,9 @@ enum {
 /* activation selector for the fused epilogue (GCN.py:127-128 applies F.relu after the layer) */
 enum { CB_ACT_NONE = 0, CB_ACT_RELU = 1 };
 
+/* storage type of the feature matrices an aggregation reads / writes (sums and epilogue are always fp32) */
+enum { CB_F32 = 0, CB_BF16 = 1 };
+
 /* which side of the graph an aggregation walks */
 enum {
     CB_BY_DST = 0, /* rows = destination nodes, gathers over in-edges   (forward,  GCN.py:238) */
@@ -130,6 +133,15 @@ int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t ld_h, int64_t d,
                    uint8_t* mask, int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * bf16 storage (BASELINE.json configs[4]: 128-dim bf16 features): H, x0, out, out_scaled hold bf16 bit patterns; every
+ * row is widened to fp32 when gathered, the in-order fp32 sum and the whole epilogue are those of cb_agg_forward, and
+ * the results are rounded to nearest-even on store.  Half the gather traffic of the fp32 path.  Pitches in elements.
+ */
+int cb_agg_forward_bf16(const cb_graph_t* g, const uint16_t* H, int64_t ld_h, int64_t d, const float* bias,
+                        const uint16_t* x0, double alpha, int act, uint16_t* out, uint16_t* out_scaled, uint8_t* mask,
+                        int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Plain gather-reduce over one side of the graph, optional per-row scale of the result:
  *   out[r,:] = (row_scale ? row_scale[r] : 1) * sum_{j in row r} X[col[j],:]
  * side = CB_BY_SRC is the autograd transpose of GCN.py:238 (dH[u] = sum_{(u->v)} G[v]).
@@ -140,6 +152,10 @@ int cb_agg_forward(const cb_graph_t* g, const float* H, int64_t ld_h, int64_t d,
 int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, int64_t d, const float* row_scale,
                   const uint8_t* row_live, float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes,
                   void* stream);
+
+int cb_agg_gather_bf16(const cb_graph_t* g, int side, const uint16_t* X, int64_t ld_x, int64_t d,
+                       const float* row_scale, const uint8_t* row_live, uint16_t* out, int64_t ld_out, void* workspace,
+                       int64_t workspace_bytes, void* stream);
 
 /*
  * Backward prologue of cb_agg_forward: from the gradient(s) arriving at the layer output build the

@@ -462,3 +462,47 @@ def test_backward_fusion_matches_unfused(trick, se, layers):
         else:
             # the weight gradients see bias-free inputs only: bit-identical
             assert torch.equal(a_, b_), k
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 storage (BASELINE configs[4]): gathered rows widened to fp32, in-order fp32 sums, fp32 epilogue,
+# round-to-nearest-even on store -- bit-exact against the same arithmetic on the CPU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('d', [1, 6, 8, 24, 64, 128, 136, 256, 520])
+def test_aggregate_bf16_bit_exact(d):
+    C, G, ops = _pkg()
+    n, e, hub = 3000, 40000, 48
+    ei = _multigraph(n, e, 300 + d)
+    xb = torch.randn(n, d, generator=torch.Generator().manual_seed(d)).bfloat16()
+    h = G.GraphHandle(ei.to(DEV), n, hub_chunk=hub)
+    assert h.num_hub_chunks[0] > 0
+    for side, key, val in ((C.CB_BY_DST, ei[1], ei[0]), (C.CB_BY_SRC, ei[0], ei[1])):
+        rp, cl, _ = O.build_csr(key.numpy(), val.numpy(), n)
+        want = torch.from_numpy(O.aggregate_sum_csr_ordered(xb.float().numpy(), rp, cl, hub_chunk=hub)).bfloat16()
+        got = ops.agg_gather_raw(h, side, xb.to(DEV))
+        assert got.dtype == torch.bfloat16
+        assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
+
+
+@pytest.mark.parametrize('d', [12, 128, 256])
+@pytest.mark.parametrize('relu,mix', [(True, True), (False, False)])
+def test_fused_forward_bf16_matches_fp32_chain(d, relu, mix):
+    C, G, ops = _pkg()
+    n, alpha = 2500, 0.1
+    ei = torch.cat([_multigraph(n, 20000, 9), torch.arange(n).repeat(2, 1)], 1)       # every row has an in-edge
+    gen = torch.Generator().manual_seed(d)
+    hb = torch.randn(n, d, generator=gen).bfloat16()
+    x0b = torch.randn(n, d, generator=gen).bfloat16() if mix else None
+    bias = torch.randn(d, generator=gen)
+    h = G.GraphHandle(ei.to(DEV), n)
+    out, out_s, mask = ops.agg_forward_raw(h, hb.to(DEV), bias.to(DEV), x0b.to(DEV) if mix else None, alpha, relu,
+                                           want_out=True, want_scaled=True, want_mask=True)
+    rp, cl, _ = O.build_csr(ei[1].numpy(), ei[0].numpy(), n)
+    acc = torch.from_numpy(O.aggregate_sum_csr_ordered(hb.float().numpy(), rp, cl, hub_chunk=h.hub_chunk))
+    z = acc * h.din_inv_sqrt.cpu()[:, None] + bias                                    # separately rounded fp32 ops
+    r = z.clamp_min(0) if relu else z
+    if mix:
+        r = (torch.tensor(1.0 - alpha, dtype=torch.float32) * r) + (torch.tensor(alpha, dtype=torch.float32) * x0b.float())
+    assert torch.equal(out.cpu().view(torch.int16), r.bfloat16().view(torch.int16))
+    assert torch.equal(out_s.cpu().view(torch.int16), (r * h.dout_inv_sqrt.cpu()[:, None]).bfloat16().view(torch.int16))
+    assert torch.equal(mask.cpu().bool(), z > 0)

@@ -27,7 +27,7 @@ class PeerPush(ctypes.Structure):
     """cb_peer_push_t: where the rows of a kernel output go besides its local `out`."""
     _fields_ = [('n_peers', ctypes.c_int32), ('max_ctas', ctypes.c_int32),
                 ('peer', ctypes.c_void_p * CB_MAX_PEERS), ('need', ctypes.c_void_p),
-                ('row0', ctypes.c_int64), ('ld', ctypes.c_int64)]
+                ('row0', ctypes.c_int64), ('ld', ctypes.c_int64), ('row_live', ctypes.c_void_p)]
 
 
 # every symbol include/coldbrew_b200.h declares: name -> (restype, argtypes)

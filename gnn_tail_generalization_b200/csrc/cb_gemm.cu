@@ -196,7 +196,10 @@ __device__ __forceinline__ void push_to_peers(const cb_peer_push_t& ps, int64_t 
                                               const float4 (&v)[8]) {
     uint32_t nd[8];
 #pragma unroll
-    for (int itr = 0; itr < 8; ++itr) nd[itr] = itr < nval ? (uint32_t)__ldg(ps.need + rbase + itr * 4) : 0u;
+    for (int itr = 0; itr < 8; ++itr) {
+        nd[itr] = itr < nval ? (uint32_t)__ldg(ps.need + rbase + itr * 4) : 0u;
+        if (ps.row_live && itr < nval && __ldg(ps.row_live + rbase + itr * 4) == 0) nd[itr] = 0u;
+    }
     for (int j = 0; j < ps.n_peers; ++j) {
         float* p = ps.peer[j] + (ps.row0 + rbase) * ps.ld + col;
 #pragma unroll

@@ -274,11 +274,12 @@ def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_s
 
 def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=None, mixed=False, alpha=0.0,
                        d_x0=None, accumulate_x0=False, want_x0=False, post_scale=None, want_col_sum=False,
-                       push=None, row_live=None):
+                       push=None, row_live=None, push_live=None):
     """cb_gemm_rows_grad: the adjoint GEMM with the backward prologue of the layer below in its epilogue.
     Returns (out, col_sum or None, d_x0 or None); with ``push`` the output goes to the exchange slot
     (see gemm_rows_raw) and its local view is returned.  row_live: zeroed uint8 [M] that receives 1 for
-    every output row holding a non-zero element."""
+    every output row holding a non-zero element.  push_live: uint8 [M], 0 for rows known to come out all-zero
+    (their A row is zero): those are not pushed to the peers."""
     _need_cuda(A, row_scale, add, gate_u8, gate_f32, d_x0, post_scale)
     A, row_scale, add, gate_f32, post_scale = _f32c(A), _f32c(row_scale), _f32c(add), _f32c(gate_f32), _f32c(post_scale)
     M, K = A.shape
@@ -300,6 +301,8 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
     panels = [(0, N, None, out)] if push is None else \
         [(p * push.panel_width, push.panel_width, push.descs[p], push.panel_local[p]) for p in range(push.n_panels)]
     for p, (c0, w, desc, dst) in enumerate(panels):
+        if desc is not None:
+            desc.row_live = push_live.data_ptr() if push_live is not None else None
         alg = 4 * (M * K + 2 * w * K + M * w * (1 + extra)) + (M * w if gate_u8 is not None else 0) + \
             (push.pushed_rows * w * 4 if push is not None else 0)
         with torch.cuda.device(A.device), _Timed('gemm_rows_grad_push' if push is not None else 'gemm_rows_grad', alg,
@@ -460,15 +463,21 @@ class BwdPlan:
         if add is not None and sink is not None and sink.buf is not None:
             return None     # the kernel keeps one [M, N] epilogue input: the caller runs the two-kernel path
         slot = g.push_slot(C.CB_BY_SRC, wb.n)    # G is what the transposed aggregation gathers
-        live = torch.zeros(dtot_in.shape[0], dtype=torch.uint8, device=dtot_in.device) if self.row_sparse_hint else None
+        live = push_live = None
+        if self.row_sparse_hint and slot is not None and add is None:
+            # multi-GPU: a zero row of the incoming gradient gives a zero row of G -- known BEFORE the GEMM, so
+            # such rows are neither pushed to the peers nor gathered by anyone
+            push_live = (dtot_in != 0).any(dim=1).to(torch.uint8)
+        elif self.row_sparse_hint:
+            live = torch.zeros(dtot_in.shape[0], dtype=torch.uint8, device=dtot_in.device)
         out, col, d_x0 = gemm_rows_grad_raw(
             dtot_in, wb, row_scale=rs, add=add, gate_u8=self.gate_u8, gate_f32=self.gate_f32 if self.relu else None,
             mixed=self.mixed, alpha=self.alpha, d_x0=sink.buf if sink is not None else None,
             accumulate_x0=sink is not None and sink.buf is not None, want_x0=self.want_x0,
-            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot, row_live=live)
+            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot, row_live=live, push_live=push_live)
         if sink is not None:
             sink.buf, d_x0 = d_x0, None
-        self.result = {'d_bias': col, 'd_x0': d_x0, 'G': out, 'live': live}
+        self.result = {'d_bias': col, 'd_x0': d_x0, 'G': out, 'live': live if push_live is None else push_live}
         if out.dim() == 3:
             # a panelled slot cannot be viewed as [M, N]: G travels in the plan, autograd gets a placeholder
             return out.new_zeros(()).expand(dtot_in.shape[0], wb.n)

@@ -206,6 +206,8 @@ typedef struct {
     const uint8_t* need;         /* [M] device: bit j set = remote j gathers local row m */
     int64_t row0;                /* global index of local row 0 */
     int64_t ld;                  /* row pitch of the remote buffers, floats */
+    const uint8_t* row_live;     /* [M] device or NULL: rows with 0 are known to be all-zero and are not pushed
+                                    (the receivers skip them with the same flags, cb_agg_gather row_live) */
 } cb_peer_push_t;
 int cb_peer_alloc(int64_t bytes, void** ptr, void* handle_out /* CB_PEER_HANDLE_BYTES */);
 int cb_peer_open(const void* handle, void** ptr);

@@ -506,3 +506,43 @@ def test_fused_forward_bf16_matches_fp32_chain(d, relu, mix):
     assert torch.equal(out.cpu().view(torch.int16), r.bfloat16().view(torch.int16))
     assert torch.equal(out_s.cpu().view(torch.int16), (r * h.dout_inv_sqrt.cpu()[:, None]).bfloat16().view(torch.int16))
     assert torch.equal(mask.cpu().bool(), z > 0)
+
+
+def test_graphed_train_step_matches_eager():
+    """A whole training step captured in a CUDA graph (graphs.GraphedTrainStep) replays to exactly the eager
+    result: the kernels never synchronise or allocate behind the caller's back."""
+    from gnn_tail_generalization_b200.graphs import GraphedTrainStep
+    n, F_in, H, Cn = 2708, 120, 64, 7
+    ei = O.powerlaw_graph(n, 5278, seed=0).to(DEV)
+    kw = dict(type_trick='Initial', whetherHasSE='111', num_layers=2, dim_hidden=H, num_feats=F_in, num_classes=Cn,
+              N_nodes=n, dataset='Cora', res_alpha=0.1)
+    x = torch.randn(n, F_in, generator=torch.Generator().manual_seed(1)).to(DEV)
+    y = torch.randint(0, Cn, (n,), generator=torch.Generator().manual_seed(2)).to(DEV)
+    mask = torch.arange(n // 5).to(DEV)        # index mask: a boolean one makes emb[mask] synchronise (nonzero)
+
+    def loss_fn(res, yy, model):
+        return F.nll_loss(F.log_softmax(res.emb4classi, 1), yy[mask]) + 0.5 * model.se_reg_all
+
+    def make():
+        torch.manual_seed(11)
+        a = O.make_args(**kw)
+        a.device = DEV
+        m = _teacher(a).to(DEV).train()
+        m.model.model.dropout = m.model.model.embedding_dropout = m.model.model.args.dropout = 0.0
+        return m, torch.optim.Adam(m.parameters(), lr=1e-2, capturable=True)
+
+    eager, opt_e = make()
+    graphed, opt_g = make()
+    warm, steps = 2, 5
+    step = GraphedTrainStep(graphed, opt_g, loss_fn, x, ei, mask, y, warmup=warm)     # runs the warm-up steps; the capture
+    losses_g = [float(step()) for _ in range(steps)]                                   # itself only records
+    losses_e = []
+    for _ in range(warm + steps):
+        opt_e.zero_grad(set_to_none=True)
+        le = loss_fn(eager.get_3_embs(x, ei, mask), y, eager)
+        le.backward()
+        opt_e.step()
+        losses_e.append(float(le.detach()))
+    assert losses_g == losses_e[warm:]
+    for (k, p), (_, q) in zip(eager.named_parameters(), graphed.named_parameters()):
+        assert torch.equal(p, q), k

@@ -6,6 +6,11 @@
 //       GCN.py:205-213         out-degree row scale             (epilogue: rs[row] * acc, since (D X) W = D (X W))
 //       GCN.py:230-231         + self.le                        (epilogue: + add[row, col])
 //       GCN.py:104-106,138     Linear + bias (+ relu)           (epilogue: + bias[col], relu)
+//   cb_gemm_rows_grad  the adjoint dX = dH . W^T with the backward prologue of the layer below in its epilogue
+//       autograd of GCN.py:242-253, 127-128, res_tricks.py:23 (relu gate, residual split, degree scale, bias
+//       column sums) or of the input Linear's relu + bias (GCN.py:104-106); optional row-liveness flags
+//   cb_peer_push_t     multi-GPU: finished rows are also stored into the peers that gather them (the exchange of
+//                      the node-sliced path rides on the epilogue)
 //   cb_gemm_split_weight       hi/lo TF32 split of the small weight operand (done once per call, 256 KB)
 //
 // Precision.  Every fp32 value x is split as x = hi + lo with hi = tf32_rna(x), lo = tf32_rna(x - hi)
@@ -20,9 +25,12 @@
 //               (element-wise at identical offsets, so the TMA swizzle is preserved), fence.proxy.async
 //   warp 1      MMA issuer: 3 x (BK/8) tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per chunk into one of two
 //               TMEM accumulators; tcgen05.commit frees the stage / publishes the accumulator
-//   warps 6-9   epilogue: tcgen05.ld 32x32b.x32 -> registers -> per-warp padded smem transpose ->
-//               coalesced 16-byte global loads/stores with the fused row-scale / bias / add / relu
-// The weight operand is re-streamed from L2 per tile (it is 2 x N x K x 4 bytes = 512 KB at 256x256).
+//   warps 6-9   epilogue: tcgen05.ld 32x32b.x32 -> registers -> per-warp padded smem transpose -> an 8 x float4
+//               register tile per lane (8 rows x 4 columns of a 32-column slab) -> straight passes over that tile,
+//               each behind a uniform branch -> coalesced 16-byte stores.  One warp per SM sub-partition issues
+//               all of it: no per-element predicates, pointers stepped by constant strides.
+// The weight operand is re-streamed from L2 per tile (it is 2 x N x K x 4 bytes = 512 KB at 256x256); measured, that
+// is not the limiter (the kernel runs at ~78 % of the TF32 issue rate; see profiles/r01_summary_final.md).
 #include <cuda.h>
 #include <stdlib.h>
 

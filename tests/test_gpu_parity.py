@@ -546,3 +546,30 @@ def test_graphed_train_step_matches_eager():
     assert losses_g == losses_e[warm:]
     for (k, p), (_, q) in zip(eager.named_parameters(), graphed.named_parameters()):
         assert torch.equal(p, q), k
+
+
+@pytest.mark.parametrize('mode', ['DAD', 'DA', 'AD'])
+def test_label_propagation_matches_edge_valued_spmm(mode):
+    """the reference's propagation loop (outcome_correlation.py:128-158) with its normalised adjacency
+    as an edge-valued sparse matrix on the CPU (fp64) against the unit-weight gather between two row scalings."""
+    from gnn_tail_generalization_b200 import label_propagation as LP
+    _, G, _ = _pkg()
+    n, c, alpha, iters = 4000, 9, 0.8, 50
+    ei = O.powerlaw_graph(n, 12000, seed=3)
+    ei = ei[:, ei[0] != ei[1]]                                  # to_undirected graph without self loops
+    ei = ei[:, (ei[0] != 5) & (ei[1] != 5)]                      # node 5 isolated: the inf -> 0 rule
+    labels = torch.randint(0, c, (n, 1), generator=torch.Generator().manual_seed(1))
+    idx = torch.randperm(n, generator=torch.Generator().manual_seed(2))[: n // 3]
+    deg = torch.bincount(ei[0], minlength=n).double()
+    f = {'DAD': (-0.5, -0.5), 'DA': (-1.0, 0.0), 'AD': (0.0, -1.0)}[mode]
+    pw = lambda p: torch.where(deg > 0, deg.pow(p), torch.zeros_like(deg)) if p else torch.ones_like(deg)
+    vals = pw(f[0])[ei[0]] * pw(f[1])[ei[1]]
+    adj = torch.sparse_coo_tensor(ei, vals, (n, n)).coalesce()
+    y = torch.zeros(n, c, dtype=torch.float64)
+    y[idx] = F.one_hot(labels[idx].reshape(-1), c).double()
+    want = y.clone()
+    for _ in range(iters):
+        want = torch.clamp(alpha * torch.sparse.mm(adj, want) + (1 - alpha) * y, 0, 1)
+    g = G.GraphHandle(ei.to(DEV), n)
+    got = LP.label_propagation(g, labels.to(DEV), idx.to(DEV), alpha, iters, mode)
+    assert float((got.cpu().double() - want).abs().max()) <= 2e-5

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcoldbrew_b200.so')
 
 CB_OK = 0
+ABI_VERSION = 2
 CB_ACT_NONE, CB_ACT_RELU = 0, 1
 CB_BY_DST, CB_BY_SRC = 0, 1
 
@@ -91,8 +92,8 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.cb_abi_version() != 1:
-            raise ImportError(f'{LIB_PATH}: ABI version {handle.cb_abi_version()} != 1, rebuild')
+        if handle.cb_abi_version() != ABI_VERSION:
+            raise ImportError(f'{LIB_PATH}: ABI version {handle.cb_abi_version()} != {ABI_VERSION}, rebuild')
         _lib = handle
     return _lib
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 1
+#define CB_ABI_VERSION 2   /* 2: row pitches on cb_agg_*, cb_peer_push_t, cb_gemm_rows_grad, bf16 aggregation */
 
 enum {
     CB_OK = 0,

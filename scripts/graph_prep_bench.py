@@ -2,7 +2,6 @@
 Python loops (utils.py:300-334, 732-752) timed on a sample beside it and extrapolated per edge."""
 import os, sys, time
 from types import SimpleNamespace
-import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gnn_tail_generalization_b200 import graph_prep as P, synth

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in _declared_symbols():
         assert hasattr(lib, name), name
     lib.cb_abi_version.restype = ctypes.c_int
-    assert lib.cb_abi_version() == 1
+    assert lib.cb_abi_version() == 2
     lib.cb_last_error.restype = ctypes.c_char_p
     assert lib.cb_last_error() == b''
     lib.cb_launch_count.restype = ctypes.c_int64

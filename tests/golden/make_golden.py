@@ -113,9 +113,10 @@ def _args(**kw):
              dataset='Cora', dim_learnable_input=0, lamda=0.5, num_groups=None, skip_weight=None,
              graph_dropout=0.0, layerwise_dropout=False, dim_commonEmb=None)
     se = kw.pop('whetherHasSE', '000')
+    featureless = kw.pop('change_to_featureless', False)
     d.update(kw)
     a = SimpleNamespace(**d)
-    a.TeacherGNN = SimpleNamespace(whetherHasSE=[int(c) for c in se], change_to_featureless=False)
+    a.TeacherGNN = SimpleNamespace(whetherHasSE=[int(c) for c in se], change_to_featureless=featureless)
     if a.dim_commonEmb is None:
         a.dim_commonEmb = a.num_classes
     return a
@@ -158,6 +159,10 @@ CASES = {
     'learnable_input_L2':    (dict(type_trick='Initial', whetherHasSE='010', num_layers=2, dim_learnable_input=6), 30, 70, 14),
     'odd_dims_L2':           (dict(type_trick='NoRes', whetherHasSE='101', num_layers=2, dim_hidden=10, num_feats=9,
                                    num_classes=3), 33, 75, 15),
+    # added later (the earlier fixtures are not regenerated: `make_golden.py NAME...` writes only the named cases)
+    'initial_se000_L2':      (dict(type_trick='Initial', whetherHasSE='000', num_layers=2), 52, 140, 16),   # bench topology
+    'featureless_se111_L2':  (dict(type_trick='Initial', whetherHasSE='111', num_layers=2,
+                                   change_to_featureless=True), 38, 95, 17),             # GNN_normalizations.py:32-33
 }
 
 
@@ -206,6 +211,8 @@ def _json_args(a):
     import json
     d = {k: v for k, v in vars(a).items() if isinstance(v, (int, float, str, bool, type(None)))}
     d['whetherHasSE'] = ''.join(str(int(v)) for v in a.TeacherGNN.whetherHasSE)
+    if a.TeacherGNN.change_to_featureless:
+        d['change_to_featureless'] = True
     # TeacherGNN.__init__ rewrites these in place (GNN_normalizations.py:13-22); store the user-facing values
     return json.dumps(d)
 
@@ -238,6 +245,9 @@ if __name__ == '__main__':
     _install_shims()
     sys.path.insert(0, REF)
     torch.set_num_threads(1)
-    kat_toy()
+    only = sys.argv[1:]
+    if not only:
+        kat_toy()
     for name, (over, n, m, seed) in CASES.items():
-        run_case(name, dict(over), n, m, seed)
+        if not only or name in only:
+            run_case(name, dict(over), n, m, seed)

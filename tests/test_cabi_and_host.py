@@ -97,7 +97,8 @@ def test_state_dict_keys_and_shapes_match_reference(name):
 _SEEDS = {'nores_se000_L2': 1, 'nores_se111_L3': 2, 'nores_se100_L4': 3, 'initial_se111_L2': 4,
           'initial_se100_L3': 5, 'residual_se010_L3': 6, 'dense_concat_L2': 7, 'dense_maxpool_L2': 8,
           'dense_attention_L2': 9, 'jumping_concat_L3': 10, 'jumping_maxpool_L2': 11, 'exact_batchnorm_L2': 12,
-          'exact_pairnorm_L3': 13, 'learnable_input_L2': 14, 'odd_dims_L2': 15}
+          'exact_pairnorm_L3': 13, 'learnable_input_L2': 14, 'odd_dims_L2': 15, 'initial_se000_L2': 16,
+          'featureless_se111_L2': 17}
 
 
 @pytest.mark.parametrize('name', golden_cases())

@@ -8,8 +8,9 @@ A "step" is one full-graph training step of the 2-layer GCN teacher (Initial top
 Linear F->H, 2 x GCNConv H->H with the Initial residual, Linear H->C): forward, NLL loss on the train
 rows, backward, Adam step.  It aggregates 2*L*E edges (L forward + L transposed aggregations).
 N=1 workload = BASELINE.json configs[3]: synthetic power-law graph, 10M nodes / 100M directed edges,
-256-dim fp32.  N>1 = the same graph node-sliced over N GPUs ("strong" scaling), NCCL all-gather of the
-row blocks per aggregation.
+256-dim fp32.  N>1 = the same graph node-sliced over N GPUs ("strong" scaling); the per-aggregation exchange
+is fused into the producing GEMM's epilogue (NVLink peer stores of the rows each peer gathers, --exchange push,
+default) or an NCCL all-gather of the row blocks (--exchange nccl).
 
 Prints ONE JSON line (rank 0).  Extra keys beside the driver contract: roofline (forward aggregation
 kernel), roofline_kernels (every C-ABI kernel), cpu_baseline, e2e, clocks, gpu_launches.

@@ -251,7 +251,10 @@ def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_s
     out2 = torch.empty((M, N), dtype=torch.float32, device=A.device) if want_out2 else None
     act = C.CB_ACT_RELU if relu else C.CB_ACT_NONE
     if M == 0:
-        out = push.local if push is not None else out
+        if push is not None:      # a rank that owns no rows still takes part in every panel's barrier
+            for p in range(push.n_panels):
+                push.pushed(p)
+            out = push.local
         return (out, out2) if want_out2 else out
     if push is None:
         alg = 4 * (M * K + 2 * N * K + M * N * (int(want_out) + int(want_out2) + int(add is not None)))
@@ -297,6 +300,9 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=A.device) if ws_bytes else None
     extra = int(add is not None) + int(gate_f32 is not None) + int(d_x0 is not None) * (1 + int(bool(accumulate_x0)))
     if M == 0:
+        if push is not None:      # a rank that owns no rows still takes part in every panel's barrier
+            for p in range(push.n_panels):
+                push.pushed(p)
         return out, (col_sum.zero_() if col_sum is not None else None), d_x0
     panels = [(0, N, None, out)] if push is None else \
         [(p * push.panel_width, push.panel_width, push.descs[p], push.panel_local[p]) for p in range(push.n_panels)]

@@ -52,19 +52,23 @@ def parse():
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--cpu-nodes', type=int, default=1_000_000, help='sample size of the CPU baseline / reference arm')
     p.add_argument('--cpu-steps', type=int, default=2)
+    p.add_argument('--dropout', type=float, default=0.0,
+                   help='TeacherGNN dropout (reference defaults are 0.2-0.6, base_options.py:20,190-220); > 0 takes the '
+                        'layers off the pre-scaled hand-off, reported as a second line under profiles/')
     p.add_argument('--profile', default='', help='write a torch.profiler kernel table of 2 steps to this file')
     return p.parse_args()
 
 
 def workload_name(a):
     return (f'synthetic power-law (gamma=2.5) N={a.nodes} E={a.edges} d={a.dim} fp32, {a.layers}-layer GCN '
-            f'(Initial topology, C={a.classes}, SE={a.se}), fwd+bwd+Adam')
+            f'(Initial topology, C={a.classes}, SE={a.se}' + (f', dropout={a.dropout}' if a.dropout else '') +
+            '), fwd+bwd+Adam')
 
 
 def model_args(a, n_nodes, device):
     from types import SimpleNamespace
     m = SimpleNamespace(type_trick='Initial', type_model='GCN', num_layers=a.layers, dim_hidden=a.dim,
-                        num_feats=a.dim, num_classes=a.classes, dropout=0.0, res_alpha=0.1, layer_agg='concat',
+                        num_feats=a.dim, num_classes=a.classes, dropout=a.dropout, res_alpha=0.1, layer_agg='concat',
                         transductive=True, N_nodes=n_nodes, device=device, dataset='synthetic',
                         dim_learnable_input=0, lamda=0.5, num_groups=None, skip_weight=None, graph_dropout=0.0,
                         layerwise_dropout=False, dim_commonEmb=a.classes)
@@ -173,14 +177,16 @@ def run_reference(a):
     if rank != 0:
         return
     steps = max(1, a.steps)
-    warm = max(1, min(a.warmup, 3))
-    # bounded sample: ~11 us of host time per node per step on 8 cores; keep the whole run near 2 minutes
-    a.cpu_nodes = int(max(50_000, min(a.cpu_nodes, 120.0 / ((steps + warm) * 11e-6))))
+    warm = max(0, a.warmup)       # the same warm-up count as the repo's arm
+    # bounded sample: ~11 us of host time per node per step on 8 cores (less with more cores); the largest sample
+    # that keeps the whole --steps/--warmup run inside a 4-minute box, capped at a fifth of the workload
+    a.cpu_nodes = int(max(50_000, min(a.nodes // 5, 240.0 / ((steps + warm) * 11e-6))))
     val, ms, sample, threads = cpu_reference_run(a, steps, warm)
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': steps,
             'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(a), 'timed_on': 'bounded sample, see cpu_baseline.sample'},
+            'config': {'workload': workload_name(a), 'timed_on': 'bounded sample, see cpu_baseline.sample',
+                       'sample_nodes': a.cpu_nodes, 'sample_fraction_of_workload': round(a.cpu_nodes / a.nodes, 5)},
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -245,17 +251,6 @@ def run_ours(a):
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     se_coef = 0.5
 
-    def step(x=x):
-        opt.zero_grad(set_to_none=True)
-        res = model.get_3_embs(x, None, idx)
-        loss = F.nll_loss(F.log_softmax(res.emb4classi, 1), y[idx], reduction='sum') / n_train
-        if model.se_reg_all is not None:
-            loss = loss + se_coef * model.se_reg_all
-        loss.backward()
-        cbdist.allreduce_dense_grads(model, world)
-        opt.step()
-        return loss
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -274,6 +269,36 @@ def run_ours(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    def allsum(t):
+        t = t.detach().double().reshape(-1).clone()
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t]
+
+    # parity evidence the driver can compare across N: the forward pass at the INITIAL weights is bit-identical for
+    # every world size (per-row arithmetic does not depend on the slicing), so its fp64 checksums must agree to
+    # the last printed digit; the loss after the timed steps agrees to fp32 all-reduce reassociation (~1e-6).
+    model.eval()
+    with torch.no_grad():
+        lg0 = model.get_3_embs(x, None, idx).emb4classi_full.double()
+        logits_checksum = [float('%.12e' % v) for v in allsum(torch.stack([lg0.sum(), lg0.abs().sum(), (lg0 * lg0).sum()]))]
+        del lg0
+    model.train()
+
+    last = {}
+
+    def step(x=x):
+        opt.zero_grad(set_to_none=True)
+        res = model.get_3_embs(x, None, idx)
+        loss = F.nll_loss(F.log_softmax(res.emb4classi, 1), y[idx], reduction='sum') / n_train
+        if model.se_reg_all is not None:
+            loss = loss + se_coef * model.se_reg_all
+        loss.backward()
+        cbdist.allreduce_dense_grads(model, world)
+        opt.step()
+        last['nll'] = loss.detach() if model.se_reg_all is None else (loss.detach() - se_coef * model.se_reg_all.detach())
+        return loss
+
     for _ in range(max(3, a.warmup)):
         step()
     launches0, exch0 = _cabi.launch_count(), graph.exchanged_bytes
@@ -282,6 +307,7 @@ def run_ours(a):
     launches = _cabi.launch_count() - launches0
     exch_per_step = (graph.exchanged_bytes - exch0) // a.steps
     value = 2 * L * E / (ms_step * 1e-3)
+    nll_after = allsum(last['nll'])[0]        # global train NLL of the last timed step (each rank holds its share)
 
     if a.profile and rank == 0:
         from torch.profiler import profile, ProfilerActivity
@@ -399,6 +425,11 @@ def run_ours(a):
                            'gemm': 'tcgen05 3xTF32 split (fp32-class accuracy), fp32 accumulate in TMEM'},
                 'roofline': roofline, 'roofline_kernels': kernels, 'cpu_baseline': cpu, 'e2e': e2e,
                 'clocks': clk.summary(), 'gpu_launches': launches,
+                'parity': {'logits_checksum_initial_weights': logits_checksum,
+                           'what': '[sum, sum|.|, sum of squares] in fp64 over the [N, C] logits of one forward at the '
+                                   'seeded initial weights, all-reduced: identical for every --gpus N',
+                           'train_nll_after_timed_steps': float('%.8e' % nll_after),
+                           'steps_taken': max(3, a.warmup) + a.steps},
                 'exchange_bytes_per_step_per_rank': exch_per_step}
         print(json.dumps(line), flush=True)
     if world > 1:

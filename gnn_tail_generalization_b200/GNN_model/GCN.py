@@ -216,13 +216,24 @@ class TricksComb(nn.Module):
 
         # plan of the op whose output is the current x, handed to x's single consumer (see ops.BwdPlan)
         prev_plan = None
+        norm_runs = norm_is_executed(trick)
+        initial = AcontainsB(trick, ['Initial'])
+        mixes = AcontainsB(trick, ['Initial', 'Dense', 'Residual'])
+        keeps_history = AcontainsB(trick, ['Residual', 'Dense', 'Jumping'])   # x_list entries are re-read later
+        # the Initial mix rides on the aggregation epilogue only if nothing else reads the pre-mix activations:
+        # no norm layer in between, no want_les, and no history consumer (x_list holds the PRE-mix relu outputs,
+        # GCN.py:127-131, which a "Jumping"/"Dense"/"Residual" name re-reads)
+        mix_will_fuse = initial and not norm_runs and not want_les and not keeps_history
         if self.has_residual_MLP:
             x = F.dropout(x, p=self.embedding_dropout, training=self.training)
             lin = self.layers_MLP[0]
             lin_plan = _ops.new_plan()
             x, _ = _ops.dense(x, lin.weight, 'nk', bias=lin.bias, relu=True, my_plan=lin_plan)
-            if AcontainsB(self.type_trick, ['Initial']) and x.requires_grad:
-                # x0 feeds every layer's residual mix: collect those gradients inside the backward kernels
+            if mix_will_fuse and x.requires_grad:
+                # x0 feeds every layer's residual mix, and the mix is fused into the aggregation epilogue: collect
+                # those gradients inside the backward kernels.  (With an un-fused mix -- norm layer in between, or
+                # want_les -- x0 also receives plain autograd gradients from layers_res[i](x_list); the Linear then
+                # runs its own relu/bias backward on their sum.)
                 x0_sink = _ops.GradSink()
                 x = _ops.sink_hub(x, x0_sink)
                 # every gradient of x0 ends in layer 0's dX GEMM (the residual shares are parked in the
@@ -230,10 +241,6 @@ class TricksComb(nn.Module):
                 prev_plan = lin_plan
             x_list.append(x)
 
-        norm_runs = norm_is_executed(trick)
-        initial = AcontainsB(trick, ['Initial'])
-        mixes = AcontainsB(trick, ['Initial', 'Dense', 'Residual'])
-        keeps_history = AcontainsB(trick, ['Residual', 'Dense', 'Jumping'])   # x_list entries are re-read later
         no_drop = (not self.training) or self.dropout == 0
         xs_next = None   # D_out^-1/2-scaled copy of x produced by the previous layer's epilogue
 
@@ -247,7 +254,7 @@ class TricksComb(nn.Module):
             # really runs between them or the caller wants the pre-activation values
             fuse_tail = not norm_runs and not want_les
             relu_fused = fuse_tail and want_relu
-            mix_fused = fuse_tail and initial and len(x_list) >= 1
+            mix_fused = mix_will_fuse and len(x_list) >= 1
             last = i == L - 1
             feeds_conv = (not last) and no_drop and (mix_fused or not mixes) and fuse_tail
             need_plain = last or keeps_history or not feeds_conv

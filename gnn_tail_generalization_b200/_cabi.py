@@ -12,9 +12,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcoldbrew_b200.so')
 
 CB_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 CB_ACT_NONE, CB_ACT_RELU = 0, 1
 CB_BY_DST, CB_BY_SRC = 0, 1
+CB_F32, CB_BF16 = 0, 1
 
 Q_NUM_NODES, Q_NUM_EDGES, Q_ROW_BEGIN, Q_ROW_END, Q_HAS_ZERO_IN_DEG, Q_HUB_CHUNK = 0, 1, 2, 3, 4, 5
 Q_DST_ROWPTR, Q_DST_COL, Q_DST_PERM, Q_DST_NUM_HUB_CHUNKS = 10, 11, 12, 13
@@ -45,6 +46,9 @@ SYMBOLS = {
     'cb_agg_gather': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_agg_forward_bf16': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_agg_gather_bf16': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    'cb_graph_live_workspace_bytes': (_i64, [_vp, _int]),
+    'cb_graph_compact_live': (_int, [_vp, _int, _vp, _vp, _i64, _vp]),
+    'cb_agg_gather_compacted': (_int, [_vp, _int, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_prep_workspace_bytes': (_i64, [_i64, _i64]),
     'cb_agg_backward_prep': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _dbl, _vp, _vp, _vp, _int, _vp,
                                     _i64, _vp]),

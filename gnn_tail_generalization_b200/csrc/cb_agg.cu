@@ -46,6 +46,11 @@ struct AggArgs {
     void* out2;               // [rows, d] or null (storage type S)
     uint8_t* mask;            // [rows, d] or null
     const uint8_t* live;      // [n_src] or null: rows of X with live[s] == 0 are all-zero and are not gathered
+    // live-column compacted lists (cb_graph_compact_live): rowptr / col / chunk_beg point into the compacted CSR,
+    // hub_rowptr is the ORIGINAL rowptr (a row is a hub by its original degree, so that every partial sum keeps
+    // the association of the uncompacted walk) and chunk_end bounds each chunk explicitly
+    const int64_t* hub_rowptr;  // null: rowptr
+    const int64_t* chunk_end;   // null: min(chunk_beg + hub_chunk, row end)
 };
 
 template <int VEC>
@@ -222,13 +227,22 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
         row = task;
         beg = __ldg(a.rowptr + row);
         end = __ldg(a.rowptr + row + 1);
-        if (end - beg > a.hub_chunk) return;  // hub row: its chunks and k_combine produce it
+        // hub row: its chunks and k_combine produce it
+        if (a.hub_rowptr) {
+            if (__ldg(a.hub_rowptr + row + 1) - __ldg(a.hub_rowptr + row) > a.hub_chunk) return;
+        } else if (end - beg > a.hub_chunk) {
+            return;
+        }
     } else {
         const int64_t c = task - a.n_rows;
         row = __ldg(a.chunk_row + c);
         beg = __ldg(a.chunk_beg + c);
-        const int64_t rend = __ldg(a.rowptr + row + 1);
-        end = beg + a.hub_chunk < rend ? beg + a.hub_chunk : rend;
+        if (a.chunk_end) {
+            end = __ldg(a.chunk_end + c);
+        } else {
+            const int64_t rend = __ldg(a.rowptr + row + 1);
+            end = beg + a.hub_chunk < rend ? beg + a.hub_chunk : rend;
+        }
     }
 
     float acc[NCH][VEC];
@@ -295,7 +309,8 @@ __global__ void __launch_bounds__(256) k_combine(const AggArgs a) {
     if (c >= a.n_chunks) return;
     const int64_t row = a.chunk_row[c];
     if (c > 0 && a.chunk_row[c - 1] == row) return;  // only the first chunk of a row combines
-    const int64_t deg = a.rowptr[row + 1] - a.rowptr[row];
+    const int64_t* rp = a.hub_rowptr ? a.hub_rowptr : a.rowptr;
+    const int64_t deg = rp[row + 1] - rp[row];
     const int64_t n = (deg + a.hub_chunk - 1) / a.hub_chunk;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
@@ -363,7 +378,7 @@ static int launch_vec(AggArgs a, cudaStream_t st) {
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int run_agg(const cb_graph* g, int side_id, int dtype, AggArgs a, void* workspace, int64_t workspace_bytes,
-                   cudaStream_t st) {
+                   cudaStream_t st, const void* live_ws = nullptr) {
     const Side& s = side_id == CB_BY_DST ? g->by_dst : g->by_src;
     a.rowptr = s.rowptr;
     a.col = s.col;
@@ -371,6 +386,14 @@ static int run_agg(const cb_graph* g, int side_id, int dtype, AggArgs a, void* w
     a.chunk_row = s.chunk_row;
     a.chunk_beg = s.chunk_beg;
     a.n_chunks = s.n_chunks;
+    if (live_ws) {
+        const LiveView v = live_view(g, side_id, const_cast<void*>(live_ws));
+        a.hub_rowptr = s.rowptr;
+        a.rowptr = v.rowptr;
+        a.col = v.col;
+        a.chunk_beg = v.chunk_beg;
+        a.chunk_end = v.chunk_end;
+    }
     a.hub_chunk = g->hub_chunk;
     a.col0 = 0;
     a.partial = (float*)workspace;
@@ -419,7 +442,7 @@ static int agg_forward_impl(const cb_graph* g, int dtype, const void* H, int64_t
 
 static int agg_gather_impl(const cb_graph* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
                            const float* row_scale, const uint8_t* row_live, void* out, int64_t ld_out, void* workspace,
-                           int64_t workspace_bytes, void* stream) {
+                           int64_t workspace_bytes, void* stream, const void* live_ws = nullptr) {
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_gather: graph is NULL");
     CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_agg_gather: unknown side");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_gather: d must be positive");
@@ -435,7 +458,7 @@ static int agg_gather_impl(const cb_graph* g, int side, int dtype, const void* X
     a.act = CB_ACT_NONE;
     a.out = out;
     a.live = row_live;
-    return run_agg(g, side, dtype, a, workspace, workspace_bytes, (cudaStream_t)stream);
+    return run_agg(g, side, dtype, a, workspace, workspace_bytes, (cudaStream_t)stream, live_ws);
 }
 
 }  // namespace cb
@@ -467,6 +490,15 @@ int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, i
                   void* stream) {
     return cb::agg_gather_impl(g, side, CB_F32, X, ld_x, d, row_scale, row_live, out, ld_out, workspace,
                                workspace_bytes, stream);
+}
+
+int cb_agg_gather_compacted(const cb_graph_t* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
+                            const float* row_scale, const void* live_ws, void* out, int64_t ld_out, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+    CB_REQUIRE(live_ws != nullptr, CB_E_INVALID, "cb_agg_gather_compacted: live_ws is NULL");
+    CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_agg_gather_compacted: unknown dtype");
+    return cb::agg_gather_impl(g, side, dtype, X, ld_x, d, row_scale, nullptr, out, ld_out, workspace,
+                               workspace_bytes, stream, live_ws);
 }
 
 int cb_agg_gather_bf16(const cb_graph_t* g, int side, const uint16_t* X, int64_t ld_x, int64_t d,

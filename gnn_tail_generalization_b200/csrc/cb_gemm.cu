@@ -719,11 +719,14 @@ template <int BN, bool GRAD>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const GemmArgs& g,
                        cudaStream_t st) {
     using C = Cfg<BN>;
-    static bool configured = false;
-    if (!configured) {
+    // the attribute is per device (and per context): one flag per device ordinal, set under a benign race
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         CB_CUDA(cudaFuncSetAttribute(k_gemm_rows<BN, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     dim3 grid((unsigned)gemm_grid_x(g.n_tiles_m, g.push.max_ctas), (unsigned)ceil_div(g.N, BN));
     k_gemm_rows<BN, GRAD><<<grid, THREADS, C::SMEM_BYTES, st>>>(ma, mh, ml, g);
@@ -1180,10 +1183,12 @@ int cb_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t
                CB_E_UNSUPPORTED, "cb_gemm_tn: operands must be 16-byte aligned, pitches multiples of 4 floats");
     CB_REQUIRE(workspace && workspace_bytes >= cb_gemm_tn_workspace_bytes(M, Ka, Nb), CB_E_WORKSPACE,
                "cb_gemm_tn: workspace missing or smaller than cb_gemm_tn_workspace_bytes()");
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<bool> configured[64];   // per device ordinal (the attribute is per device)
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         CB_CUDA(cudaFuncSetAttribute(tc::k_gemm_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TN_SMEM_BYTES));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     cudaStream_t st = (cudaStream_t)stream;
     int64_t chunks, n_segs;

@@ -341,6 +341,148 @@ static int build(cb_graph* g, const int64_t* edge_index, int64_t E, cudaStream_t
     return CB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// live-column compaction (row-sparse gathers: the gradient under a loss over the train rows only)
+// ---------------------------------------------------------------------------------------------
+static inline int64_t align256(int64_t b) { return (b + 255) & ~(int64_t)255; }
+
+LiveView live_view(const cb_graph* g, int side_id, void* workspace) {
+    const Side& s = side_id == CB_BY_DST ? g->by_dst : g->by_src;
+    const int64_t groups = ceil_div(s.n_edges > 0 ? s.n_edges : 1, 32);
+    const int64_t tiles = ceil_div(s.n_edges > 0 ? s.n_edges : 1, LIVE_TILE);
+    char* p = (char*)workspace;
+    int64_t o = 0;
+    LiveView v{};
+    v.rowptr = (int64_t*)(p + o);    o += align256((g->rows + 1) * (int64_t)sizeof(int64_t));
+    v.chunk_beg = (int64_t*)(p + o); o += align256((s.n_chunks + 1) * (int64_t)sizeof(int64_t));
+    v.chunk_end = (int64_t*)(p + o); o += align256((s.n_chunks + 1) * (int64_t)sizeof(int64_t));
+    v.col = (int32_t*)(p + o);       o += align256((s.n_edges + 1) * (int64_t)sizeof(int32_t));
+    v.bits = (uint32_t*)(p + o);     o += align256(groups * (int64_t)sizeof(uint32_t));
+    v.posw = (int32_t*)(p + o);      o += align256(groups * (int64_t)sizeof(int32_t));
+    v.spine = (int32_t*)(p + o);     o += align256((tiles + 1) * (int64_t)sizeof(int32_t));
+    v.bytes = o;
+    return v;
+}
+
+// pass 1: one live bit per stored edge (ballot of live[col[j]] over 32 consecutive edges), live count per tile
+__global__ void __launch_bounds__(256) k_live_bits(const int32_t* __restrict__ col, int64_t E,
+                                                   const uint8_t* __restrict__ live, uint32_t* __restrict__ bits,
+                                                   int32_t* __restrict__ tile_count) {
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t g0 = (int64_t)blockIdx.x * (LIVE_TILE / 32) + w * (LIVE_TILE / 32 / 8);
+    int cnt = 0;
+#pragma unroll 4
+    for (int k = 0; k < LIVE_TILE / 32 / 8; ++k) {
+        const int64_t j = (g0 + k) * 32 + lane;
+        const bool on = j < E && __ldg(live + __ldg(col + j)) != 0;
+        const uint32_t b = __ballot_sync(0xffffffffu, on);
+        if (lane == 0 && (g0 + k) * 32 < E) bits[g0 + k] = b;
+        cnt += __popc(b);
+    }
+    if (lane == 0) wsum[w] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += wsum[i];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+// exclusive prefix of the tile counts in place (one block), grand total into spine[n]
+__global__ void __launch_bounds__(1024) k_live_spine(int32_t* __restrict__ spine, int64_t n) {
+    __shared__ int wtot[32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < n; b += 1024) {
+        const int64_t i = b + threadIdx.x;
+        const int v = i < n ? spine[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wtot[w] = inc;
+        __syncthreads();
+        int base = carry_s;
+        for (int k = 0; k < w; ++k) base += wtot[k];
+        if (i < n) spine[i] = base + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = base + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) spine[n] = carry_s;
+}
+
+// pass 2: position of every 32-edge group in the compacted list, and the compacted column ids themselves
+__global__ void __launch_bounds__(256) k_live_fill(const int32_t* __restrict__ col, int64_t E,
+                                                   const uint32_t* __restrict__ bits, const int32_t* __restrict__ spine,
+                                                   int32_t* __restrict__ posw, int32_t* __restrict__ col_c) {
+    constexpr int GPW = LIVE_TILE / 32 / 8;   // groups per warp: 16
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t g0 = (int64_t)blockIdx.x * (LIVE_TILE / 32) + w * GPW;
+    const int64_t n_groups = (E + 31) >> 5;
+    // lane k < GPW holds the bit word of the warp's k-th group
+    const uint32_t mine = (lane < GPW && g0 + lane < n_groups) ? __ldg(bits + g0 + lane) : 0u;
+    int inc = __popc(mine);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const int excl = inc - __popc(mine);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int base = __ldg(spine + blockIdx.x);
+    for (int k = 0; k < w; ++k) base += wsum[k];
+    if (lane < GPW && g0 + lane < n_groups) posw[g0 + lane] = base + excl;
+#pragma unroll 4
+    for (int k = 0; k < GPW; ++k) {
+        const uint32_t b = __shfl_sync(0xffffffffu, mine, k);
+        const int off = __shfl_sync(0xffffffffu, excl, k);
+        if ((b >> lane) & 1u) {
+            const int64_t j = (g0 + k) * 32 + lane;
+            col_c[base + off + __popc(b & ((1u << lane) - 1u))] = __ldg(col + j);
+        }
+    }
+}
+
+__device__ __forceinline__ int64_t live_pos(int64_t e, int64_t E, const uint32_t* __restrict__ bits,
+                                            const int32_t* __restrict__ posw, int32_t total) {
+    if (e >= E) return total;
+    const uint32_t b = __ldg(bits + (e >> 5));
+    return (int64_t)__ldg(posw + (e >> 5)) + __popc(b & ((1u << (e & 31)) - 1u));
+}
+
+// pass 3: row offsets and hub-chunk bounds of the compacted list
+__global__ void __launch_bounds__(256) k_live_offsets(const int64_t* __restrict__ rowptr, int64_t rows, int64_t E,
+                                                      const int32_t* __restrict__ chunk_row,
+                                                      const int64_t* __restrict__ chunk_beg, int64_t n_chunks,
+                                                      int hub_chunk, const uint32_t* __restrict__ bits,
+                                                      const int32_t* __restrict__ posw, const int32_t* __restrict__ spine,
+                                                      int64_t n_tiles, int64_t* __restrict__ rowptr_c,
+                                                      int64_t* __restrict__ chunk_beg_c, int64_t* __restrict__ chunk_end_c) {
+    const int32_t total = __ldg(spine + n_tiles);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= rows + n_chunks; i += stride) {
+        if (i <= rows) {
+            rowptr_c[i] = live_pos(__ldg(rowptr + i), E, bits, posw, total);
+        } else {
+            const int64_t c = i - rows - 1;
+            const int64_t b = __ldg(chunk_beg + c);
+            const int64_t rend = __ldg(rowptr + __ldg(chunk_row + c) + 1);
+            const int64_t e = b + hub_chunk < rend ? b + hub_chunk : rend;
+            chunk_beg_c[c] = live_pos(b, E, bits, posw, total);
+            chunk_end_c[c] = live_pos(e, E, bits, posw, total);
+        }
+    }
+}
+
 }  // namespace cb
 
 // ---------------------------------------------------------------------------------------------
@@ -380,6 +522,39 @@ int cb_graph_create_sliced(const int64_t* edge_index, int64_t num_edges, int64_t
 int cb_graph_create(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int hub_chunk,
                     void* stream, cb_graph_t** out) {
     return cb_graph_create_sliced(edge_index, num_edges, num_nodes, 0, num_nodes, hub_chunk, stream, out);
+}
+
+int64_t cb_graph_live_workspace_bytes(const cb_graph_t* g, int side) {
+    if (!g || (side != CB_BY_DST && side != CB_BY_SRC)) return 0;
+    return cb::live_view(g, side, nullptr).bytes;
+}
+
+int cb_graph_compact_live(const cb_graph_t* g, int side_id, const uint8_t* row_live, void* live_ws,
+                          int64_t live_ws_bytes, void* stream) {
+    using namespace cb;
+    CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_graph_compact_live: graph is NULL");
+    CB_REQUIRE(side_id == CB_BY_DST || side_id == CB_BY_SRC, CB_E_INVALID, "cb_graph_compact_live: unknown side");
+    CB_REQUIRE(row_live != nullptr, CB_E_INVALID, "cb_graph_compact_live: row_live is NULL");
+    CB_REQUIRE(live_ws != nullptr && live_ws_bytes >= cb_graph_live_workspace_bytes(g, side_id), CB_E_WORKSPACE,
+               "cb_graph_compact_live: workspace smaller than cb_graph_live_workspace_bytes()");
+    CB_REQUIRE((reinterpret_cast<uintptr_t>(live_ws) & 255u) == 0, CB_E_INVALID,
+               "cb_graph_compact_live: workspace must be 256-byte aligned");
+    const Side& s = side_id == CB_BY_DST ? g->by_dst : g->by_src;
+    const LiveView v = live_view(g, side_id, live_ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t E = s.n_edges;
+    const int64_t tiles = ceil_div(E > 0 ? E : 1, LIVE_TILE);
+    k_live_bits<<<(unsigned)tiles, 256, 0, st>>>(s.col, E, row_live, v.bits, v.spine);
+    CB_LAUNCH_CHECK();
+    k_live_spine<<<1, 1024, 0, st>>>(v.spine, tiles);
+    CB_LAUNCH_CHECK();
+    k_live_fill<<<(unsigned)tiles, 256, 0, st>>>(s.col, E, v.bits, v.spine, v.posw, v.col);
+    CB_LAUNCH_CHECK();
+    k_live_offsets<<<grid_for(g->rows + 1 + s.n_chunks, 256), 256, 0, st>>>(
+        s.rowptr, g->rows, E, s.chunk_row, s.chunk_beg, s.n_chunks, g->hub_chunk, v.bits, v.posw, v.spine, tiles,
+        v.rowptr, v.chunk_beg, v.chunk_end);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
 }
 
 int cb_graph_destroy(cb_graph_t* g) {

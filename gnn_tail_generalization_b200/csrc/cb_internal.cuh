@@ -40,6 +40,22 @@ struct cb_graph {
 
 namespace cb {
 
+// Live-column compaction of one CSR side (cb_graph_compact_live): the caller-supplied workspace holds a second
+// CSR whose rows keep only the columns flagged live, in the stored order, plus the hub-chunk bounds mapped into
+// it (a chunk still covers the same ORIGINAL edges, so every partial sum keeps its association).
+struct LiveView {
+    int64_t* rowptr;     // [rows+1] offsets into col
+    int64_t* chunk_beg;  // [n_chunks]
+    int64_t* chunk_end;  // [n_chunks]
+    int32_t* col;        // [<= n_edges]
+    uint32_t* bits;      // [ceil(n_edges/32)] live bit per stored edge
+    int32_t* posw;       // [ceil(n_edges/32)] number of live edges before each 32-edge group
+    int32_t* spine;      // [ceil(n_edges/LIVE_TILE)+1] exclusive prefix of the tile counts, total in the last slot
+    int64_t bytes;
+};
+constexpr int LIVE_TILE = 4096;
+LiveView live_view(const cb_graph* g, int side, void* workspace);
+
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 extern std::atomic<int64_t> g_launches;

@@ -263,6 +263,12 @@ class SlicedGraph(GraphHandle):
         self.rank, self.world, self.group = rank, world, group
         self.exchanged_bytes = 0
         self.peer = None
+        if world > 1 and dist.is_initialized():
+            # the reference's check is global (GCN.py:187-197): every rank must raise together, or the ranks that
+            # own no such node would walk into the exchange collectives alone
+            flag = torch.tensor([int(self.has_zero_in_degree)], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            self.has_zero_in_degree = bool(int(flag))
 
     def enable_push(self, max_d, panels=1, push_ctas=0):
         """Switch the exchange from an NCCL all-gather after the producing kernel to peer stores from

@@ -124,10 +124,32 @@ def agg_forward_raw(graph, H, bias=None, x0=None, alpha=0.0, relu=False, want_ou
     return out, out_scaled, mask
 
 
-def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None, live=None):
+def compact_live_raw(graph, side, live):
+    """cb_graph_compact_live: the CSR of ``side`` restricted to the columns with live[s] != 0, built in a workspace
+    cached on the graph handle (one per side; every use is ordered on the calling stream).  Returns the workspace."""
+    _need_cuda(live)
+    if live.dtype != torch.uint8 or live.numel() != graph.num_nodes:
+        raise ValueError('live must be uint8 [num_nodes]')
+    live = live.contiguous()
+    need = int(C.lib().cb_graph_live_workspace_bytes(graph.handle, side))
+    ws = graph._ws.get(('live', side))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=graph.device)
+        graph._ws[('live', side)] = ws
+    e = graph.num_edges if side == C.CB_BY_DST else graph.num_edges_by_src
+    alg = 2 * e * 4 + e // 4 + 2 * (graph.rows + 1) * 8 + graph.num_nodes
+    with torch.cuda.device(graph.device), _Timed('live_compact', alg, graph.device):
+        C.call('cb_graph_compact_live', graph.handle, side, C.ptr(live), C.ptr(ws), need, C.stream_ptr(graph.device))
+    return ws
+
+
+def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None, live=None, live_ws=None, flag_walk=False):
     """out[r] = row_scale[r] * sum_{j in row r} X[col[j]]  over one CSR side of the graph (X fp32 or bf16).
     panel=(c0, w): X is a [N_global, w] column panel; ``out`` is the preallocated full-width result.
-    live: uint8 [N_global], 0 where the row of X is known to be all-zero (not gathered)."""
+    live: uint8 [N_global], 0 where the row of X is known to be all-zero (not gathered): the side is first
+    compacted to the live columns (compact_live_raw) and the gather walks only those.  live_ws: an already
+    compacted workspace (several panels share one).  flag_walk: keep the full walk and test the flag per column
+    (the A/B partner of the compacted path; same sums)."""
     _need_cuda(X, row_scale)
     if X.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError(f'X must be float32 or bfloat16, got {X.dtype}')
@@ -148,9 +170,20 @@ def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None, live=No
     alg = gather_alg_bytes(graph, side, d, 1, 1, False, int(row_scale is not None), X.element_size())
     if live is not None and (live.dtype != torch.uint8 or live.numel() != graph.num_nodes):
         raise ValueError('live must be uint8 [num_nodes]')
-    name = ('agg_gather_dst' if side == C.CB_BY_DST else 'agg_gather_src') + ('_rowsparse' if live is not None else '') + \
+    sparse = live is not None or live_ws is not None
+    name = ('agg_gather_dst' if side == C.CB_BY_DST else 'agg_gather_src') + ('_rowsparse' if sparse else '') + \
         ('' if st == torch.float32 else '_bf16')
-    with torch.cuda.device(X.device), _Timed(name, alg, X.device):
+    if sparse and not flag_walk:
+        if live_ws is None:
+            live_ws = compact_live_raw(graph, side, live)
+        # bytes that must move whatever the live fraction is: the output, the row offsets (compacted + original)
+        alg = graph.rows * d * X.element_size() + 2 * (graph.rows + 1) * 8 + int(row_scale is not None) * graph.rows * 4
+        with torch.cuda.device(X.device), _Timed(name, alg, X.device):
+            C.call('cb_agg_gather_compacted', graph.handle, side, C.CB_F32 if st == torch.float32 else C.CB_BF16,
+                   C.ptr(X), d, d, C.ptr(row_scale), C.ptr(live_ws), _pofs(out, c0), D, C.ptr(ws), ws_bytes,
+                   C.stream_ptr(X.device))
+        return out
+    with torch.cuda.device(X.device), _Timed(name + ('_flagwalk' if sparse else ''), alg, X.device):
         C.call('cb_agg_gather' if st == torch.float32 else 'cb_agg_gather_bf16', graph.handle, side, C.ptr(X), d, d,
                C.ptr(row_scale), C.ptr(live), _pofs(out, c0), D, C.ptr(ws), ws_bytes, C.stream_ptr(X.device))
     return out
@@ -226,7 +259,9 @@ def split_weight(W, transpose):
 
 
 def gemm_supported(M, N, K):
-    return bool(C.lib().cb_gemm_rows_supported(int(M), int(N), int(K)))
+    """Shape test of cb_gemm_rows / cb_gemm_rows_grad.  M == 0 (a rank of a node-sliced graph that owns no rows)
+    counts as supported: the raw wrappers then launch nothing but still take part in the exchange barriers."""
+    return bool(C.lib().cb_gemm_rows_supported(max(int(M), 1), int(N), int(K)))
 
 
 def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_scale=None, want_out=True,
@@ -325,7 +360,7 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
 
 
 def gemm_tn_supported(M, Ka, Nb):
-    return bool(C.lib().cb_gemm_tn_supported(int(M), int(Ka), int(Nb)))
+    return bool(C.lib().cb_gemm_tn_supported(max(int(M), 1), int(Ka), int(Nb)))
 
 
 def gemm_tn_raw(A, B, a_row_scale=None, b_row_scale=None):
@@ -341,6 +376,8 @@ def gemm_tn_raw(A, B, a_row_scale=None, b_row_scale=None):
     if B.shape[0] != M:
         raise ValueError(f'A has {M} rows, B has {B.shape[0]}')
     Nb = B.shape[1]
+    if M == 0:
+        return torch.zeros((Ka, Nb), dtype=torch.float32, device=A.device)
     out = torch.empty((Ka, Nb), dtype=torch.float32, device=A.device)
     nb = int(C.lib().cb_gemm_tn_workspace_bytes(M, Ka, Nb))
     ws = torch.empty(nb, dtype=torch.uint8, device=A.device)
@@ -469,11 +506,14 @@ class BwdPlan:
         if add is not None and sink is not None and sink.buf is not None:
             return None     # the kernel keeps one [M, N] epilogue input: the caller runs the two-kernel path
         slot = g.push_slot(C.CB_BY_SRC, wb.n)    # G is what the transposed aggregation gathers
-        live = push_live = None
+        live = push_live = live_full = None
         if self.row_sparse_hint and slot is not None and add is None:
             # multi-GPU: a zero row of the incoming gradient gives a zero row of G -- known BEFORE the GEMM, so
-            # such rows are neither pushed to the peers nor gathered by anyone
+            # such rows are neither pushed to the peers nor gathered by anyone.  The flags of every rank are
+            # all-gathered HERE, ahead of the first panel's GEMM: the side-stream gathers wait only for their
+            # panel's event, which is recorded after this point, so they can never read a half-written flag array.
             push_live = (dtot_in != 0).any(dim=1).to(torch.uint8)
+            live_full = compact_live_raw(g, C.CB_BY_SRC, g.exchange_flags(push_live))   # the compacted workspace
         elif self.row_sparse_hint:
             live = torch.zeros(dtot_in.shape[0], dtype=torch.uint8, device=dtot_in.device)
         out, col, d_x0 = gemm_rows_grad_raw(
@@ -483,7 +523,7 @@ class BwdPlan:
             post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot, row_live=live, push_live=push_live)
         if sink is not None:
             sink.buf, d_x0 = d_x0, None
-        self.result = {'d_bias': col, 'd_x0': d_x0, 'G': out, 'live': live if push_live is None else push_live}
+        self.result = {'d_bias': col, 'd_x0': d_x0, 'G': out, 'live': live, 'live_full': live_full}
         if out.dim() == 3:
             # a panelled slot cannot be viewed as [M, N]: G travels in the plan, autograd gets a placeholder
             return out.new_zeros(()).expand(dtot_in.shape[0], wb.n)
@@ -580,9 +620,11 @@ class _Dense(torch.autograd.Function):
         x, weight, row_scale, out2_scale, y = ctx.saved_tensors
         if dy is not None and dy.dim() == 3:      # the output was a panelled exchange slot [M, panels, N/panels]
             dy = dy.reshape(dy.shape[0], -1)
-        if dy is not None and dy.numel() == 0:
+        # the unused output slot was a 1-D empty placeholder; a real [0, N] gradient (a rank that owns no rows)
+        # must still run, so that this rank enters the exchange barriers of the backward pass
+        if dy is not None and dy.dim() == 1:
             dy = None
-        if dy2 is not None and dy2.numel() == 0:
+        if dy2 is not None and dy2.dim() == 1:
             dy2 = None
         if dy is None and dy2 is None:
             return (None,) * 14
@@ -635,7 +677,7 @@ def dense(x, weight, layout, bias=None, add=None, relu=False, row_scale=None, ou
     Returns (out, out2); the one not asked for is None."""
     M, K = x.shape
     N = weight.shape[1] if layout == 'kn' else weight.shape[0]
-    if _dense_backend == 'tcgen05' and x.is_cuda and M > 0 and gemm_supported(M, N, K):
+    if _dense_backend == 'tcgen05' and x.is_cuda and gemm_supported(M, N, K):
         out, out2 = _Dense.apply(x, weight, bias, add, row_scale, out2_scale, layout, bool(relu), bool(want_out),
                                  bool(want_out2), dx_sink, my_plan, dx_plan, push_graph)
         return (out if want_out else None), (out2 if want_out2 else None)
@@ -645,7 +687,7 @@ def dense(x, weight, layout, bias=None, add=None, relu=False, row_scale=None, ou
     return _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, want_out, want_out2)
 
 
-def _panelled(graph, ex, make_outputs, run_panel):
+def _panelled(graph, ex, make_outputs, run_panel, after=None):
     """Runs ``run_panel(p, rows_of_panel_p, outputs)`` for every panel of an exchange slot on its side stream,
     each as soon as that panel's barrier has passed, while the compute stream goes on pushing the next panels.
 
@@ -660,6 +702,8 @@ def _panelled(graph, ex, make_outputs, run_panel):
             run_panel(p, ex.rows(p, graph.num_nodes), outputs)
         return outputs
     with torch.cuda.stream(side):
+        if after is not None:
+            side.wait_event(after)
         outputs = make_outputs()
         for p in range(ex.n_panels):
             side.wait_event(ex.events[p])
@@ -687,18 +731,26 @@ def aggregate_forward(graph, H, bias, x0, alpha, relu, want_out, want_scaled, wa
         graph, Hp, bias, x0, alpha, relu, outs=outs, panel=(p * pw, pw)))
 
 
-def aggregate_gather(graph, side, X, row_scale=None, live=None):
+def aggregate_gather(graph, side, X, row_scale=None, live=None, live_full=None):
     """Exchange + plain gather-reduce over one side; panel-pipelined when X was pushed in column panels.
-    live: uint8 [rows] flags of the local rows of X (0 = all-zero row), exchanged like the rows themselves."""
-    if live is not None:
-        live = graph.exchange_flags(live)
+    live: uint8 [rows] flags of the local rows of X (0 = all-zero row), exchanged like the rows themselves.
+    live_full: the compacted workspace built from the already exchanged flags (ordered before the pushes -- see
+    BwdPlan.run)."""
+    flags_event = None
+    live_ws = live_full
+    if live_ws is None and live is not None:
+        live_ws = compact_live_raw(graph, side, graph.exchange_flags(live))
+        if graph.world > 1:
+            # built on the compute stream AFTER the pushes: a side-stream gather must wait for it explicitly
+            flags_event = torch.cuda.Event()
+            flags_event.record(torch.cuda.current_stream(graph.device))
     ex = graph.exchange(X)
     if torch.is_tensor(ex):
-        return agg_gather_raw(graph, side, ex, row_scale, live=live)
+        return agg_gather_raw(graph, side, ex, row_scale, live_ws=live_ws)
     pw = ex.panel_width
-    (out,) = _panelled(graph, ex, lambda: (torch.empty((graph.rows, ex.width), dtype=torch.float32, device=graph.device),),
+    (out,) = _panelled(graph, ex, lambda: (torch.empty((graph.rows, ex.width), dtype=X.dtype, device=graph.device),),
                        lambda p, Xp, outs: agg_gather_raw(graph, side, Xp, row_scale, out=outs[0], panel=(p * pw, pw),
-                                                          live=live))
+                                                          live_ws=live_ws), after=flags_event)
     return out
 
 
@@ -746,9 +798,9 @@ class _FusedAggregate(torch.autograd.Function):
     def backward(ctx, d_out, d_out_scaled):
         mask, relu_out = ctx.saved_tensors
         graph = ctx.graph
-        if d_out is not None and d_out.numel() == 0:
+        if d_out is not None and d_out.dim() == 1:          # 1-D empty placeholder of the unused slot
             d_out = None
-        if d_out_scaled is not None and d_out_scaled.numel() == 0:
+        if d_out_scaled is not None and d_out_scaled.dim() == 1:
             d_out_scaled = None
         if d_out is None and d_out_scaled is None:
             return (None,) * 10
@@ -758,9 +810,9 @@ class _FusedAggregate(torch.autograd.Function):
             G = done.get('G')
             if G is None:
                 G = (d_out if d_out is not None else d_out_scaled).contiguous()
-            d_bias, d_x0, live = done['d_bias'], done['d_x0'], done.get('live')
+            d_bias, d_x0, live, live_full = done['d_bias'], done['d_x0'], done.get('live'), done.get('live_full')
         else:
-            live = None
+            live = live_full = None
             want_bias = ctx.has_bias and ctx.needs_input_grad[1]
             want_x0 = ctx.mixed and ctx.needs_input_grad[2]
             sink = ctx.x0_sink if want_x0 else None
@@ -771,7 +823,7 @@ class _FusedAggregate(torch.autograd.Function):
                 sink.buf, d_x0 = d_x0, None
         dH = None
         if ctx.needs_input_grad[0]:
-            dH = aggregate_gather(graph, C.CB_BY_SRC, G, live=live).view(ctx.h_shape)
+            dH = aggregate_gather(graph, C.CB_BY_SRC, G, live=live, live_full=live_full).view(ctx.h_shape)
         return dH, d_bias, d_x0, None, None, None, None, None, None, None
 
 

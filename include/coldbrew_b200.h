@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 2   /* 2: row pitches on cb_agg_*, cb_peer_push_t, cb_gemm_rows_grad, bf16 aggregation */
+#define CB_ABI_VERSION 3   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build */
 
 enum {
     CB_OK = 0,
@@ -156,6 +156,23 @@ int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, i
 int cb_agg_gather_bf16(const cb_graph_t* g, int side, const uint16_t* X, int64_t ld_x, int64_t d,
                        const float* row_scale, const uint8_t* row_live, uint16_t* out, int64_t ld_out, void* workspace,
                        int64_t workspace_bytes, void* stream);
+
+/*
+ * Row-sparse gather without walking the dead columns.  cb_graph_compact_live builds, in the caller's workspace
+ * (cb_graph_live_workspace_bytes, 256-byte aligned), a second CSR of one side that keeps only the columns s with
+ * row_live[s] != 0, in the stored order; cb_agg_gather_compacted then gathers over it (dtype CB_F32 / CB_BF16 of X
+ * and out).  Hub rows keep the chunk bounds of the full list, so every partial sum has the same association as the
+ * full walk and the result is bit-identical to cb_agg_gather with the same flags (and, x + 0 = x, without them).
+ * Use: the gradient under a loss over the train rows only (trainer_node_classification.py:390-391) is non-zero on
+ * those rows alone; the transposed aggregation (autograd of GCN.py:238) of the last layer is then a gather over
+ * ~|train|/N of the edges.  The compaction is 4 small kernels reading the column ids twice.
+ */
+int64_t cb_graph_live_workspace_bytes(const cb_graph_t* g, int side);
+int cb_graph_compact_live(const cb_graph_t* g, int side, const uint8_t* row_live, void* live_ws,
+                          int64_t live_ws_bytes, void* stream);
+int cb_agg_gather_compacted(const cb_graph_t* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
+                            const float* row_scale, const void* live_ws, void* out, int64_t ld_out, void* workspace,
+                            int64_t workspace_bytes, void* stream);
 
 /*
  * Backward prologue of cb_agg_forward: from the gradient(s) arriving at the layer output build the

@@ -163,6 +163,12 @@ CASES = {
     'initial_se000_L2':      (dict(type_trick='Initial', whetherHasSE='000', num_layers=2), 52, 140, 16),   # bench topology
     'featureless_se111_L2':  (dict(type_trick='Initial', whetherHasSE='111', num_layers=2,
                                    change_to_featureless=True), 38, 95, 17),             # GNN_normalizations.py:32-33
+    # combined trick names: the Initial mix runs per layer while x_list (pre-mix relu outputs, GCN.py:127-131) feeds
+    # the head; with "Jumping" in the name that head is layers_res[0](x_list) (GCN.py:134-136)
+    'initial_jumping_L3':    (dict(type_trick='InitialJumping', whetherHasSE='010', num_layers=3, layer_agg='concat',
+                                   res_alpha=0.2), 42, 105, 18),
+    'residual_jumping_L2':   (dict(type_trick='ResidualJumping', whetherHasSE='000', num_layers=2, layer_agg='maxpool',
+                                   res_alpha=0.3), 34, 85, 19),
 }
 
 

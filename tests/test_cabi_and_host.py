@@ -37,7 +37,8 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in _declared_symbols():
         assert hasattr(lib, name), name
     lib.cb_abi_version.restype = ctypes.c_int
-    assert lib.cb_abi_version() == 2
+    from gnn_tail_generalization_b200 import _cabi
+    assert lib.cb_abi_version() == _cabi.ABI_VERSION == 3
     lib.cb_last_error.restype = ctypes.c_char_p
     assert lib.cb_last_error() == b''
     lib.cb_launch_count.restype = ctypes.c_int64
@@ -98,7 +99,7 @@ _SEEDS = {'nores_se000_L2': 1, 'nores_se111_L3': 2, 'nores_se100_L4': 3, 'initia
           'initial_se100_L3': 5, 'residual_se010_L3': 6, 'dense_concat_L2': 7, 'dense_maxpool_L2': 8,
           'dense_attention_L2': 9, 'jumping_concat_L3': 10, 'jumping_maxpool_L2': 11, 'exact_batchnorm_L2': 12,
           'exact_pairnorm_L3': 13, 'learnable_input_L2': 14, 'odd_dims_L2': 15, 'initial_se000_L2': 16,
-          'featureless_se111_L2': 17}
+          'featureless_se111_L2': 17, 'initial_jumping_L3': 18, 'residual_jumping_L2': 19}
 
 
 @pytest.mark.parametrize('name', golden_cases())

@@ -209,9 +209,47 @@ def test_gemm_rows_grad_row_live_flags_and_sparse_gather():
     assert torch.equal(live.bool(), want)
     assert 0 < int(want.sum()) < M // 5
     dense = ops.agg_gather_raw(gph, C.CB_BY_SRC, G)
-    sparse = ops.agg_gather_raw(gph, C.CB_BY_SRC, G, live=live)
-    assert torch.equal(dense, sparse)
+    sparse = ops.agg_gather_raw(gph, C.CB_BY_SRC, G, live=live)                      # compacted live columns
+    walked = ops.agg_gather_raw(gph, C.CB_BY_SRC, G, live=live, flag_walk=True)      # full walk, flag per column
+    assert torch.equal(dense, sparse) and torch.equal(dense, walked)
     # flags that wrongly kill a live row change the result (the kernel really skips)
     wrong = live.clone()
     wrong[int(want.nonzero()[0])] = 0
     assert not torch.equal(ops.agg_gather_raw(gph, C.CB_BY_SRC, G, live=wrong), dense)
+    assert not torch.equal(ops.agg_gather_raw(gph, C.CB_BY_SRC, G, live=wrong, flag_walk=True), dense)
+
+
+@pytest.mark.parametrize('d,frac,dtype', [(256, 0.1, torch.float32), (64, 0.5, torch.float32), (12, 0.02, torch.float32),
+                                          (128, 0.1, torch.bfloat16), (256, 0.0, torch.float32),
+                                          (256, 1.0, torch.float32)])
+def test_compacted_gather_bit_identical_incl_hub_rows(d, frac, dtype):
+    """cb_graph_compact_live + cb_agg_gather_compacted against the dense gather of a row-sparse matrix, on a graph
+    with hub rows (chunked sums keep their association), both CSR sides, and the compacted lists themselves
+    against a torch restatement (bit-exact indexing)."""
+    from gnn_tail_generalization_b200 import _cabi as C, graph as Gm
+    from oracle import coldbrew_oracle as O
+    ops = _ops()
+    n = 20011
+    ei = O.powerlaw_graph(n, 150000, seed=5).to('cuda')
+    gph = Gm.GraphHandle(ei, n, hub_chunk=64)
+    assert min(gph.num_hub_chunks) > 0
+    g = torch.Generator(device='cuda').manual_seed(5)
+    live = (torch.rand(n, device='cuda', generator=g) < frac).to(torch.uint8)
+    X = (torch.randn(n, d, device='cuda', generator=g) * live[:, None]).to(dtype)
+    for side in (C.CB_BY_SRC, C.CB_BY_DST):
+        dense = ops.agg_gather_raw(gph, side, X, row_scale=gph.din_inv_sqrt)
+        assert torch.equal(dense, ops.agg_gather_raw(gph, side, X, row_scale=gph.din_inv_sqrt, live=live))
+        # the compacted structure
+        ws = ops.compact_live_raw(gph, side, live)
+        rowptr, col, _ = gph.csr(side)
+        keep = live[col.long()].bool()
+        want_col = col[keep]
+        csum = torch.cat([torch.zeros(1, dtype=torch.int64, device='cuda'), keep.long().cumsum(0)])
+        want_rowptr = csum[rowptr]
+        got_rowptr = ws[:(n + 1) * 8].view(torch.int64)
+        assert torch.equal(got_rowptr, want_rowptr)
+        al = lambda b: (b + 255) // 256 * 256
+        nch = gph.num_hub_chunks[0 if side == C.CB_BY_DST else 1]
+        off = al((n + 1) * 8) + 2 * al((nch + 1) * 8)
+        got_col = ws[off:off + 4 * int(want_col.numel())].view(torch.int32)
+        assert torch.equal(got_col, want_col)

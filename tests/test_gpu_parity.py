@@ -337,16 +337,30 @@ def test_config_shapes_match_oracle(cfg):
     got = res.emb4classi_full.detach().cpu()
     assert float((got - want).abs().max()) <= LOGIT_TOL
     assert float(lg) == pytest.approx(float(lr), rel=1e-5)
-    rg = dict(ref.named_parameters())
+    # Gradients are judged against the SAME oracle run in fp64 (every config here has <= 2e5 rows): the fp32 CPU
+    # oracle is itself up to ~1e-3 of the largest entry away from fp64 on the weight gradients (fp32 reductions
+    # over up to 1.7e5 rows with heavy cancellation), so it cannot referee a 1e-4 bar.
+    ref64 = O.OracleTeacherGNN(O.make_args(**kw), None)
+    ref64.load_state_dict(ref.state_dict(), strict=True)
+    ref64.double().train()
+    l64 = O.teacher_loss(ref64, x.double(), ei, y, mask, 0.5)
+    l64.backward()
+    assert float(lg) == pytest.approx(float(l64), rel=2e-6)
+    rg, rg64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
+    worst = {}
     for k, p in model.named_parameters():
-        if rg[k].grad is None:
+        if rg64[k].grad is None:
             assert p.grad is None, k
             continue
-        scale = max(1e-6, float(rg[k].grad.abs().max()))
-        # fp32 reductions over up to 1.7e5 rows in a different order and with heavy cancellation (a few train /
-        # hub rows dominate): cuBLAS vs MKL already differ by ~1e-3 of the largest entry; the tensor-core
-        # accumulator truncates, which adds a bias of ~3e-8 per accumulation (<= 384 per chain)
-        assert float((p.grad.cpu() - rg[k].grad).abs().max()) <= 1e-2 * scale + 1e-7, k
+        scale = max(1e-6, float(rg64[k].grad.abs().max()))
+        ours = float((p.grad.cpu().double() - rg64[k].grad).abs().max()) / scale
+        cpu32 = float((rg[k].grad.double() - rg64[k].grad).abs().max()) / scale
+        worst[k] = (ours, cpu32)
+        # bar: 1e-4 of the largest entry (the logit bar of north_star carried over to the gradients); the 3xTF32
+        # tensor-core chains (truncating accumulator, <= 384 accumulations) stay an order of magnitude below it
+        assert ours <= 1e-4 + 1e-7 / scale, (k, ours, cpu32)
+    print(cfg, 'max grad error / largest entry (ours vs fp64, fp32 CPU oracle vs fp64):',
+          {k.split('model.model.')[-1]: (f'{a:.1e}', f'{b:.1e}') for k, (a, b) in worst.items()})
 
 
 def test_zero_in_degree_raises_dglerror():

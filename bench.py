@@ -36,12 +36,19 @@ def parse():
     p.add_argument('--steps', type=int, default=10)
     p.add_argument('--warmup', type=int, default=3)
     p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    p.add_argument('--nodes', type=int, default=10_000_000)
-    p.add_argument('--edges', type=int, default=100_000_000, help='directed edges incl. one self loop per node')
-    p.add_argument('--dim', type=int, default=256)
+    p.add_argument('--config', default='cfg4', choices=['cfg4', 'cfg5'],
+                   help='cfg4 = BASELINE.json configs[3] (10M nodes / 100M edges / 256-dim fp32, 2 layers, the metric\'s '
+                        'config; N>1 slices the same graph: strong scaling).  cfg5 = configs[4] (50M nodes / 1B edges / '
+                        '128-dim bf16, 3-layer GCN + SE on every layer, 8 GPUs; generated shard by shard, 6.25M nodes / '
+                        '125M edges per GPU: weak scaling when run on fewer GPUs)')
+    p.add_argument('--nodes', type=int, default=0, help='0 = the config\'s size')
+    p.add_argument('--edges', type=int, default=0, help='directed edges incl. one self loop per node; 0 = the config\'s')
+    p.add_argument('--dim', type=int, default=0)
     p.add_argument('--classes', type=int, default=64)
-    p.add_argument('--layers', type=int, default=2)
-    p.add_argument('--se', default='000', help='whetherHasSE flags (BASELINE configs[3] has no SE)')
+    p.add_argument('--layers', type=int, default=0)
+    p.add_argument('--se', default='', help='whetherHasSE flags (configs[3] has no SE; configs[4]: 010 = every layer '
+                                            'of the Initial topology)')
+    p.add_argument('--se-reg', type=float, default=0.5, help='coefficient of the SE regulariser in the loss')
     p.add_argument('--exchange', default='push', choices=['push', 'nccl'],
                    help='N>1: rows pushed to the peers from the producing GEMM epilogue (default) or NCCL all-gather')
     p.add_argument('--panels', type=int, default=0,
@@ -56,11 +63,21 @@ def parse():
                    help='TeacherGNN dropout (reference defaults are 0.2-0.6, base_options.py:20,190-220); > 0 takes the '
                         'layers off the pre-scaled hand-off, reported as a second line under profiles/')
     p.add_argument('--profile', default='', help='write a torch.profiler kernel table of 2 steps to this file')
-    return p.parse_args()
+    a = p.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1')) if a.impl == 'ours' else max(1, a.gpus)
+    if a.config == 'cfg5':
+        per_gpu_nodes, per_gpu_edges = 6_250_000, 125_000_000
+        a.nodes = a.nodes or per_gpu_nodes * world
+        a.edges = a.edges or per_gpu_edges * world
+        a.dim, a.layers, a.se, a.storage = a.dim or 128, a.layers or 3, a.se or '010', 'bf16'
+    else:
+        a.nodes, a.edges = a.nodes or 10_000_000, a.edges or 100_000_000
+        a.dim, a.layers, a.se, a.storage = a.dim or 256, a.layers or 2, a.se or '000', 'fp32'
+    return a
 
 
 def workload_name(a):
-    return (f'synthetic power-law (gamma=2.5) N={a.nodes} E={a.edges} d={a.dim} fp32, {a.layers}-layer GCN '
+    return (f'synthetic power-law (gamma=2.5) N={a.nodes} E={a.edges} d={a.dim} {a.storage}, {a.layers}-layer GCN '
             f'(Initial topology, C={a.classes}, SE={a.se}' + (f', dropout={a.dropout}' if a.dropout else '') +
             '), fwd+bwd+Adam')
 
@@ -221,18 +238,32 @@ def run_ours(a):
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_kind = 'measured' if 'hbm_gbs' in peaks else 'fallback'
 
-    # ---- workload (generated on the device, identical on every rank) ---------------------------
+    # ---- workload (generated on the device) ------------------------------------------------------
     N, d, L = a.nodes, a.dim, a.layers
+    bf16 = a.storage == 'bf16'
+    st_dtype = torch.bfloat16 if bf16 else torch.float32
+    es = 2 if bf16 else 4
     und = max(1, (a.edges - N) // 2)
-    ei = synth.powerlaw_graph(N, und, seed=0, device=dev)
-    E = ei.shape[1]
-    graph = cbdist.SlicedGraph(ei, N, rank, world)
+    if a.config == 'cfg5':
+        # configs[4]: every rank generates and keeps only its own in-edges (the 10^9-edge list never exists) and
+        # builds its slice from them (cb_graph_create_local); the out-edges of a symmetric graph are the same list
+        # with its rows swapped
+        ei = synth.powerlaw_graph_sharded(N, und, rank, world, seed=0, device=dev)
+        e_cnt = torch.tensor([ei.shape[1]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(e_cnt)
+        E = int(e_cnt)
+        graph = cbdist.SlicedGraph(ei, N, rank, world, local_out_edges=ei.flip(0))
+    else:
+        ei = synth.powerlaw_graph(N, und, seed=0, device=dev)          # identical on every rank, sliced by the build
+        E = ei.shape[1]
+        graph = cbdist.SlicedGraph(ei, N, rank, world)
     del ei
     if a.panels <= 0:
         a.panels = 4 if world >= 8 else 1
     if world > 1 and a.exchange == 'push':
         try:
-            graph.enable_push(d, a.panels, a.push_ctas)
+            graph.enable_push(d, a.panels, a.push_ctas, elem_bytes=es)
         except RuntimeError as e:   # raised on every rank together (PeerExchange); reported in config.parallelism
             if rank == 0:
                 print(f'bench: {e}; using the NCCL all-gather exchange', file=sys.stderr, flush=True)
@@ -240,16 +271,33 @@ def run_ours(a):
     torch.cuda.empty_cache()
     lo, hi = graph.row_begin, graph.row_end
     rows = hi - lo
-    x = synth.features(N, d, seed=1, device=dev)[lo:hi].clone() if world > 1 else synth.features(N, d, 1, dev)
-    y = synth.labels(N, a.classes, seed=2, device=dev)[lo:hi]
+    if a.config == 'cfg5':
+        x = synth.features(rows, d, seed=1000 + rank, device=dev).to(st_dtype)      # this rank's rows only
+        y = synth.labels(rows, a.classes, seed=2000 + rank, device=dev)
+    else:
+        x = synth.features(N, d, seed=1, device=dev)[lo:hi].clone() if world > 1 else synth.features(N, d, 1, dev)
+        y = synth.labels(N, a.classes, seed=2, device=dev)[lo:hi]
+        x = x.to(st_dtype)
     n_train = N // 10
-    idx = torch.arange(max(0, min(n_train, hi) - lo), device=dev)       # train rows = first 10% of the nodes
+    if a.config == 'cfg5':
+        idx = torch.arange(rows // 10, device=dev)                      # train rows = first 10% of every rank's rows
+    else:
+        idx = torch.arange(max(0, min(n_train, hi) - lo), device=dev)   # train rows = first 10% of the nodes
     torch.manual_seed(3)
-    model = TeacherGNN(model_args(a, rows, str(dev)), None).to(dev)     # same seed => same dense weights on all ranks
+    model = TeacherGNN(model_args(a, rows, str(dev)), None).to(dev)     # SE tables: this rank's rows (row-sharded)
+    cbdist.broadcast_dense_params(model, world)     # the SE tables consume RNG: make the replicated weights equal
     cbdist.attach_graph(model, graph)
     model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    se_coef = 0.5
+    se_coef = a.se_reg
+    se_opt = None
+    if any(c == '1' for c in a.se):
+        # SE tables + Adam moments are the largest thing in HBM: one fused pass per table (cb_se_adam_step) instead
+        # of autograd's norm backward + torch.optim.Adam's passes; bf16 forward reads a bf16 shadow of the fp32 master
+        from gnn_tail_generalization_b200 import se_optim
+        se_opt = se_optim.FusedSEAdam(model, lr=1e-3, se_reg=se_coef, shadow_dtype=torch.bfloat16 if bf16 else None)
+        opt = torch.optim.Adam(se_opt.other_parameters(), lr=1e-3)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 
     def barrier():
         if world > 1:
@@ -290,13 +338,14 @@ def run_ours(a):
     def step(x=x):
         opt.zero_grad(set_to_none=True)
         res = model.get_3_embs(x, None, idx)
-        loss = F.nll_loss(F.log_softmax(res.emb4classi, 1), y[idx], reduction='sum') / n_train
-        if model.se_reg_all is not None:
-            loss = loss + se_coef * model.se_reg_all
+        nll = F.nll_loss(F.log_softmax(res.emb4classi.float(), 1), y[idx], reduction='sum') / n_train
+        loss = nll if model.se_reg_all is None else nll + se_coef * model.se_reg_all
         loss.backward()
         cbdist.allreduce_dense_grads(model, world)
         opt.step()
-        last['nll'] = loss.detach() if model.se_reg_all is None else (loss.detach() - se_coef * model.se_reg_all.detach())
+        if se_opt is not None:
+            se_opt.step()
+        last['nll'] = nll.detach()
         return loss
 
     for _ in range(max(3, a.warmup)):
@@ -342,15 +391,16 @@ def run_ours(a):
         if r['flops']:
             # 3 TF32 tensor-core products per fp32 product: flops counts the MMA work actually issued
             kernels[name]['tensor_tflops_tf32'] = round(r['flops'] / r['launches'] / (avg_ms * 1e-3) / 1e12, 1)
-    dom = kernels.get('agg_forward', {})
-    roofline = {'bound': 'hbm', 'kernel': 'k_agg (cb_agg_forward)', 'achieved': dom.get('achieved_gbs'),
+    dom = kernels.get('agg_forward_bf16' if bf16 else 'agg_forward', {})
+    roofline = {'bound': 'hbm', 'kernel': 'k_agg (cb_agg_forward_bf16)' if bf16 else 'k_agg (cb_agg_forward)', 'achieved': dom.get('achieved_gbs'),
                 'peak': hbm_peak, 'peak_source': f'{peak_kind} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)',
                 'unit': 'GB/s', 'frac': dom.get('frac'), 'traffic': None,
                 'avg_launch_ms': dom.get('avg_ms'), 'alg_bytes_per_launch': dom.get('alg_bytes')}
     try:
         tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
-        roofline['traffic'] = tr.get('k_agg_forward_dram_bytes_per_launch')
-        roofline['traffic_source'] = tr.get('source')
+        if a.config == 'cfg4' and world == 1:      # the capture is of this kernel at this size
+            roofline['traffic'] = tr.get('k_agg_forward_dram_bytes_per_launch')
+            roofline['traffic_source'] = tr.get('source')
     except Exception:
         pass
 
@@ -360,7 +410,7 @@ def run_ours(a):
     # step i computes; the first copy of the timed region is fully exposed.
     e2e = None
     if not a.no_e2e:
-        x_host = torch.empty((rows, d), dtype=torch.float32, pin_memory=True)
+        x_host = torch.empty((rows, d), dtype=st_dtype, pin_memory=True)
         x_host.copy_(x)
         result = torch.zeros(1, dtype=torch.float32, pin_memory=True)
         bufs = [x, torch.empty_like(x)]
@@ -400,7 +450,7 @@ def run_ours(a):
         e2e_region(2)
         e2e_steps = max(2, a.steps)
         ms_e2e = e2e_region(e2e_steps)
-        e2e = {'value': 2 * L * E / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': rows * d * 4 * world,
+        e2e = {'value': 2 * L * E / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': rows * d * es * world,
                'd2h_bytes_per_step': 4 * world, 'ms_per_step': ms_e2e, 'steps': e2e_steps,
                'h2d_copies_in_region': e2e_steps,
                'what': 'features copied from pinned host memory every step (double-buffered, the copy of step '
@@ -416,13 +466,17 @@ def run_ours(a):
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps,
-                'warmup': max(3, a.warmup), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
-                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'warmup': max(3, a.warmup), 'ms_per_step': ms_step, 'higher_is_better': True,
+                'scaling': 'weak' if a.config == 'cfg5' else 'strong',
+                'vs_baseline': None, 'dtype': 'bf16' if bf16 else 'f32', 'data': 'synthetic',
                 'config': {'workload': workload_name(a), 'edges': E, 'edges_aggregated_per_step': 2 * L * E,
-                           'l2': 'inputs exceed L2 (feature matrix %.1f GB vs 126 MB)' % (N * d * 4 / 1e9),
+                           'l2': 'inputs exceed L2 (feature matrix %.1f GB vs 126 MB)' % (N * d * es / 1e9),
                            'parallelism': (f'node-slice x{world}, exchange={a.exchange}, panels={a.panels}' if world > 1
                                            else 'single GPU'),
-                           'gemm': 'tcgen05 3xTF32 split (fp32-class accuracy), fp32 accumulate in TMEM'},
+                           'gemm': ('tcgen05 kind::f16 on bf16 operands as stored, fp32 accumulate in TMEM' if bf16 else
+                                    'tcgen05 3xTF32 split (fp32-class accuracy), fp32 accumulate in TMEM'),
+                           'se_optimizer': ('cb_se_adam_step (fused Adam + ||E|| gradient' +
+                                            (', fp32 master + bf16 shadow' if bf16 else '') + ')') if se_opt else None},
                 'roofline': roofline, 'roofline_kernels': kernels, 'cpu_baseline': cpu, 'e2e': e2e,
                 'clocks': clk.summary(), 'gpu_launches': launches,
                 'parity': {'logits_checksum_initial_weights': logits_checksum,

@@ -58,6 +58,7 @@ class GCNConv(nn.Module):
         self.reset_parameters()
         self._activation = activation
         self.whetherHasSE = whetherHasSE
+        self.se_fused = None       # set by se_optim.FusedSEAdam: the table is then stepped by cb_se_adam_step
         if whetherHasSE:
             self.le = nn.Parameter(th.randn(args.N_nodes, self._out_feats), requires_grad=True)
 
@@ -89,14 +90,24 @@ class GCNConv(nn.Module):
         """row_scale * (X W) + E  ( = (D_out^-1/2 X) W + E, GCN.py:205-231) and the SE regulariser
         (GCN.py:232-236).  One tcgen05 GEMM with the scale and the SE add in its epilogue."""
         le = self.le if self.whetherHasSE else None
+        fused = getattr(self, 'se_fused', None) if self.whetherHasSE else None   # se_optim.FusedSEAdam owns the table
+        add_sink = None
+        if fused is not None:
+            le, add_sink = fused.operand(feat.dtype), fused.slot
+        elif le is not None and le.dtype != feat.dtype:
+            le = le.to(feat.dtype)      # bf16 forward without the fused optimizer: an autograd cast per call
         if weight is not None:
             h, _ = _ops.dense(feat, weight, 'kn', add=le, row_scale=row_scale, dx_sink=dx_sink, dx_plan=dx_plan,
-                              push_graph=graph)
+                              push_graph=graph, add_sink=add_sink)
         else:
+            if fused is not None:
+                raise DGLError('the fused SE optimizer needs the layer to own its weight')
             h = feat if row_scale is None else _ops.row_scale(feat, row_scale)
             if le is not None:
                 h = h + le
-        return h, (_ops.frob_norm(self.le, graph) if self.whetherHasSE else None)
+        if not self.whetherHasSE:
+            return h, None
+        return h, (fused.norm(graph) if fused is not None else _ops.frob_norm(self.le, graph))
 
     def fused(self, graph, feat, prescaled=False, relu=False, x0=None, alpha=0.0, want_out=True,
               want_scaled=False, weight=None, x0_sink=None, dx_sink=None, my_plan=None, dx_plan=None):

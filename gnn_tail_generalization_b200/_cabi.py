@@ -39,6 +39,7 @@ SYMBOLS = {
     'cb_abi_version': (_int, []),
     'cb_graph_create': (_int, [_vp, _i64, _i64, _int, _vp, ctypes.POINTER(_vp)]),
     'cb_graph_create_sliced': (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp, ctypes.POINTER(_vp)]),
+    'cb_graph_create_local': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _vp, ctypes.POINTER(_vp)]),
     'cb_graph_destroy': (_int, [_vp]),
     'cb_graph_query': (_int, [_vp, _int, _vp]),
     'cb_graph_workspace_bytes': (_i64, [_vp, _int, _i64]),
@@ -52,6 +53,10 @@ SYMBOLS = {
     'cb_prep_workspace_bytes': (_i64, [_i64, _i64]),
     'cb_agg_backward_prep': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _dbl, _vp, _vp, _vp, _int, _vp,
                                     _i64, _vp]),
+    'cb_agg_backward_prep_bf16': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _dbl, _vp, _vp, _vp, _int, _vp,
+                                         _i64, _vp]),
+    'cb_se_adam_step': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _i64, _vp, _dbl, _vp]),
+    'cb_to_bf16': (_int, [_vp, _i64, _vp, _vp]),
     'cb_row_scale': (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     'cb_sumsq_workspace_bytes': (_i64, []),
     'cb_sumsq': (_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
@@ -69,6 +74,15 @@ SYMBOLS = {
     'cb_gemm_tn_supported': (_int, [_i64, _i64, _i64]),
     'cb_gemm_tn_workspace_bytes': (_i64, [_i64, _i64, _i64]),
     'cb_gemm_tn': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp, _i64, _vp, _i64, _vp]),
+    'cb_gemm_weight_to_bf16': (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
+    'cb_gemm_rows_supported_bf16': (_int, [_i64, _i64, _i64]),
+    'cb_gemm_rows_bf16': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _int, _vp, _i64, _vp, _vp, _i64,
+                                 _vp, _vp]),
+    'cb_gemm_rows_grad_bf16': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _int, _dbl,
+                                      _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'cb_gemm_tn_supported_bf16': (_int, [_i64, _i64, _i64]),
+    'cb_gemm_tn_workspace_bytes_bf16': (_i64, [_i64, _i64, _i64]),
+    'cb_gemm_tn_bf16': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
     'cb_launch_count': (_i64, []),
 }
 

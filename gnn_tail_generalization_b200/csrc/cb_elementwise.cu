@@ -3,6 +3,9 @@
 //   cb_sumsq              GCN.py:232       th.norm(self.le)                 (sum of squares; sqrt on the caller side)
 //   cb_agg_backward_prep  autograd of GCN.py:242-253, 127-128 and res_tricks.py:14/23
 // plus the library-wide bookkeeping (error text, launch counter).
+#include <cuda_bf16.h>
+#include <math.h>
+
 #include "cb_internal.cuh"
 
 namespace cb {
@@ -108,17 +111,53 @@ __global__ void __launch_bounds__(256) k_sumsq_final(const float* __restrict__ p
 // ---------------------------------------------------------------------------------------------
 // backward prologue
 // ---------------------------------------------------------------------------------------------
+// element access in the storage type S of the streamed matrices (fp32, or bf16 widened on load / rounded on store)
+template <typename S, int VEC>
+struct PIo;
+template <>
+struct PIo<float, 4> {
+    static __device__ __forceinline__ void ld(float (&v)[4], const float* p) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <>
+struct PIo<float, 1> {
+    static __device__ __forceinline__ void ld(float (&v)[1], const float* p) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[1]) { *p = v[0]; }
+};
+template <>
+struct PIo<__nv_bfloat16, 4> {
+    static __device__ __forceinline__ void ld(float (&v)[4], const __nv_bfloat16* p) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+        v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+        v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[4]) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+};
+template <>
+struct PIo<__nv_bfloat16, 1> {
+    static __device__ __forceinline__ void ld(float (&v)[1], const __nv_bfloat16* p) { v[0] = __bfloat162float(*p); }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[1]) { *p = __float2bfloat16_rn(v[0]); }
+};
+
 struct PrepArgs {
-    const float* d_out;
-    const float* d_out2;
+    const void* d_out;     // storage type S
+    const void* d_out2;    // S
     const float* s2;       // dout^-1/2 (scale of d_out2)
     const float* rs;       // din^-1/2
     const uint8_t* mask;
-    const float* relu_out;
+    const void* relu_out;  // S
     int act, mixed;
     float alpha, one_minus_alpha;
-    float* G;
-    float* d_x0;
+    void* G;               // S
+    void* d_x0;            // S
     int accumulate_x0;
     float* bias_partial;   // [gridDim.x, d] or null
     int64_t rows, d;
@@ -128,8 +167,14 @@ struct PrepArgs {
 // Block layout: CU = min(units, 256) column slots side by side, RL = 256 / CU row lanes.  Every thread
 // keeps a running bias-gradient sum for its column slot over the rows it visits; the row lanes of a
 // block are then added in lane order, giving one partial row per block.
-template <int VEC>
+template <typename S, int VEC>
 __global__ void __launch_bounds__(256) k_prep(const PrepArgs a) {
+    using IO = PIo<S, VEC>;
+    const S* p_out = reinterpret_cast<const S*>(a.d_out);
+    const S* p_out2 = reinterpret_cast<const S*>(a.d_out2);
+    const S* p_relu = reinterpret_cast<const S*>(a.relu_out);
+    S* p_G = reinterpret_cast<S*>(a.G);
+    S* p_x0 = reinterpret_cast<S*>(a.d_x0);
     extern __shared__ float sm[];  // [RL][CU*VEC] when bias partials are wanted
     const int64_t units = (a.d + VEC - 1) / VEC;
     const int cu = (int)(units < 256 ? units : 256);
@@ -152,33 +197,24 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs a) {
                 float dt[VEC];
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) dt[i] = 0.f;
-                if (a.d_out) {
-                    if (VEC == 4) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(a.d_out + off));
-                        dt[0] = v.x; dt[1 % VEC] = v.y; dt[2 % VEC] = v.z; dt[3 % VEC] = v.w;
-                    } else {
-                        dt[0] = __ldg(a.d_out + off);
-                    }
-                }
+                if (a.d_out) IO::ld(dt, p_out + off);
                 if (a.d_out2) {
                     const float s2 = __ldg(a.s2 + r);
-                    if (VEC == 4) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(a.d_out2 + off));
-                        const float t[4] = {v.x, v.y, v.z, v.w};
+                    float t[VEC];
+                    IO::ld(t, p_out2 + off);
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i)
-                            dt[i] = a.d_out ? __fadd_rn(dt[i], __fmul_rn(s2, t[i])) : __fmul_rn(s2, t[i]);
-                    } else {
-                        const float t = __ldg(a.d_out2 + off);
-                        dt[0] = a.d_out ? __fadd_rn(dt[0], __fmul_rn(s2, t)) : __fmul_rn(s2, t);
-                    }
+                    for (int i = 0; i < VEC; ++i)
+                        dt[i] = a.d_out ? __fadd_rn(dt[i], __fmul_rn(s2, t[i])) : __fmul_rn(s2, t[i]);
                 }
                 if (a.d_x0) {
+                    float old_[VEC], g0[VEC];
+                    if (a.accumulate_x0) IO::ld(old_, p_x0 + off);
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
-                        const float g0 = __fmul_rn(a.alpha, dt[i]);
-                        a.d_x0[off + i] = a.accumulate_x0 ? __fadd_rn(a.d_x0[off + i], g0) : g0;
+                        g0[i] = __fmul_rn(a.alpha, dt[i]);
+                        if (a.accumulate_x0) g0[i] = __fadd_rn(old_[i], g0[i]);
                     }
+                    IO::st(p_x0 + off, g0);
                 }
                 bool m[VEC];
 #pragma unroll
@@ -192,8 +228,10 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs a) {
                             m[0] = a.mask[off] != 0;
                         }
                     } else {
+                        float ro[VEC];
+                        IO::ld(ro, p_relu + off);
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) m[i] = __ldg(a.relu_out + off + i) > 0.f;
+                        for (int i = 0; i < VEC; ++i) m[i] = ro[i] > 0.f;
                     }
                 }
                 const float rs = __ldg(a.rs + r);
@@ -205,11 +243,7 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs a) {
                     bsum[i] += dz;
                     g[i] = __fmul_rn(rs, dz);
                 }
-                if (VEC == 4) {
-                    *reinterpret_cast<float4*>(a.G + off) = make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]);
-                } else {
-                    a.G[off] = g[0];
-                }
+                IO::st(p_G + off, g);
             }
         }
         if (a.bias_partial) {
@@ -239,6 +273,85 @@ __global__ void __launch_bounds__(256) k_bias_final(const float* __restrict__ pa
     float t = 0.f;
     for (int b = 0; b < nblocks; ++b) t += partial[(int64_t)b * d + c];
     d_bias[c] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Structural-Embedding optimizer step: Adam + weight decay + the ||E||_F regulariser's gradient, one pass
+// ---------------------------------------------------------------------------------------------
+struct SeAdamArgs {
+    float* E;              // [n] fp32 master of GCNConv.le
+    const void* grad;      // [n] dL/dh of the layer's transform (= dL/dE of the additive term), fp32 or bf16, or null
+    float* m;
+    float* v;
+    __nv_bfloat16* shadow; // [n] bf16 copy the forward pass reads, or null
+    int64_t n;
+    float one_minus_b1, b2, one_minus_b2, eps, wd, step_size, inv_bc2_sqrt;
+    const float* sumsq;    // device scalar sum(E^2) over every rank's rows (this step's forward), or null
+    float reg_coef;        // se_reg coefficient of the loss
+};
+
+template <typename GS>
+__global__ void __launch_bounds__(256) k_se_adam(const SeAdamArgs a) {
+    // d/dE [ coef * ||E||_F ] = coef * E / ||E||_F  (0 at E = 0, like torch.norm's subgradient)
+    float reg = 0.f;
+    if (a.sumsq) {
+        const float ss = __ldg(a.sumsq);
+        reg = ss > 0.f ? a.reg_coef / sqrtf(ss) : 0.f;
+    }
+    const int64_t n4 = a.n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const GS* gp = reinterpret_cast<const GS*>(a.grad);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float e[4], g[4], m[4], v[4];
+        PIo<float, 4>::ld(e, a.E + 4 * i);
+        PIo<float, 4>::ld(m, a.m + 4 * i);
+        PIo<float, 4>::ld(v, a.v + 4 * i);
+        if (gp) PIo<GS, 4>::ld(g, gp + 4 * i);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float gr = gp ? g[k] : 0.f;
+            gr = fmaf(reg, e[k], gr);
+            gr = fmaf(a.wd, e[k], gr);                                   // grad.add(param, alpha=weight_decay)
+            m[k] = fmaf(a.one_minus_b1, gr - m[k], m[k]);                // exp_avg.lerp_(grad, 1 - beta1)
+            v[k] = fmaf(a.one_minus_b2 * gr, gr, a.b2 * v[k]);           // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+            const float denom = sqrtf(v[k]) * a.inv_bc2_sqrt + a.eps;
+            e[k] = e[k] - a.step_size * (m[k] / denom);                  // param.addcdiv_(exp_avg, denom, -step_size)
+        }
+        PIo<float, 4>::st(a.E + 4 * i, e);
+        PIo<float, 4>::st(a.m + 4 * i, m);
+        PIo<float, 4>::st(a.v + 4 * i, v);
+        if (a.shadow) PIo<__nv_bfloat16, 4>::st(a.shadow + 4 * i, e);
+    }
+    // tail (n not a multiple of 4)
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        float gr = 0.f;
+        if (gp) {
+            float t[1];
+            PIo<GS, 1>::ld(t, gp + i);
+            gr = t[0];
+        }
+        const float e = a.E[i];
+        gr = fmaf(reg, e, gr);
+        gr = fmaf(a.wd, e, gr);
+        const float m = fmaf(a.one_minus_b1, gr - a.m[i], a.m[i]);
+        const float v = fmaf(a.one_minus_b2 * gr, gr, a.b2 * a.v[i]);
+        const float en = e - a.step_size * (m / (sqrtf(v) * a.inv_bc2_sqrt + a.eps));
+        a.E[i] = en; a.m[i] = m; a.v[i] = v;
+        if (a.shadow) a.shadow[i] = __float2bfloat16_rn(en);
+    }
+}
+
+// fp32 -> bf16 copy (initialises the shadow table)
+__global__ void __launch_bounds__(256) k_to_bf16(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float t[4];
+        PIo<float, 4>::ld(t, x + 4 * i);
+        PIo<__nv_bfloat16, 4>::st(y + 4 * i, t);
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = __float2bfloat16_rn(x[i]);
 }
 
 static int prep_blocks(int64_t rows) {
@@ -292,15 +405,63 @@ int cb_sumsq(const float* x, int64_t n, float* out, void* workspace, int64_t wor
     return CB_OK;
 }
 
+int cb_se_adam_step(float* E, const void* grad, int grad_dtype, float* m, float* v, uint16_t* shadow_bf16, int64_t n,
+                    double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                    const float* sumsq, double reg_coef, void* stream) {
+    using namespace cb;
+    CB_REQUIRE(n >= 0 && step >= 1, CB_E_INVALID, "cb_se_adam_step: bad size or step");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(E && m && v, CB_E_INVALID, "cb_se_adam_step: NULL state");
+    CB_REQUIRE(grad_dtype == CB_F32 || grad_dtype == CB_BF16, CB_E_INVALID, "cb_se_adam_step: unknown gradient dtype");
+    auto al = [](const void* p, uintptr_t msk) { return (reinterpret_cast<uintptr_t>(p) & msk) == 0; };
+    CB_REQUIRE(al(E, 15) && al(m, 15) && al(v, 15) && al(shadow_bf16, 7) && al(grad, grad_dtype == CB_BF16 ? 7 : 15),
+               CB_E_UNSUPPORTED, "cb_se_adam_step: buffers must be aligned to 4 elements");
+    SeAdamArgs a{};
+    a.E = E; a.grad = grad; a.m = m; a.v = v; a.shadow = (__nv_bfloat16*)shadow_bf16; a.n = n;
+    a.one_minus_b1 = (float)(1.0 - beta1);
+    a.b2 = (float)beta2;
+    a.one_minus_b2 = (float)(1.0 - beta2);
+    a.eps = (float)eps;
+    a.wd = (float)weight_decay;
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    a.step_size = (float)(lr / bc1);
+    a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+    a.sumsq = sumsq;
+    a.reg_coef = (float)reg_coef;
+    const int64_t want = ceil_div(ceil_div(n, 4), 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (grad_dtype == CB_BF16)
+        k_se_adam<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else
+        k_se_adam<float><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_to_bf16(const float* x, int64_t n, uint16_t* y, void* stream) {
+    using namespace cb;
+    CB_REQUIRE(n >= 0, CB_E_INVALID, "cb_to_bf16: negative size");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(x && y, CB_E_INVALID, "cb_to_bf16: NULL buffer");
+    CB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(y) & 7u) == 0,
+               CB_E_UNSUPPORTED, "cb_to_bf16: buffers must be aligned to 4 elements");
+    const int64_t want = ceil_div(ceil_div(n, 4), 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    k_to_bf16<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(x, n, (__nv_bfloat16*)y);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
 int64_t cb_prep_workspace_bytes(int64_t rows, int64_t d) {
     if (rows < 0 || d <= 0) return 0;
     return (int64_t)cb::prep_blocks(rows) * d * (int64_t)sizeof(float);
 }
 
-int cb_agg_backward_prep(const cb_graph_t* g, const float* d_out, const float* d_out_scaled, int64_t d,
-                         const uint8_t* mask, const float* relu_out, int act, int mixed, double alpha,
-                         float* G, float* d_bias, float* d_x0, int accumulate_x0, void* workspace,
-                         int64_t workspace_bytes, void* stream) {
+static int backward_prep_impl(const cb_graph_t* g, int dtype, const void* d_out, const void* d_out_scaled, int64_t d,
+                              const uint8_t* mask, const void* relu_out, int act, int mixed, double alpha,
+                              void* G, float* d_bias, void* d_x0, int accumulate_x0, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
     using namespace cb;
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_backward_prep: graph is NULL");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_backward_prep: d must be positive");
@@ -333,22 +494,43 @@ int cb_agg_backward_prep(const cb_graph_t* g, const float* d_out, const float* d
     a.d = d;
     a.rows_per_block = ceil_div(rows > 0 ? rows : 1, blocks);
     auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & m) == 0; };
-    const bool vec = d % 4 == 0 && al(d_out, 15) && al(d_out_scaled, 15) && al(G, 15) && al(d_x0, 15) &&
-                     al(relu_out, 15) && al(mask, 3);
+    const uintptr_t am = dtype == CB_BF16 ? 7 : 15;    // 4 elements per access
+    const bool vec = d % 4 == 0 && al(d_out, am) && al(d_out_scaled, am) && al(G, am) && al(d_x0, am) &&
+                     al(relu_out, am) && al(mask, 3);
     const int64_t units = vec ? d / 4 : d;
     const int cu = (int)(units < 256 ? units : 256);
     const int rl = 256 / cu;
     const size_t smem = d_bias ? (size_t)rl * cu * (vec ? 4 : 1) * sizeof(float) : 0;
-    if (vec)
-        k_prep<4><<<blocks, 256, smem, (cudaStream_t)stream>>>(a);
-    else
-        k_prep<1><<<blocks, 256, smem, (cudaStream_t)stream>>>(a);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CB_BF16) {
+        if (vec) k_prep<__nv_bfloat16, 4><<<blocks, 256, smem, st>>>(a);
+        else k_prep<__nv_bfloat16, 1><<<blocks, 256, smem, st>>>(a);
+    } else {
+        if (vec) k_prep<float, 4><<<blocks, 256, smem, st>>>(a);
+        else k_prep<float, 1><<<blocks, 256, smem, st>>>(a);
+    }
     CB_LAUNCH_CHECK();
     if (d_bias) {
         k_bias_final<<<(unsigned)ceil_div(d, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, blocks, d, d_bias);
         CB_LAUNCH_CHECK();
     }
     return CB_OK;
+}
+
+int cb_agg_backward_prep(const cb_graph_t* g, const float* d_out, const float* d_out_scaled, int64_t d,
+                         const uint8_t* mask, const float* relu_out, int act, int mixed, double alpha,
+                         float* G, float* d_bias, float* d_x0, int accumulate_x0, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+    return backward_prep_impl(g, CB_F32, d_out, d_out_scaled, d, mask, relu_out, act, mixed, alpha, G, d_bias, d_x0,
+                              accumulate_x0, workspace, workspace_bytes, stream);
+}
+
+int cb_agg_backward_prep_bf16(const cb_graph_t* g, const uint16_t* d_out, const uint16_t* d_out_scaled, int64_t d,
+                              const uint8_t* mask, const uint16_t* relu_out, int act, int mixed, double alpha,
+                              uint16_t* G, float* d_bias, uint16_t* d_x0, int accumulate_x0, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+    return backward_prep_impl(g, CB_BF16, d_out, d_out_scaled, d, mask, relu_out, act, mixed, alpha, G, d_bias, d_x0,
+                              accumulate_x0, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -32,6 +32,7 @@
 // The weight operand is re-streamed from L2 per tile (it is 2 x N x K x 4 bytes = 512 KB at 256x256); measured, that
 // is not the limiter (the kernel runs at ~78 % of the TF32 issue rate; see profiles/r01_summary_final.md).
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "cb_internal.cuh"
@@ -40,18 +41,38 @@ namespace cb {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BK = 32;     // fp32 per k-chunk = 128 bytes = one SWIZZLE_128B row
-constexpr int UMMA_K = 8;  // K of one tcgen05.mma.kind::tf32
 constexpr int THREADS = 320;
 constexpr int STG_LD = 36;  // floats per staging row (32 + 4 pad: 16-byte aligned, conflict-free)
 
-template <int BN>
+// Storage type S of the streamed matrices (A, add, gate, d_x0, out, out2): float -> 3xTF32 split operands
+// (kind::tf32), __nv_bfloat16 -> operands fed as stored (kind::f16, BASELINE.json configs[4]).  A k-chunk is
+// always one 128-byte SWIZZLE_128B row; the accumulator and the whole epilogue are fp32 either way, bf16 results
+// are rounded to nearest-even once, at the store.
+template <typename S>
+struct El;
+template <>
+struct El<float> {
+    static constexpr int BKE = 32, UK = 8;       // elements per k-chunk, K of one MMA
+    static constexpr bool SPLIT = true;
+    static constexpr uint32_t FMT = 2u;          // TF32
+    static constexpr CUtensorMapDataType TMA_T = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+};
+template <>
+struct El<__nv_bfloat16> {
+    static constexpr int BKE = 64, UK = 16;
+    static constexpr bool SPLIT = false;
+    static constexpr uint32_t FMT = 1u;          // BF16
+    static constexpr CUtensorMapDataType TMA_T = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+};
+
+template <typename S, int BN>
 struct Cfg {
-    static constexpr int STAGES = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
-    static constexpr int A_BYTES = BM * BK * 4;   // 16 KB
-    static constexpr int B_BYTES = BN * BK * 4;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
+    static constexpr bool SPLIT = El<S>::SPLIT;
+    static constexpr int STAGES = SPLIT ? (BN >= 256 ? 2 : (BN >= 128 ? 3 : 4)) : 4;
+    static constexpr int A_BYTES = BM * 128;      // 16 KB
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = SPLIT ? 2 * A_BYTES + 2 * B_BYTES : A_BYTES + B_BYTES;
+    static constexpr int TX_BYTES = SPLIT ? A_BYTES + 2 * B_BYTES : A_BYTES + B_BYTES;
     static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
     static constexpr int CS_BYTES = 4 * BN * 4;   // per-epilogue-warp column sums (gradient epilogue)
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES + STG_BYTES + CS_BYTES;
@@ -64,22 +85,22 @@ struct GemmArgs {
     int N, K;
     const float* row_scale;  // [M] or null
     const float* bias;       // [N] or null
-    const float* add;        // [M, ld_add] or null
+    const void* add;         // [M, ld_add] or null (storage type S)
     int64_t ld_add;
     int act;
-    float* out;              // [M, ld_out] or null
+    void* out;               // [M, ld_out] or null (S)
     int64_t ld_out;
     const float* out2_scale; // [M]
-    float* out2;             // [M, ld_out2] or null
+    void* out2;              // [M, ld_out2] or null (S)
     int64_t ld_out2;
     int64_t n_tiles_m;
-    // ---- gradient epilogue (k_gemm_rows<BN, true>): the backward prologue of the layer below ----
+    // ---- gradient epilogue (k_gemm_rows<S, BN, true>): the backward prologue of the layer below ----
     const uint8_t* gate_u8;   // [M, ld_gate] relu mask bytes, or null
-    const float* gate_f32;    // [M, ld_gate] relu output (gate = value > 0), or null
+    const void* gate_f32;     // [M, ld_gate] relu output in S (gate = value > 0), or null
     int64_t ld_gate;
     int mixed;                // dz = (1-alpha) * dtot when the layer output was mixed with x0
     float alpha, one_minus_alpha;
-    float* d_x0;              // [M, ld_dx0] (+)= alpha * dtot, or null
+    void* d_x0;               // [M, ld_dx0] (+)= alpha * dtot, or null (S)
     int64_t ld_dx0;
     int accumulate_x0;
     const float* post_scale;  // [M] scale of the stored value (din^-1/2), or null
@@ -151,6 +172,39 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <typename S>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (El<S>::SPLIT) umma_tf32(d_tmem, adesc, bdesc, idesc, acc);
+    else umma_f16(d_tmem, adesc, bdesc, idesc, acc);
+}
+
+// four consecutive elements of a streamed matrix <-> float4 (bf16: widened on load, rounded to nearest-even on store)
+__device__ __forceinline__ float4 bf16x4_to_f32(uint2 u) {
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+}
+__device__ __forceinline__ uint2 f32_to_bf16x4(float4 v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+__device__ __forceinline__ float4 ld4_cs(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4_cs(const __nv_bfloat16* p) { return bf16x4_to_f32(__ldcs(reinterpret_cast<const uint2*>(p))); }
+__device__ __forceinline__ float4 ld4_g(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4_g(const __nv_bfloat16* p) { return bf16x4_to_f32(__ldg(reinterpret_cast<const uint2*>(p))); }
+__device__ __forceinline__ void st4_cs(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void st4_cs(__nv_bfloat16* p, float4 v) { __stcs(reinterpret_cast<uint2*>(p), f32_to_bf16x4(v)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) { *reinterpret_cast<uint2*>(p) = f32_to_bf16x4(v); }
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -189,17 +243,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
     return d;
 }
 
-template <int BN>
-__device__ __forceinline__ constexpr uint32_t instr_desc_tf32() {
+template <typename S, int BN>
+__device__ __forceinline__ constexpr uint32_t instr_desc() {
     return (1u << 4)                 // D format  = F32
-           | (2u << 7)               // A format  = TF32
-           | (2u << 10)              // B format  = TF32
+           | (El<S>::FMT << 7)       // A format  = TF32 / BF16
+           | (El<S>::FMT << 10)      // B format
            | ((uint32_t)(BN >> 3) << 17)   // N >> 3
            | ((uint32_t)(BM >> 4) << 24);  // M >> 4   (A and B both K-major: bits 15/16 = 0)
 }
 
 // Stores the lane's 8 x float4 register tile (rows rbase + 4*itr, column col) into every peer whose bit is
 // set in need[row]: the exchange step of the node-sliced path, riding on the epilogue.
+template <typename S>
 __device__ __forceinline__ void push_to_peers(const cb_peer_push_t& ps, int64_t rbase, int col, int nval,
                                               const float4 (&v)[8]) {
     uint32_t nd[8];
@@ -209,20 +264,23 @@ __device__ __forceinline__ void push_to_peers(const cb_peer_push_t& ps, int64_t 
         if (ps.row_live && itr < nval && __ldg(ps.row_live + rbase + itr * 4) == 0) nd[itr] = 0u;
     }
     for (int j = 0; j < ps.n_peers; ++j) {
-        float* p = ps.peer[j] + (ps.row0 + rbase) * ps.ld + col;
+        S* p = reinterpret_cast<S*>(ps.peer[j]) + (ps.row0 + rbase) * ps.ld + col;
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr)
-            if ((nd[itr] >> j) & 1u) *reinterpret_cast<float4*>(p + (int64_t)itr * 4 * ps.ld) = v[itr];
+            if ((nd[itr] >> j) & 1u) st4(p + (int64_t)itr * 4 * ps.ld, v[itr]);
     }
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int BN, bool GRAD>
+template <typename S, int BN, bool GRAD>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
             const __grid_constant__ CUtensorMap map_blo, const GemmArgs g) {
-    using C = Cfg<BN>;
+    using C = Cfg<S, BN>;
     constexpr int STAGES = C::STAGES;
+    constexpr bool SPLIT = C::SPLIT;
+    constexpr int BKE = El<S>::BKE;     // elements per k-chunk (one 128-byte row)
+    constexpr int UK = El<S>::UK;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -240,14 +298,14 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     auto a_hi = [&](int s) { return smem_base + (uint32_t)s * C::STAGE_BYTES; };
     auto a_lo = [&](int s) { return smem_base + (uint32_t)s * C::STAGE_BYTES + C::A_BYTES; };
-    auto b_hi = [&](int s) { return smem_base + (uint32_t)s * C::STAGE_BYTES + 2 * C::A_BYTES; };
+    auto b_hi = [&](int s) { return smem_base + (uint32_t)s * C::STAGE_BYTES + (SPLIT ? 2 : 1) * C::A_BYTES; };
     auto b_lo = [&](int s) { return smem_base + (uint32_t)s * C::STAGE_BYTES + 2 * C::A_BYTES + C::B_BYTES; };
 
     if (warp == 0) {
         if (lane == 0) {
             tma_prefetch_desc(&map_a);
             tma_prefetch_desc(&map_bhi);
-            tma_prefetch_desc(&map_blo);
+            if (SPLIT) tma_prefetch_desc(&map_blo);
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(full_bar(s), 1);
                 mbar_init(ready_bar(s), 4);
@@ -271,7 +329,8 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const uint32_t tmem_base = *tmem_slot;
 
     const int n0 = blockIdx.y * BN;
-    const int nk = (g.K + BK - 1) / BK;
+    const int nk = (g.K + BKE - 1) / BKE;
+    constexpr int ES = (int)sizeof(S);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -281,11 +340,11 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 const int64_t r0 = tile * BM;
                 const int nr = (int)(g.M - r0 < BM ? g.M - r0 : BM);
                 const int nc = g.N - n0 < BN ? g.N - n0 : BN;
-                if (g.add) l2_prefetch_rows(g.add, 4, g.ld_add, r0, nr, n0, nc, lane);
+                if (g.add) l2_prefetch_rows(g.add, ES, g.ld_add, r0, nr, n0, nc, lane);
                 if (GRAD) {
-                    if (g.d_x0 && g.accumulate_x0) l2_prefetch_rows(g.d_x0, 4, g.ld_dx0, r0, nr, n0, nc, lane);
+                    if (g.d_x0 && g.accumulate_x0) l2_prefetch_rows(g.d_x0, ES, g.ld_dx0, r0, nr, n0, nc, lane);
                     if (g.gate_u8) l2_prefetch_rows(g.gate_u8, 1, g.ld_gate, r0, nr, n0, nc, lane);
-                    if (g.gate_f32) l2_prefetch_rows(g.gate_f32, 4, g.ld_gate, r0, nr, n0, nc, lane);
+                    if (g.gate_f32) l2_prefetch_rows(g.gate_f32, ES, g.ld_gate, r0, nr, n0, nc, lane);
                 }
             }
             for (int kc = 0; kc < nk; ++kc, ++it) {
@@ -294,16 +353,16 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 if (lane == 0) {
                     mbar_arrive_expect_tx(full_bar(s), C::TX_BYTES);
-                    tma_load_2d(a_hi(s), &map_a, full_bar(s), kc * BK, (int)(tile * BM));
-                    tma_load_2d(b_hi(s), &map_bhi, full_bar(s), kc * BK, n0);
-                    tma_load_2d(b_lo(s), &map_blo, full_bar(s), kc * BK, n0);
+                    tma_load_2d(a_hi(s), &map_a, full_bar(s), kc * BKE, (int)(tile * BM));
+                    tma_load_2d(b_hi(s), &map_bhi, full_bar(s), kc * BKE, n0);
+                    if (SPLIT) tma_load_2d(b_lo(s), &map_blo, full_bar(s), kc * BKE, n0);
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = instr_desc_tf32<BN>();
+        constexpr uint32_t idesc = instr_desc<S, BN>();
         uint32_t it = 0, tl = 0;
         for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x, ++tl) {
             const int acc = tl & 1u;
@@ -315,19 +374,27 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
                 mbar_wait(full_bar(s), ph);
-                mbar_wait(ready_bar(s), ph);
+                if (SPLIT) mbar_wait(ready_bar(s), ph);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint64_t dah = smem_desc_sw128(a_hi(s));
-                    const uint64_t dal = smem_desc_sw128(a_lo(s));
                     const uint64_t dbh = smem_desc_sw128(b_hi(s));
-                    const uint64_t dbl = smem_desc_sw128(b_lo(s));
+                    if (SPLIT) {
+                        const uint64_t dal = smem_desc_sw128(a_lo(s));
+                        const uint64_t dbl = smem_desc_sw128(b_lo(s));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // 32 bytes per k-step
-                        umma_tf32(d_tmem, dal + adv, dbh + adv, idesc, (kc | k) != 0);
-                        umma_tf32(d_tmem, dah + adv, dbl + adv, idesc, 1u);
-                        umma_tf32(d_tmem, dah + adv, dbh + adv, idesc, 1u);
+                        for (int k = 0; k < BKE / UK; ++k) {
+                            const uint64_t adv = (uint64_t)((k * UK * ES) >> 4);  // 32 bytes per k-step
+                            umma<S>(d_tmem, dal + adv, dbh + adv, idesc, (kc | k) != 0);
+                            umma<S>(d_tmem, dah + adv, dbl + adv, idesc, 1u);
+                            umma<S>(d_tmem, dah + adv, dbh + adv, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < BKE / UK; ++k) {
+                            const uint64_t adv = (uint64_t)((k * UK * ES) >> 4);  // 32 bytes per k-step
+                            umma<S>(d_tmem, dah + adv, dbh + adv, idesc, (kc | k) != 0);
+                        }
                     }
                     umma_commit(empty_bar(s));
                     if (kc == nk - 1) umma_commit(tfull_bar(acc));
@@ -336,10 +403,10 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
         }
     } else if (warp < 6) {
-        // ===== split warps: raw fp32 A chunk -> TF32 hi (in place) + lo =====
+        // ===== split warps: raw fp32 A chunk -> TF32 hi (in place) + lo  (idle for bf16 operands) =====
         const int t = threadIdx.x - 64;
         uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x) {
+        for (int64_t tile = blockIdx.x; SPLIT && tile < g.n_tiles_m; tile += gridDim.x) {
             for (int kc = 0; kc < nk; ++kc, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
@@ -413,10 +480,10 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     const bool acc_x0 = g.d_x0 && g.accumulate_x0;
                     if (g.add || acc_x0) {
                         const int64_t ld = g.add ? g.ld_add : g.ld_dx0;
-                        const float* p = (g.add ? g.add : g.d_x0) + rbase * ld + col;
+                        const S* p = reinterpret_cast<const S*>(g.add ? g.add : g.d_x0) + rbase * ld + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) av[itr] = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)itr * 4 * ld));
+                            if (itr < nval) av[itr] = ld4_cs(p + (int64_t)itr * 4 * ld);
                     }
                     if (g.gate_u8) {
                         const uint8_t* p = g.gate_u8 + rbase * g.ld_gate + col;
@@ -424,10 +491,10 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         for (int itr = 0; itr < 8; ++itr)
                             if (itr < nval) gm[itr] = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)itr * 4 * g.ld_gate));
                     } else if (g.gate_f32) {
-                        const float* p = g.gate_f32 + rbase * g.ld_gate + col;
+                        const S* p = reinterpret_cast<const S*>(g.gate_f32) + rbase * g.ld_gate + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) gy[itr] = __ldg(reinterpret_cast<const float4*>(p + (int64_t)itr * 4 * g.ld_gate));
+                            if (itr < nval) gy[itr] = ld4_g(p + (int64_t)itr * 4 * g.ld_gate);
                     }
                     if (g.row_scale) {
 #pragma unroll
@@ -459,7 +526,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         }
                     }
                     if (g.d_x0) {
-                        float* p = g.d_x0 + rbase * g.ld_dx0 + col;
+                        S* p = reinterpret_cast<S*>(g.d_x0) + rbase * g.ld_dx0 + col;
                         const float al = g.alpha;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr) {
@@ -469,7 +536,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                                 x.x = __fadd_rn(av[itr].x, x.x); x.y = __fadd_rn(av[itr].y, x.y);
                                 x.z = __fadd_rn(av[itr].z, x.z); x.w = __fadd_rn(av[itr].w, x.w);
                             }
-                            if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_dx0), x);
+                            if (itr < nval) st4_cs(p + (int64_t)itr * 4 * g.ld_dx0, x);
                         }
                     }
                     if (g.mixed) {
@@ -525,12 +592,12 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         }
                     }
                     {
-                        float* p = g.out + rbase * g.ld_out + col;
+                        S* p = reinterpret_cast<S*>(g.out) + rbase * g.ld_out + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_out), v[itr]);
+                            if (itr < nval) st4_cs(p + (int64_t)itr * 4 * g.ld_out, v[itr]);
                     }
-                    if (g.push.n_peers) push_to_peers(g.push, rbase, col, nval, v);
+                    if (g.push.n_peers) push_to_peers<S>(g.push, rbase, col, nval, v);
                     if (g.row_live) {
                         // a row's 32 columns of this slab sit in the 8 lanes with equal rsub: one ballot per row group
 #pragma unroll
@@ -554,10 +621,10 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (g.bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(g.bias + col));
                     if (g.add) {
-                        const float* p = g.add + rbase * g.ld_add + col;
+                        const S* p = reinterpret_cast<const S*>(g.add) + rbase * g.ld_add + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) av[itr] = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)itr * 4 * g.ld_add));
+                            if (itr < nval) av[itr] = ld4_cs(p + (int64_t)itr * 4 * g.ld_add);
                     }
                     if (g.row_scale) {
 #pragma unroll
@@ -603,20 +670,20 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         }
                     }
                     if (g.out) {
-                        float* p = g.out + rbase * g.ld_out + col;
+                        S* p = reinterpret_cast<S*>(g.out) + rbase * g.ld_out + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_out), v[itr]);
-                        if (g.push.n_peers) push_to_peers(g.push, rbase, col, nval, v);
+                            if (itr < nval) st4_cs(p + (int64_t)itr * 4 * g.ld_out, v[itr]);
+                        if (g.push.n_peers) push_to_peers<S>(g.push, rbase, col, nval, v);
                     }
                     if (g.out2) {
-                        float* p = g.out2 + rbase * g.ld_out2 + col;
+                        S* p = reinterpret_cast<S*>(g.out2) + rbase * g.ld_out2 + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr) {
                             const float s_ = s2v[itr];
                             const float4 w = make_float4(__fmul_rn(v[itr].x, s_), __fmul_rn(v[itr].y, s_),
                                                          __fmul_rn(v[itr].z, s_), __fmul_rn(v[itr].w, s_));
-                            if (itr < nval) __stcs(reinterpret_cast<float4*>(p + (int64_t)itr * 4 * g.ld_out2), w);
+                            if (itr < nval) st4_cs(p + (int64_t)itr * 4 * g.ld_out2, w);
                         }
                     }
                 }
@@ -692,15 +759,16 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// [rows, cols] fp32 row-major with a row pitch of ld floats; box = box_rows x 32 floats, SWIZZLE_128B
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// [rows, cols] row-major matrix of S with a row pitch of ld elements; box = box_rows x one 128-byte row, SWIZZLE_128B
+template <typename S>
+static int make_map(CUtensorMap* map, const S* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     CB_REQUIRE(fn != nullptr, CB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(S)};
+    const cuuint32_t box[2] = {(cuuint32_t)El<S>::BKE, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+    const CUresult r = fn(map, El<S>::TMA_T, 2, const_cast<S*>(base), dims, strides, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -715,25 +783,154 @@ static int64_t gemm_grid_x(int64_t n_tiles_m, int max_ctas = 0) {
     return (max_ctas > 0 && max_ctas < g) ? max_ctas : g;
 }
 
-template <int BN, bool GRAD>
+template <typename S, int BN, bool GRAD>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const GemmArgs& g,
                        cudaStream_t st) {
-    using C = Cfg<BN>;
+    using C = Cfg<S, BN>;
     // the attribute is per device (and per context): one flag per device ordinal, set under a benign race
     static std::atomic<bool> configured[64];
     int dev = 0;
     CB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        CB_CUDA(cudaFuncSetAttribute(k_gemm_rows<BN, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CB_CUDA(cudaFuncSetAttribute(k_gemm_rows<S, BN, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     dim3 grid((unsigned)gemm_grid_x(g.n_tiles_m, g.push.max_ctas), (unsigned)ceil_div(g.N, BN));
-    k_gemm_rows<BN, GRAD><<<grid, THREADS, C::SMEM_BYTES, st>>>(ma, mh, ml, g);
+    k_gemm_rows<S, BN, GRAD><<<grid, THREADS, C::SMEM_BYTES, st>>>(ma, mh, ml, g);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
 
+// fp32 weight -> bf16, optionally transposed:  dst[n, k] = src[n, k] or src[k, n]   (round to nearest even)
+__global__ void __launch_bounds__(256) k_weight_to_bf16(const float* __restrict__ W, int n_rows, int k_cols,
+                                                        int transpose, __nv_bfloat16* __restrict__ out) {
+    const int64_t total = (int64_t)n_rows * k_cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / k_cols), k = (int)(i % k_cols);
+        out[i] = __float2bfloat16_rn(transpose ? W[(int64_t)k * n_rows + n] : W[i]);
+    }
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// elements per 16 bytes: pitches and widths must be multiples of it (TMA strides, vector accesses)
+template <typename S>
+constexpr int vec16() { return 16 / (int)sizeof(S); }
+
+template <typename S>
+static int rows_supported(int64_t M, int64_t N, int64_t K) {
+    return M > 0 && N > 0 && K > 0 && N % 4 == 0 && K % vec16<S>() == 0 && M < ((int64_t)1 << 31) - 128 &&
+           N < (1 << 20) && K < (1 << 20);
+}
+
+template <typename S>
+static int gemm_rows_impl(const S* A, int64_t M, int64_t K, int64_t lda, const S* Bt_hi, const S* Bt_lo, int64_t N,
+                          const float* row_scale, const float* bias, const S* add, int64_t ld_add, int act, S* out,
+                          int64_t ld_out, const float* out2_scale, S* out2, int64_t ld_out2, const cb_peer_push_t* push,
+                          void* stream) {
+    CB_REQUIRE(!push || (push->n_peers >= 0 && push->n_peers <= CB_MAX_PEERS && (push->n_peers == 0 ||
+                         (out && push->need && push->ld >= N && push->ld % 4 == 0))), CB_E_INVALID,
+               "cb_gemm_rows: bad cb_peer_push_t");
+    CB_REQUIRE(A && Bt_hi && (Bt_lo || !El<S>::SPLIT), CB_E_INVALID, "cb_gemm_rows: NULL operand");
+    CB_REQUIRE(out || out2, CB_E_INVALID, "cb_gemm_rows: no output buffer");
+    CB_REQUIRE(!out2 || out2_scale, CB_E_INVALID, "cb_gemm_rows: out2 needs out2_scale");
+    CB_REQUIRE(act == CB_ACT_NONE || act == CB_ACT_RELU, CB_E_INVALID, "cb_gemm_rows: unknown activation");
+    CB_REQUIRE(rows_supported<S>(M, N, K), CB_E_UNSUPPORTED,
+               "cb_gemm_rows: needs N % 4 == 0, K a multiple of 16 bytes and M < 2^31");
+    CB_REQUIRE(lda >= K && lda % vec16<S>() == 0 && al16(A) && al16(Bt_hi) && al16(Bt_lo), CB_E_UNSUPPORTED,
+               "cb_gemm_rows: operands must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
+    // epilogue accesses are 4 elements wide: 16 bytes (fp32) or 8 bytes (bf16)
+    auto al4 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & (4 * sizeof(S) - 1)) == 0; };
+    CB_REQUIRE((!out || (al4(out) && ld_out % 4 == 0 && ld_out >= N)) &&
+                   (!out2 || (al4(out2) && ld_out2 % 4 == 0 && ld_out2 >= N)) &&
+                   (!add || (al4(add) && ld_add % 4 == 0 && ld_add >= N)) && (!bias || al16(bias)),
+               CB_E_UNSUPPORTED, "cb_gemm_rows: epilogue buffers must be aligned to 4 elements, pitches multiples of 4");
+    const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    CUtensorMap ma, mh, ml;
+    int rc = make_map<S>(&ma, A, M, K, lda, BM);
+    if (rc) return rc;
+    rc = make_map<S>(&mh, Bt_hi, N, K, K, bn);
+    if (rc) return rc;
+    ml = mh;
+    if (El<S>::SPLIT) {
+        rc = make_map<S>(&ml, Bt_lo, N, K, K, bn);
+        if (rc) return rc;
+    }
+    GemmArgs g{};
+    g.M = M; g.N = (int)N; g.K = (int)K;
+    g.row_scale = row_scale; g.bias = bias; g.add = add; g.ld_add = ld_add; g.act = act;
+    g.out = out; g.ld_out = ld_out; g.out2_scale = out2_scale; g.out2 = out2; g.ld_out2 = ld_out2;
+    if (push) g.push = *push;
+    g.n_tiles_m = ceil_div(M, BM);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 64) return launch_gemm<S, 64, false>(ma, mh, ml, g, st);
+    if (bn == 128) return launch_gemm<S, 128, false>(ma, mh, ml, g, st);
+    return launch_gemm<S, 256, false>(ma, mh, ml, g, st);
+}
+
+template <typename S>
+static int gemm_rows_grad_impl(const S* A, int64_t M, int64_t K, int64_t lda, const S* Bt_hi, const S* Bt_lo, int64_t N,
+                               const float* row_scale, const S* add, int64_t ld_add, const uint8_t* gate_u8,
+                               const S* gate_val, int64_t ld_gate, int mixed, double alpha, S* d_x0, int64_t ld_dx0,
+                               int accumulate_x0, const float* post_scale, S* out, int64_t ld_out, float* col_sum,
+                               uint8_t* row_live, void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push,
+                               void* stream) {
+    CB_REQUIRE(!push || (push->n_peers >= 0 && push->n_peers <= CB_MAX_PEERS && (push->n_peers == 0 ||
+                         (push->need && push->ld >= N && push->ld % 4 == 0))), CB_E_INVALID,
+               "cb_gemm_rows_grad: bad cb_peer_push_t");
+    CB_REQUIRE(A && Bt_hi && (Bt_lo || !El<S>::SPLIT) && out, CB_E_INVALID, "cb_gemm_rows_grad: NULL operand");
+    CB_REQUIRE(!(gate_u8 && gate_val), CB_E_INVALID, "cb_gemm_rows_grad: one gate at most");
+    CB_REQUIRE(!(add && d_x0 && accumulate_x0), CB_E_UNSUPPORTED,
+               "cb_gemm_rows_grad: `add` and an accumulating d_x0 cannot be combined");
+    CB_REQUIRE(rows_supported<S>(M, N, K), CB_E_UNSUPPORTED,
+               "cb_gemm_rows_grad: needs N % 4 == 0, K a multiple of 16 bytes and M < 2^31");
+    CB_REQUIRE(lda >= K && lda % vec16<S>() == 0 && al16(A) && al16(Bt_hi) && al16(Bt_lo), CB_E_UNSUPPORTED,
+               "cb_gemm_rows_grad: operands must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
+    auto al4 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & (4 * sizeof(S) - 1)) == 0; };
+    CB_REQUIRE(al4(out) && ld_out % 4 == 0 && ld_out >= N && (!add || (al4(add) && ld_add % 4 == 0 && ld_add >= N)) &&
+                   (!d_x0 || (al4(d_x0) && ld_dx0 % 4 == 0 && ld_dx0 >= N)) &&
+                   (!gate_val || (al4(gate_val) && ld_gate % 4 == 0 && ld_gate >= N)) &&
+                   (!gate_u8 || ((reinterpret_cast<uintptr_t>(gate_u8) & 3u) == 0 && ld_gate % 4 == 0 && ld_gate >= N)),
+               CB_E_UNSUPPORTED, "cb_gemm_rows_grad: epilogue buffers must be aligned, pitches multiples of 4");
+    CB_REQUIRE(!col_sum || (workspace && workspace_bytes >= cb_gemm_rows_grad_workspace_bytes(M, N)), CB_E_WORKSPACE,
+               "cb_gemm_rows_grad: workspace smaller than cb_gemm_rows_grad_workspace_bytes()");
+    const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    CUtensorMap ma, mh, ml;
+    int rc = make_map<S>(&ma, A, M, K, lda, BM);
+    if (rc) return rc;
+    rc = make_map<S>(&mh, Bt_hi, N, K, K, bn);
+    if (rc) return rc;
+    ml = mh;
+    if (El<S>::SPLIT) {
+        rc = make_map<S>(&ml, Bt_lo, N, K, K, bn);
+        if (rc) return rc;
+    }
+    GemmArgs g{};
+    g.M = M; g.N = (int)N; g.K = (int)K;
+    g.row_scale = row_scale; g.add = add; g.ld_add = ld_add;
+    g.out = out; g.ld_out = ld_out;
+    g.n_tiles_m = ceil_div(M, BM);
+    g.gate_u8 = gate_u8; g.gate_f32 = gate_val; g.ld_gate = ld_gate;
+    g.mixed = mixed; g.alpha = (float)alpha; g.one_minus_alpha = (float)(1.0 - alpha);
+    g.d_x0 = d_x0; g.ld_dx0 = ld_dx0; g.accumulate_x0 = d_x0 ? accumulate_x0 : 0;
+    g.post_scale = post_scale;
+    g.col_partial = col_sum ? (float*)workspace : nullptr;
+    g.row_live = row_live;
+    if (push) g.push = *push;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = bn == 64 ? launch_gemm<S, 64, true>(ma, mh, ml, g, st)
+                  : (bn == 128 ? launch_gemm<S, 128, true>(ma, mh, ml, g, st)
+                               : launch_gemm<S, 256, true>(ma, mh, ml, g, st));
+    if (rc) return rc;
+    if (col_sum) {
+        k_col_final<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(
+            (const float*)workspace, (int)gemm_grid_x(g.n_tiles_m, g.push.max_ctas), (int)N, col_sum);
+        CB_LAUNCH_CHECK();
+    }
+    return CB_OK;
+}
 
 // =====================================================================================================
 // Weight gradient:  C[Ka, Nb] = A[M, Ka]^T . B[M, Nb]   (reduction over the M node rows)
@@ -750,13 +947,33 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mh, const CUten
 // halves), warps 10-13 drain it to its own slot of the workspace, and k_reduce_partials adds the slots
 // in segment order in double precision (fixed association, bit-stable run to run).
 // =====================================================================================================
-constexpr int TN_BK = 16;                    // node rows per k-chunk
-constexpr int TN_GROUP_BYTES = TN_BK * 128;  // one 32-feature group of a chunk: 2 KB
-constexpr int TN_OP_BYTES = 8 * TN_GROUP_BYTES;  // up to 256 features: 16 KB per operand per chunk
-constexpr int TN_STAGE_BYTES = 4 * TN_OP_BYTES;  // A raw | B raw | A lo | B lo
-constexpr int TN_STAGES = 3;
-constexpr int TN_BAR_OFF = TN_STAGES * TN_STAGE_BYTES;
-constexpr int TN_SMEM_BYTES = TN_BAR_OFF + 256 + 1024;
+// Per storage type: fp32 operands are split hi/lo in shared memory (TF32, SWIZZLE_128B_BASE32B, 16 node rows per
+// chunk, 32 features per 128-byte group); bf16 operands are fed as stored (kind::f16, plain SWIZZLE_128B, 32 node rows
+// per chunk, 64 features per group).  Either way one operand chunk is 16 KB for 256 features.
+template <typename S>
+struct Tn;
+template <>
+struct Tn<float> {
+    static constexpr int BKR = 16, FEAT = 32, UKR = 8;    // node rows per chunk, features per group, rows per MMA
+    static constexpr int STAGES = 3, OPS = 4;             // A raw | B raw | A lo | B lo
+    static constexpr uint32_t SBO = 512, SWZ = 1;         // 4-row swizzle atoms, SWIZZLE_128B_BASE32B
+    static constexpr CUtensorMapSwizzle TMA_SWZ = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+};
+template <>
+struct Tn<__nv_bfloat16> {
+    static constexpr int BKR = 32, FEAT = 64, UKR = 16;
+    static constexpr int STAGES = 6, OPS = 2;             // A | B
+    static constexpr uint32_t SBO = 1024, SWZ = 2;        // 8-row swizzle atoms, SWIZZLE_128B
+    static constexpr CUtensorMapSwizzle TMA_SWZ = CU_TENSOR_MAP_SWIZZLE_128B;
+};
+constexpr int TN_OP_BYTES = 16384;               // up to 256 features of one chunk: 16 KB per operand
+template <typename S>
+struct TnCfg {
+    static constexpr int GROUP_BYTES = Tn<S>::BKR * 128;          // one feature group of a chunk
+    static constexpr int STAGE_BYTES = Tn<S>::OPS * TN_OP_BYTES;
+    static constexpr int BAR_OFF = Tn<S>::STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+};
 constexpr int TN_THREADS = 448;              // warp 0 TMA, warp 1 MMA, warps 2-9 split, warps 10-13 drain
 constexpr int TN_MAX_SEG_CHUNKS = 64;   // 1024 rows: 384 accumulations per chain, ~1e-5 worst-case relative bias
 
@@ -773,12 +990,14 @@ struct TnArgs {
     int64_t M;
 };
 
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+// MN-major operand: swz = 1 SWIZZLE_128B_BASE32B (the only shared-memory layout for MN-major TF32 operands),
+// swz = 2 SWIZZLE_128B (16-bit operands)
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t swz) {
     uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)(lbo >> 4) << 16;
     d |= (uint64_t)(sbo >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B: the only shared-memory layout for MN-major TF32 operands
+    d |= (uint64_t)swz << 61;
     return d;
 }
 
@@ -790,8 +1009,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+template <typename S>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TnArgs g) {
+    constexpr int TN_BK = Tn<S>::BKR;
+    constexpr int TN_STAGES = Tn<S>::STAGES;
+    constexpr int TN_GROUP_BYTES = TnCfg<S>::GROUP_BYTES;
+    constexpr int TN_STAGE_BYTES = TnCfg<S>::STAGE_BYTES;
+    constexpr int TN_BAR_OFF = TnCfg<S>::BAR_OFF;
+    constexpr bool SPLIT = El<S>::SPLIT;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -854,7 +1080,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
     } else if (warp == 1) {
         // A and B both MN-major (bits 15 / 16), N = nb
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+        const uint32_t idesc = (1u << 4) | (El<S>::FMT << 7) | (El<S>::FMT << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(g.nb >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         uint32_t it = 0, seg = 0;
         for (int64_t c = c_beg; c < c_end; ++c, ++it) {
@@ -867,23 +1093,28 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 tc_fence_after();
             }
             mbar_wait(full_bar(s), ph);
-            mbar_wait(ready_bar(s), ph);
+            if (SPLIT) mbar_wait(ready_bar(s), ph);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t st = smem_base + (uint32_t)s * TN_STAGE_BYTES;
+                constexpr uint32_t SWZ = Tn<S>::SWZ;
                 for (int h = 0; h < halves; ++h) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)(h * 256);
-                    const uint32_t a_off = (uint32_t)h * 4u * TN_GROUP_BYTES;
+                    const uint32_t a_off = (uint32_t)h * 8192u;     // 128 features further: half an operand chunk
 #pragma unroll
-                    for (int k = 0; k < TN_BK / UMMA_K; ++k) {
-                        const uint32_t koff = (uint32_t)k * 1024u;  // next group of 8 node rows
-                        const uint64_t dah = smem_desc_mn_sw128(st + a_off + koff, g.lbo, g.sbo);
-                        const uint64_t dal = smem_desc_mn_sw128(st + 2 * TN_OP_BYTES + a_off + koff, g.lbo, g.sbo);
-                        const uint64_t dbh = smem_desc_mn_sw128(st + TN_OP_BYTES + koff, g.lbo, g.sbo);
-                        const uint64_t dbl = smem_desc_mn_sw128(st + 3 * TN_OP_BYTES + koff, g.lbo, g.sbo);
-                        umma_tf32(d_tmem, dal, dbh, idesc, (pos | k) != 0);
-                        umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                        umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                    for (int k = 0; k < TN_BK / Tn<S>::UKR; ++k) {
+                        const uint32_t koff = (uint32_t)k * (uint32_t)(Tn<S>::UKR * 128);  // next node rows of one MMA
+                        const uint64_t dah = smem_desc_mn_sw128(st + a_off + koff, g.lbo, g.sbo, SWZ);
+                        const uint64_t dbh = smem_desc_mn_sw128(st + TN_OP_BYTES + koff, g.lbo, g.sbo, SWZ);
+                        if (SPLIT) {
+                            const uint64_t dal = smem_desc_mn_sw128(st + 2 * TN_OP_BYTES + a_off + koff, g.lbo, g.sbo, SWZ);
+                            const uint64_t dbl = smem_desc_mn_sw128(st + 3 * TN_OP_BYTES + koff, g.lbo, g.sbo, SWZ);
+                            umma<S>(d_tmem, dal, dbh, idesc, (pos | k) != 0);
+                            umma<S>(d_tmem, dah, dbl, idesc, 1u);
+                            umma<S>(d_tmem, dah, dbh, idesc, 1u);
+                        } else {
+                            umma<S>(d_tmem, dah, dbh, idesc, (pos | k) != 0);
+                        }
                     }
                 }
                 umma_commit(empty_bar(s));
@@ -896,7 +1127,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // ===== split warps (2..9): hi in place, lo at +2*TN_OP_BYTES =====
         const int t = threadIdx.x - 64;  // 0..255
         uint32_t it = 0;
-        for (int64_t c = c_beg; c < c_end; ++c, ++it) {
+        for (int64_t c = c_beg; SPLIT && c < c_end; ++c, ++it) {      // bf16 operands: nothing to split
             const int s = it % TN_STAGES;
             const uint32_t ph = (it / TN_STAGES) & 1u;
             mbar_wait(full_bar(s), ph);
@@ -998,16 +1229,17 @@ __global__ void __launch_bounds__(256) k_reduce_partials_2(const double* __restr
     out[(int64_t)(i / nb) * ld_out + (i % nb)] = (float)acc;
 }
 
-// [rows, feat0 .. feat0 + 32*groups) of a row-major fp32 matrix viewed as {32 features, rows, groups}
-static int make_map_tn(CUtensorMap* map, const float* base, int64_t rows, int64_t ld, int groups) {
+// [rows, feat0 .. feat0 + FEAT*groups) of a row-major matrix of S viewed as {FEAT features (128 bytes), rows, groups}
+template <typename S>
+static int make_map_tn(CUtensorMap* map, const S* base, int64_t rows, int64_t ld, int groups) {
     EncodeTiledFn fn = encode_fn();
     CB_REQUIRE(fn != nullptr, CB_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    const cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)groups};
-    const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
-    const cuuint32_t box[3] = {32, (cuuint32_t)TN_BK, (cuuint32_t)groups};
+    const cuuint64_t dims[3] = {(cuuint64_t)Tn<S>::FEAT, (cuuint64_t)rows, (cuuint64_t)groups};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(S), 128};
+    const cuuint32_t box[3] = {(cuuint32_t)Tn<S>::FEAT, (cuuint32_t)Tn<S>::BKR, (cuuint32_t)groups};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box,
-                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+    const CUresult r = fn(map, El<S>::TMA_T, 3, const_cast<S*>(base), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, Tn<S>::TMA_SWZ,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult " + std::to_string((int)r));
@@ -1034,50 +1266,39 @@ int cb_gemm_split_weight(const float* W, int64_t n_rows, int64_t k_cols, int tra
     return CB_OK;
 }
 
-int cb_gemm_rows_supported(int64_t M, int64_t N, int64_t K) {
-    return M > 0 && N > 0 && K > 0 && N % 4 == 0 && K % 4 == 0 && M < ((int64_t)1 << 31) - 128 && N < (1 << 20) &&
-           K < (1 << 20);
+int cb_gemm_rows_supported(int64_t M, int64_t N, int64_t K) { return cb::tc::rows_supported<float>(M, N, K); }
+int cb_gemm_rows_supported_bf16(int64_t M, int64_t N, int64_t K) {
+    return cb::tc::rows_supported<__nv_bfloat16>(M, N, K);
 }
 
 int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float* Bt_hi, const float* Bt_lo,
                  int64_t N, const float* row_scale, const float* bias, const float* add, int64_t ld_add, int act,
                  float* out, int64_t ld_out, const float* out2_scale, float* out2, int64_t ld_out2,
                  const cb_peer_push_t* push, void* stream) {
+    return cb::tc::gemm_rows_impl<float>(A, M, K, lda, Bt_hi, Bt_lo, N, row_scale, bias, add, ld_add, act, out, ld_out,
+                                         out2_scale, out2, ld_out2, push, stream);
+}
+
+int cb_gemm_rows_bf16(const uint16_t* A, int64_t M, int64_t K, int64_t lda, const uint16_t* Bt, int64_t N,
+                      const float* row_scale, const float* bias, const uint16_t* add, int64_t ld_add, int act,
+                      uint16_t* out, int64_t ld_out, const float* out2_scale, uint16_t* out2, int64_t ld_out2,
+                      const cb_peer_push_t* push, void* stream) {
+    using B = __nv_bfloat16;
+    return cb::tc::gemm_rows_impl<B>((const B*)A, M, K, lda, (const B*)Bt, nullptr, N, row_scale, bias, (const B*)add,
+                                     ld_add, act, (B*)out, ld_out, out2_scale, (B*)out2, ld_out2, push, stream);
+}
+
+int cb_gemm_weight_to_bf16(const float* W, int64_t n_rows, int64_t k_cols, int transpose, uint16_t* out, void* stream) {
     using namespace cb;
-    CB_REQUIRE(!push || (push->n_peers >= 0 && push->n_peers <= CB_MAX_PEERS && (push->n_peers == 0 ||
-                         (out && push->need && push->ld >= N && push->ld % 4 == 0))), CB_E_INVALID,
-               "cb_gemm_rows: bad cb_peer_push_t");
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    CB_REQUIRE(A && Bt_hi && Bt_lo, CB_E_INVALID, "cb_gemm_rows: NULL operand");
-    CB_REQUIRE(out || out2, CB_E_INVALID, "cb_gemm_rows: no output buffer");
-    CB_REQUIRE(!out2 || out2_scale, CB_E_INVALID, "cb_gemm_rows: out2 needs out2_scale");
-    CB_REQUIRE(act == CB_ACT_NONE || act == CB_ACT_RELU, CB_E_INVALID, "cb_gemm_rows: unknown activation");
-    CB_REQUIRE(cb_gemm_rows_supported(M, N, K), CB_E_UNSUPPORTED,
-               "cb_gemm_rows: needs N % 4 == 0, K % 4 == 0 and M < 2^31");
-    CB_REQUIRE(lda >= K && lda % 4 == 0 && al16(A) && al16(Bt_hi) && al16(Bt_lo), CB_E_UNSUPPORTED,
-               "cb_gemm_rows: operands must be 16-byte aligned with a row pitch that is a multiple of 4 floats");
-    CB_REQUIRE((!out || (al16(out) && ld_out % 4 == 0 && ld_out >= N)) &&
-                   (!out2 || (al16(out2) && ld_out2 % 4 == 0 && ld_out2 >= N)) &&
-                   (!add || (al16(add) && ld_add % 4 == 0 && ld_add >= N)) && (!bias || al16(bias)),
-               CB_E_UNSUPPORTED, "cb_gemm_rows: epilogue buffers must be 16-byte aligned, pitches multiples of 4");
-    const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-    CUtensorMap ma, mh, ml;
-    int rc = tc::make_map(&ma, A, M, K, lda, tc::BM);
-    if (rc) return rc;
-    rc = tc::make_map(&mh, Bt_hi, N, K, K, bn);
-    if (rc) return rc;
-    rc = tc::make_map(&ml, Bt_lo, N, K, K, bn);
-    if (rc) return rc;
-    tc::GemmArgs g{};
-    g.M = M; g.N = (int)N; g.K = (int)K;
-    g.row_scale = row_scale; g.bias = bias; g.add = add; g.ld_add = ld_add; g.act = act;
-    g.out = out; g.ld_out = ld_out; g.out2_scale = out2_scale; g.out2 = out2; g.ld_out2 = ld_out2;
-    if (push) g.push = *push;
-    g.n_tiles_m = ceil_div(M, tc::BM);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 64) return tc::launch_gemm<64, false>(ma, mh, ml, g, st);
-    if (bn == 128) return tc::launch_gemm<128, false>(ma, mh, ml, g, st);
-    return tc::launch_gemm<256, false>(ma, mh, ml, g, st);
+    CB_REQUIRE(W && out, CB_E_INVALID, "cb_gemm_weight_to_bf16: NULL buffer");
+    CB_REQUIRE(n_rows > 0 && k_cols > 0 && n_rows * k_cols < (int64_t)1 << 31, CB_E_INVALID,
+               "cb_gemm_weight_to_bf16: bad shape");
+    const int64_t total = n_rows * k_cols;
+    const int blocks = (int)(ceil_div(total, 256) < 1184 ? ceil_div(total, 256) : 1184);
+    tc::k_weight_to_bf16<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, (int)n_rows, (int)k_cols, transpose,
+                                                                   (__nv_bfloat16*)out);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
 }
 
 int64_t cb_gemm_rows_grad_workspace_bytes(int64_t M, int64_t N) {
@@ -1091,143 +1312,147 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
                       int accumulate_x0, const float* post_scale, float* out, int64_t ld_out, float* col_sum,
                       uint8_t* row_live, void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push,
                       void* stream) {
-    using namespace cb;
-    CB_REQUIRE(!push || (push->n_peers >= 0 && push->n_peers <= CB_MAX_PEERS && (push->n_peers == 0 ||
-                         (push->need && push->ld >= N && push->ld % 4 == 0))), CB_E_INVALID,
-               "cb_gemm_rows_grad: bad cb_peer_push_t");
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    CB_REQUIRE(A && Bt_hi && Bt_lo && out, CB_E_INVALID, "cb_gemm_rows_grad: NULL operand");
-    CB_REQUIRE(!(gate_u8 && gate_f32), CB_E_INVALID, "cb_gemm_rows_grad: one gate at most");
-    CB_REQUIRE(!(add && d_x0 && accumulate_x0), CB_E_UNSUPPORTED,
-               "cb_gemm_rows_grad: `add` and an accumulating d_x0 cannot be combined");
-    CB_REQUIRE(cb_gemm_rows_supported(M, N, K), CB_E_UNSUPPORTED,
-               "cb_gemm_rows_grad: needs N % 4 == 0, K % 4 == 0 and M < 2^31");
-    CB_REQUIRE(lda >= K && lda % 4 == 0 && al16(A) && al16(Bt_hi) && al16(Bt_lo), CB_E_UNSUPPORTED,
-               "cb_gemm_rows_grad: operands must be 16-byte aligned with a row pitch that is a multiple of 4 floats");
-    CB_REQUIRE(al16(out) && ld_out % 4 == 0 && ld_out >= N && (!add || (al16(add) && ld_add % 4 == 0 && ld_add >= N)) &&
-                   (!d_x0 || (al16(d_x0) && ld_dx0 % 4 == 0 && ld_dx0 >= N)) &&
-                   (!gate_f32 || (al16(gate_f32) && ld_gate % 4 == 0 && ld_gate >= N)) &&
-                   (!gate_u8 || ((reinterpret_cast<uintptr_t>(gate_u8) & 3u) == 0 && ld_gate % 4 == 0 && ld_gate >= N)),
-               CB_E_UNSUPPORTED, "cb_gemm_rows_grad: epilogue buffers must be aligned, pitches multiples of 4");
-    CB_REQUIRE(!col_sum || (workspace && workspace_bytes >= cb_gemm_rows_grad_workspace_bytes(M, N)), CB_E_WORKSPACE,
-               "cb_gemm_rows_grad: workspace smaller than cb_gemm_rows_grad_workspace_bytes()");
-    const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-    CUtensorMap ma, mh, ml;
-    int rc = tc::make_map(&ma, A, M, K, lda, tc::BM);
-    if (rc) return rc;
-    rc = tc::make_map(&mh, Bt_hi, N, K, K, bn);
-    if (rc) return rc;
-    rc = tc::make_map(&ml, Bt_lo, N, K, K, bn);
-    if (rc) return rc;
-    tc::GemmArgs g{};
-    g.M = M; g.N = (int)N; g.K = (int)K;
-    g.row_scale = row_scale; g.add = add; g.ld_add = ld_add;
-    g.out = out; g.ld_out = ld_out;
-    g.n_tiles_m = ceil_div(M, tc::BM);
-    g.gate_u8 = gate_u8; g.gate_f32 = gate_f32; g.ld_gate = ld_gate;
-    g.mixed = mixed; g.alpha = (float)alpha; g.one_minus_alpha = (float)(1.0 - alpha);
-    g.d_x0 = d_x0; g.ld_dx0 = ld_dx0; g.accumulate_x0 = d_x0 ? accumulate_x0 : 0;
-    g.post_scale = post_scale;
-    g.col_partial = col_sum ? (float*)workspace : nullptr;
-    g.row_live = row_live;
-    if (push) g.push = *push;
-    cudaStream_t st = (cudaStream_t)stream;
-    rc = bn == 64 ? tc::launch_gemm<64, true>(ma, mh, ml, g, st)
-                  : (bn == 128 ? tc::launch_gemm<128, true>(ma, mh, ml, g, st)
-                               : tc::launch_gemm<256, true>(ma, mh, ml, g, st));
-    if (rc) return rc;
-    if (col_sum) {
-        tc::k_col_final<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(
-            (const float*)workspace, (int)tc::gemm_grid_x(g.n_tiles_m, g.push.max_ctas), (int)N, col_sum);
-        CB_LAUNCH_CHECK();
-    }
-    return CB_OK;
+    return cb::tc::gemm_rows_grad_impl<float>(A, M, K, lda, Bt_hi, Bt_lo, N, row_scale, add, ld_add, gate_u8, gate_f32,
+                                              ld_gate, mixed, alpha, d_x0, ld_dx0, accumulate_x0, post_scale, out,
+                                              ld_out, col_sum, row_live, workspace, workspace_bytes, push, stream);
 }
 
-int cb_gemm_tn_supported(int64_t M, int64_t Ka, int64_t Nb) {
-    return M > 0 && Ka > 0 && Nb > 0 && Ka % 32 == 0 && Nb % 32 == 0 && M < ((int64_t)1 << 31) - 64 &&
-           Ka <= 4096 && Nb <= 4096;
+int cb_gemm_rows_grad_bf16(const uint16_t* A, int64_t M, int64_t K, int64_t lda, const uint16_t* Bt, int64_t N,
+                           const float* row_scale, const uint16_t* add, int64_t ld_add, const uint8_t* gate_u8,
+                           const uint16_t* gate_val, int64_t ld_gate, int mixed, double alpha, uint16_t* d_x0,
+                           int64_t ld_dx0, int accumulate_x0, const float* post_scale, uint16_t* out, int64_t ld_out,
+                           float* col_sum, uint8_t* row_live, void* workspace, int64_t workspace_bytes,
+                           const cb_peer_push_t* push, void* stream) {
+    using B = __nv_bfloat16;
+    return cb::tc::gemm_rows_grad_impl<B>((const B*)A, M, K, lda, (const B*)Bt, nullptr, N, row_scale, (const B*)add,
+                                          ld_add, gate_u8, (const B*)gate_val, ld_gate, mixed, alpha, (B*)d_x0, ld_dx0,
+                                          accumulate_x0, post_scale, (B*)out, ld_out, col_sum, row_live, workspace,
+                                          workspace_bytes, push, stream);
 }
 
+}  // extern "C" (reopened below)
+
+namespace cb {
+namespace tc {
+
+template <typename S>
+static int tn_supported(int64_t M, int64_t Ka, int64_t Nb) {
+    return M > 0 && Ka > 0 && Nb > 0 && Ka % Tn<S>::FEAT == 0 && Nb % Tn<S>::FEAT == 0 &&
+           M < ((int64_t)1 << 31) - 64 && Ka <= 4096 && Nb <= 4096;
+}
+
+template <typename S>
 static void tn_plan(int64_t M, int64_t* chunks, int* seg_chunks, int64_t* n_segs, int* ctas) {
-    const int64_t ch = cb::ceil_div(M, cb::tc::TN_BK);
-    const int sms = cb::sm_count();
-    int64_t sc = cb::ceil_div(ch, sms);
-    static const int64_t max_sc = getenv("CB_TN_SEG_CHUNKS") ? atoll(getenv("CB_TN_SEG_CHUNKS")) : cb::tc::TN_MAX_SEG_CHUNKS;
+    const int64_t ch = ceil_div(M, Tn<S>::BKR);
+    const int sms = sm_count();
+    int64_t sc = ceil_div(ch, sms);
+    static const int64_t max_sc = getenv("CB_TN_SEG_CHUNKS") ? atoll(getenv("CB_TN_SEG_CHUNKS")) : TN_MAX_SEG_CHUNKS;
     if (sc > max_sc) sc = max_sc;
     if (sc < 1) sc = 1;
     *chunks = ch;
     *seg_chunks = (int)sc;
-    *n_segs = cb::ceil_div(ch, sc);
+    *n_segs = ceil_div(ch, sc);
     *ctas = (int)(*n_segs < sms ? *n_segs : sms);
 }
 
-int64_t cb_gemm_tn_workspace_bytes(int64_t M, int64_t Ka, int64_t Nb) {
-    if (!cb_gemm_tn_supported(M, Ka, Nb)) return 0;
+template <typename S>
+static int64_t tn_workspace_bytes(int64_t M, int64_t Ka, int64_t Nb) {
+    if (!tn_supported<S>(M, Ka, Nb)) return 0;
     int64_t chunks, n_segs;
     int sc, ctas;
-    tn_plan(M, &chunks, &sc, &n_segs, &ctas);
+    tn_plan<S>(M, &chunks, &sc, &n_segs, &ctas);
     const int64_t ka = Ka < 256 ? Ka : 256, nb = Nb < 256 ? Nb : 256;
-    return n_segs * ka * nb * (int64_t)sizeof(float) + cb::tc::TN_REDUCE_SLICES * ka * nb * (int64_t)sizeof(double);
+    return n_segs * ka * nb * (int64_t)sizeof(float) + TN_REDUCE_SLICES * ka * nb * (int64_t)sizeof(double);
 }
 
-int cb_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Nb,
-               const float* row_scale, int scale_b, float* out, int64_t ld_out, void* workspace,
-               int64_t workspace_bytes, void* stream) {
-    using namespace cb;
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+template <typename S>
+static int gemm_tn_impl(const S* A, int64_t lda, const S* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Nb,
+                        const float* row_scale, int scale_b, float* out, int64_t ld_out, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
     CB_REQUIRE(A && B && out, CB_E_INVALID, "cb_gemm_tn: NULL buffer");
-    CB_REQUIRE(cb_gemm_tn_supported(M, Ka, Nb), CB_E_UNSUPPORTED,
-               "cb_gemm_tn: needs Ka % 32 == 0, Nb % 32 == 0 and M < 2^31");
-    CB_REQUIRE(al16(A) && al16(B) && lda % 4 == 0 && ldb % 4 == 0 && lda >= Ka && ldb >= Nb && ld_out >= Nb,
-               CB_E_UNSUPPORTED, "cb_gemm_tn: operands must be 16-byte aligned, pitches multiples of 4 floats");
-    CB_REQUIRE(workspace && workspace_bytes >= cb_gemm_tn_workspace_bytes(M, Ka, Nb), CB_E_WORKSPACE,
+    CB_REQUIRE(tn_supported<S>(M, Ka, Nb), CB_E_UNSUPPORTED,
+               "cb_gemm_tn: needs Ka and Nb multiples of one 128-byte feature group and M < 2^31");
+    CB_REQUIRE(!row_scale || El<S>::SPLIT, CB_E_UNSUPPORTED, "cb_gemm_tn: the bf16 variant takes pre-scaled operands");
+    CB_REQUIRE(al16(A) && al16(B) && lda % vec16<S>() == 0 && ldb % vec16<S>() == 0 && lda >= Ka && ldb >= Nb &&
+                   ld_out >= Nb,
+               CB_E_UNSUPPORTED, "cb_gemm_tn: operands must be 16-byte aligned, pitches multiples of 16 bytes");
+    CB_REQUIRE(workspace && workspace_bytes >= tn_workspace_bytes<S>(M, Ka, Nb), CB_E_WORKSPACE,
                "cb_gemm_tn: workspace missing or smaller than cb_gemm_tn_workspace_bytes()");
     static std::atomic<bool> configured[64];   // per device ordinal (the attribute is per device)
     int dev = 0;
     CB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        CB_CUDA(cudaFuncSetAttribute(tc::k_gemm_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TN_SMEM_BYTES));
+        CB_CUDA(cudaFuncSetAttribute(k_gemm_tn<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, TnCfg<S>::SMEM_BYTES));
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     cudaStream_t st = (cudaStream_t)stream;
     int64_t chunks, n_segs;
     int seg_chunks, ctas;
-    tn_plan(M, &chunks, &seg_chunks, &n_segs, &ctas);
+    tn_plan<S>(M, &chunks, &seg_chunks, &n_segs, &ctas);
     for (int64_t a0 = 0; a0 < Ka; a0 += 256) {
         for (int64_t b0 = 0; b0 < Nb; b0 += 256) {
-            tc::TnArgs g{};
+            TnArgs g{};
             g.n_chunks = chunks;
             g.n_segs = n_segs;
             g.seg_chunks = seg_chunks;
             g.ka = (int)(Ka - a0 < 256 ? Ka - a0 : 256);
             g.nb = (int)(Nb - b0 < 256 ? Nb - b0 : 256);
-            g.ga = g.ka / 32;
-            g.gb = g.nb / 32;
+            g.ga = g.ka / Tn<S>::FEAT;
+            g.gb = g.nb / Tn<S>::FEAT;
             g.partial = (float*)workspace;
             g.row_scale = row_scale;
             g.scale_op = scale_b ? 1 : 0;
             g.M = M;
-            g.lbo = (uint32_t)tc::TN_GROUP_BYTES;   // between 32-feature groups
-            g.sbo = 512u;                           // between 4-node-row swizzle atoms
+            g.lbo = (uint32_t)TnCfg<S>::GROUP_BYTES;   // between feature groups
+            g.sbo = Tn<S>::SBO;                        // between swizzle atoms of node rows
             CUtensorMap ma, mb;
-            int rc = tc::make_map_tn(&ma, A + a0, M, lda, g.ga);
+            int rc = make_map_tn<S>(&ma, A + a0, M, lda, g.ga);
             if (rc) return rc;
-            rc = tc::make_map_tn(&mb, B + b0, M, ldb, g.gb);
+            rc = make_map_tn<S>(&mb, B + b0, M, ldb, g.gb);
             if (rc) return rc;
-            tc::k_gemm_tn<<<ctas, tc::TN_THREADS, tc::TN_SMEM_BYTES, st>>>(ma, mb, g);
+            k_gemm_tn<S><<<ctas, TN_THREADS, TnCfg<S>::SMEM_BYTES, st>>>(ma, mb, g);
             CB_LAUNCH_CHECK();
             const int total = g.ka * g.nb;
-            const int slices = (int)(n_segs < tc::TN_REDUCE_SLICES ? n_segs : tc::TN_REDUCE_SLICES);
+            const int slices = (int)(n_segs < TN_REDUCE_SLICES ? n_segs : TN_REDUCE_SLICES);
             double* mid = reinterpret_cast<double*>(g.partial + (size_t)n_segs * total);   // 8-byte aligned: total % 1024 == 0
-            tc::k_reduce_partials_1<<<dim3((total + 255) / 256, slices), 256, 0, st>>>(g.partial, n_segs, total, mid);
+            k_reduce_partials_1<<<dim3((total + 255) / 256, slices), 256, 0, st>>>(g.partial, n_segs, total, mid);
             CB_LAUNCH_CHECK();
-            tc::k_reduce_partials_2<<<(total + 255) / 256, 256, 0, st>>>(mid, slices, g.ka, g.nb,
-                                                                        out + a0 * ld_out + b0, ld_out);
+            k_reduce_partials_2<<<(total + 255) / 256, 256, 0, st>>>(mid, slices, g.ka, g.nb,
+                                                                    out + a0 * ld_out + b0, ld_out);
             CB_LAUNCH_CHECK();
         }
     }
     return CB_OK;
+}
+
+}  // namespace tc
+}  // namespace cb
+
+extern "C" {
+
+int cb_gemm_tn_supported(int64_t M, int64_t Ka, int64_t Nb) { return cb::tc::tn_supported<float>(M, Ka, Nb); }
+int cb_gemm_tn_supported_bf16(int64_t M, int64_t Ka, int64_t Nb) {
+    return cb::tc::tn_supported<__nv_bfloat16>(M, Ka, Nb);
+}
+int64_t cb_gemm_tn_workspace_bytes(int64_t M, int64_t Ka, int64_t Nb) {
+    return cb::tc::tn_workspace_bytes<float>(M, Ka, Nb);
+}
+int64_t cb_gemm_tn_workspace_bytes_bf16(int64_t M, int64_t Ka, int64_t Nb) {
+    return cb::tc::tn_workspace_bytes<__nv_bfloat16>(M, Ka, Nb);
+}
+
+int cb_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Nb,
+               const float* row_scale, int scale_b, float* out, int64_t ld_out, void* workspace,
+               int64_t workspace_bytes, void* stream) {
+    return cb::tc::gemm_tn_impl<float>(A, lda, B, ldb, M, Ka, Nb, row_scale, scale_b, out, ld_out, workspace,
+                                       workspace_bytes, stream);
+}
+
+int cb_gemm_tn_bf16(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Nb,
+                    float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream) {
+    using T = __nv_bfloat16;
+    return cb::tc::gemm_tn_impl<T>((const T*)A, lda, (const T*)B, ldb, M, Ka, Nb, nullptr, 0, out, ld_out, workspace,
+                                   workspace_bytes, stream);
 }
 
 }  // extern "C"

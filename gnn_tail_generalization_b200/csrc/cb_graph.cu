@@ -47,6 +47,28 @@ __global__ void k_edge_keys(const int64_t* __restrict__ src, const int64_t* __re
     }
 }
 
+// One side only (cb_graph_create_local): sort key = local row of the owned endpoint, degree count, range check.
+__global__ void k_edge_keys_side(const int64_t* __restrict__ own_end, const int64_t* __restrict__ other_end, int64_t E,
+                                 int64_t N, int64_t row_begin, int64_t row_end, uint32_t* __restrict__ key,
+                                 int32_t* __restrict__ eid, int32_t* __restrict__ deg, int* __restrict__ err) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint32_t rows = (uint32_t)(row_end - row_begin);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+        const int64_t o = own_end[e], t = other_end[e];
+        if (o < 0 || o >= N || t < 0 || t >= N) {
+            err[0] = 1;
+            key[e] = rows;
+        } else if (o < row_begin || o >= row_end) {
+            err[2] = 1;          // the caller promised edges of the owned rows only
+            key[e] = rows;
+        } else {
+            key[e] = (uint32_t)(o - row_begin);
+            atomicAdd(deg + (o - row_begin), 1);
+        }
+        eid[e] = (int32_t)e;
+    }
+}
+
 // col[j] = other endpoint of the j-th stored edge
 __global__ void k_gather_cols(const int64_t* __restrict__ other, const int32_t* __restrict__ perm,
                               int64_t n, int32_t* __restrict__ col) {
@@ -483,6 +505,67 @@ __global__ void __launch_bounds__(256) k_live_offsets(const int64_t* __restrict_
     }
 }
 
+// One CSR side from an edge list that holds exactly the edges of the owned rows on that side.
+static int build_side_local(cb_graph* g, Side& side, const int64_t* own_end, const int64_t* other_end, int64_t E,
+                            float* deg_is, int* zero_flag_host, cudaStream_t st) {
+    const int64_t rows = g->rows;
+    Scratch tmp;
+    CB_CUDA(cudaMalloc((void**)&side.deg, (size_t)(rows > 0 ? rows : 1) * sizeof(int32_t)));
+    CB_CUDA(cudaMemsetAsync(side.deg, 0, (size_t)(rows > 0 ? rows : 1) * sizeof(int32_t), st));
+    uint32_t *key = nullptr, *key_alt = nullptr;
+    int32_t *eid = nullptr, *eid_alt = nullptr;
+    int* flags = nullptr;     // [0] range error, [1] zero degree, [2] edge of a row that is not owned
+    int64_t* spine = nullptr;
+    CB_CUDA(tmp.alloc(&key, E));
+    CB_CUDA(tmp.alloc(&key_alt, E));
+    CB_CUDA(tmp.alloc(&eid, E));
+    CB_CUDA(tmp.alloc(&eid_alt, E));
+    CB_CUDA(tmp.alloc(&flags, 3));
+    CB_CUDA(tmp.alloc(&spine, ceil_div(rows > 0 ? rows : 1, SCAN_TILE) + 1));
+    CB_CUDA(cudaMemsetAsync(flags, 0, 3 * sizeof(int), st));
+    if (E > 0) {
+        k_edge_keys_side<<<grid_for(E, 256), 256, 0, st>>>(own_end, other_end, E, g->n_nodes, g->row_begin, g->row_end,
+                                                           key, eid, side.deg, flags);
+        CB_LAUNCH_CHECK();
+    }
+    k_inv_sqrt_deg<<<grid_for(rows, 256), 256, 0, st>>>(side.deg, rows, deg_is, flags + 1);
+    CB_LAUNCH_CHECK();
+    int h_flags[3] = {0, 0, 0};
+    CB_CUDA(cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    CB_REQUIRE(h_flags[0] == 0, CB_E_RANGE, "edge list holds a node id outside [0, num_nodes)");
+    CB_REQUIRE(h_flags[2] == 0, CB_E_RANGE, "cb_graph_create_local: an edge does not belong to the owned row range");
+    if (zero_flag_host) *zero_flag_host = h_flags[1];
+    const int end_bit = bits_for((uint32_t)rows);
+    cub::DoubleBuffer<uint32_t> kb(key, key_alt);
+    cub::DoubleBuffer<int32_t> vb(eid, eid_alt);
+    if (E > 0) {
+        size_t cub_bytes = 0;
+        CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, kb, vb, (int)E, 0, end_bit, st));
+        void* cub_tmp = nullptr;
+        CB_CUDA(tmp.alloc((char**)&cub_tmp, (int64_t)cub_bytes));
+        CB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, kb, vb, (int)E, 0, end_bit, st));
+        count_launch(2 * ((end_bit + 7) / 8));
+    }
+    int32_t* sorted = vb.Current();
+    side.perm = sorted;
+    int rc = finish_side(side, other_end, rows, g->hub_chunk, spine, st);
+    if (rc) {
+        side.perm = nullptr;
+        return rc;
+    }
+    int32_t* keep = nullptr;
+    cudaError_t e = cudaMalloc((void**)&keep, (size_t)(side.n_edges > 0 ? side.n_edges : 1) * sizeof(int32_t));
+    if (e != cudaSuccess) {
+        side.perm = nullptr;
+        return cuda_fail(e, "cudaMalloc(perm)", __FILE__, __LINE__);
+    }
+    side.perm = keep;
+    CB_CUDA(cudaMemcpyAsync(keep, sorted, (size_t)side.n_edges * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    return CB_OK;
+}
+
 }  // namespace cb
 
 // ---------------------------------------------------------------------------------------------
@@ -511,6 +594,50 @@ int cb_graph_create_sliced(const int64_t* edge_index, int64_t num_edges, int64_t
     cudaError_t e = cudaGetDevice(&g->device);
     int rc = e == cudaSuccess ? build(g, edge_index, num_edges, (cudaStream_t)stream)
                               : cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
+    if (rc != CB_OK) {
+        cb_graph_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return CB_OK;
+}
+
+int cb_graph_create_local(const int64_t* in_edges, int64_t num_in_edges, const int64_t* out_edges,
+                          int64_t num_out_edges, int64_t num_nodes, int64_t row_begin, int64_t row_end, int hub_chunk,
+                          void* stream, cb_graph_t** out) {
+    using namespace cb;
+    CB_REQUIRE(out != nullptr, CB_E_INVALID, "cb_graph_create_local: out is NULL");
+    *out = nullptr;
+    CB_REQUIRE(num_in_edges >= 0 && num_out_edges >= 0 && num_nodes >= 0, CB_E_INVALID,
+               "cb_graph_create_local: negative size");
+    CB_REQUIRE((num_in_edges == 0 || in_edges) && (num_out_edges == 0 || out_edges), CB_E_INVALID,
+               "cb_graph_create_local: an edge list is NULL");
+    CB_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= num_nodes, CB_E_INVALID,
+               "cb_graph_create_local: row range outside [0, num_nodes]");
+    CB_REQUIRE(num_nodes < (int64_t)INT32_MAX && num_in_edges < (int64_t)INT32_MAX &&
+                   num_out_edges < (int64_t)INT32_MAX,
+               CB_E_UNSUPPORTED, "cb_graph_create_local: num_nodes and the per-handle edge counts must be < 2^31");
+    cb_graph* g = new cb_graph();
+    g->n_nodes = num_nodes;
+    g->row_begin = row_begin;
+    g->row_end = row_end;
+    g->rows = row_end - row_begin;
+    g->hub_chunk = hub_chunk > 0 ? hub_chunk : CB_DEFAULT_HUB_CHUNK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rows1 = g->rows > 0 ? g->rows : 1;
+    int rc = CB_OK;
+    cudaError_t e = cudaGetDevice(&g->device);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
+    if (!rc && (e = cudaMalloc((void**)&g->din_is, (size_t)rows1 * sizeof(float))) != cudaSuccess)
+        rc = cuda_fail(e, "cudaMalloc(din)", __FILE__, __LINE__);
+    if (!rc && (e = cudaMalloc((void**)&g->dout_is, (size_t)rows1 * sizeof(float))) != cudaSuccess)
+        rc = cuda_fail(e, "cudaMalloc(dout)", __FILE__, __LINE__);
+    // in-edges: rows = destinations (row 1 of the list), columns = sources (row 0)
+    if (!rc) rc = build_side_local(g, g->by_dst, in_edges + num_in_edges, in_edges, num_in_edges, g->din_is,
+                                   &g->has_zero_in_deg, st);
+    // out-edges: rows = sources (row 0), columns = destinations (row 1)
+    if (!rc) rc = build_side_local(g, g->by_src, out_edges, out_edges + num_out_edges, num_out_edges, g->dout_is,
+                                   nullptr, st);
     if (rc != CB_OK) {
         cb_graph_destroy(g);
         return rc;

@@ -80,6 +80,17 @@ def allreduce_dense_grads(module, world, group=None):
     return flat.numel()
 
 
+def broadcast_dense_params(module, world, group=None, src=0):
+    """Makes the replicated (dense) parameters identical on every rank.  With SE tables each rank draws
+    ``randn(its_rows, d)`` between the layers' weight initialisations (GCN.py:177-182), so ranks that own a
+    different number of rows leave the constructor with different dense weights."""
+    if world == 1:
+        return
+    for n, p in module.named_parameters():
+        if not is_row_sharded(n):
+            dist.broadcast(p.data, src=src, group=group)
+
+
 def need_masks(col_needed, num_nodes, world, rank, group=None):
     """Which local rows each peer gathers.
 
@@ -111,7 +122,7 @@ class PushSlot:
     ``local`` is what the producer hands to autograd: [rows, width] for one panel, else the
     [rows, n_panels, panel_width] view of the panel-major buffer."""
     __slots__ = ('owner', 'width', 'local_rows', 'n_panels', 'panel_width', 'panel_full', 'panel_local', 'descs',
-                 'local', 'events', 'pushed_rows', 'keep')
+                 'local', 'events', 'pushed_rows', 'keep', 'dtype')
 
     def pushed(self, p):
         dist.all_reduce(self.owner._flag, op=dist.ReduceOp.SUM, group=self.owner.group)
@@ -135,7 +146,8 @@ class PeerExchange:
     exchange #i-1, which every rank enters only after its aggregation #i-2 -- the last reader of b -- is
     complete (the compute stream waits for the side stream that ran it)."""
 
-    def __init__(self, graph, max_d, group=None, panels=1, push_ctas=0):
+    def __init__(self, graph, max_d, group=None, panels=1, push_ctas=0, elem_bytes=4):
+        """elem_bytes: bytes per element of the widest matrix exchanged (4: fp32 features, 2: a bf16-only model)."""
         self.graph, self.group = graph, group
         self.world, self.rank = graph.world, graph.rank
         if not 2 <= self.world <= C.CB_MAX_PEERS + 1:
@@ -145,7 +157,8 @@ class PeerExchange:
         self.n_pad = self.per * self.world
         self.max_d = int(max_d)
         self.panels, self.push_ctas = max(1, int(panels)), int(push_ctas)
-        nbytes = self.n_pad * self.max_d * 4
+        self.row_bytes = self.max_d * int(elem_bytes)
+        nbytes = max(1, self.n_pad * self.row_bytes)
         self._mine, self._theirs, handles = [], [], []
         # Every rank goes through both collectives below whatever happened locally, so that a rank whose
         # allocation or mapping failed (no peer access, IPC disabled in the container ...) takes the whole
@@ -202,22 +215,27 @@ class PeerExchange:
         self._pending, self._views = {}, {}
         dist.barrier(group=group)   # every rank has mapped every buffer before the first push
 
-    def slot(self, side, d):
-        """The next exchange buffer laid out for a [., d] matrix; None if d does not fit."""
-        if d > self.max_d or d % 4:
+    def slot(self, side, d, dtype=torch.float32):
+        """The next exchange buffer laid out for a [., d] matrix of ``dtype``; None if it does not fit."""
+        es = 4 if dtype == torch.float32 else 2
+        vec = 16 // es                 # the aggregation reads rows with 16-byte accesses
+        if dtype not in (torch.float32, torch.bfloat16) or d * es > self.row_bytes or d % vec:
             return None
         b = self._turn & 1
         self._turn += 1
-        np_ = self.panels if (d % self.panels == 0 and (d // self.panels) % 4 == 0) else 1
+        np_ = self.panels if (d % self.panels == 0 and (d // self.panels) % vec == 0) else 1
         pw = d // np_
         lo, rows = self.graph.row_begin, self.graph.rows
         s = PushSlot()
-        s.owner, s.width, s.local_rows, s.n_panels, s.panel_width = self, d, rows, np_, pw
-        full3 = self._views.get((b, d, np_))
+        s.owner, s.width, s.local_rows, s.n_panels, s.panel_width, s.dtype = self, d, rows, np_, pw, dtype
+        full3 = self._views.get((b, d, np_, dtype))
         if full3 is None:
-            full3 = torch.as_tensor(_DevArray(self._mine[b], self.n_pad * d, '<f4'), device=self.dev)
+            if dtype == torch.float32:
+                full3 = torch.as_tensor(_DevArray(self._mine[b], self.n_pad * d, '<f4'), device=self.dev)
+            else:
+                full3 = torch.as_tensor(_DevArray(self._mine[b], self.n_pad * d, '<i2'), device=self.dev).view(dtype)
             full3 = full3.view(np_, self.n_pad, pw)      # panel-major
-            self._views[(b, d, np_)] = full3
+            self._views[(b, d, np_, dtype)] = full3
         s.panel_full = [full3[p] for p in range(np_)]
         s.panel_local = [full3[p, lo:lo + rows] for p in range(np_)]
         s.local = s.panel_local[0] if np_ == 1 else full3[:, lo:lo + rows].permute(1, 0, 2)
@@ -227,7 +245,7 @@ class PeerExchange:
             desc.n_peers = len(self.peers)
             desc.max_ctas = self.push_ctas if np_ > 1 else 0
             for j, q in enumerate(self._theirs[b]):
-                desc.peer[j] = q + p * self.n_pad * pw * 4
+                desc.peer[j] = q + p * self.n_pad * pw * es
             desc.need = self.need[side].data_ptr()
             desc.row0, desc.ld = lo, pw
             s.descs.append(desc)
@@ -257,9 +275,12 @@ class PeerExchange:
 class SlicedGraph(GraphHandle):
     """This rank's slice of the graph; ``exchange`` is the per-aggregation halo step."""
 
-    def __init__(self, edge_index, num_nodes, rank, world, group=None, hub_chunk=0):
+    def __init__(self, edge_index, num_nodes, rank, world, group=None, hub_chunk=0, local_out_edges=None):
+        """edge_index: the whole edge list (every rank filters its slice), or -- with ``local_out_edges`` -- only this
+        rank's in-edges, ``local_out_edges`` being its out-edges (see GraphHandle)."""
         lo, hi = slice_bounds(num_nodes, world, rank)
-        super().__init__(edge_index, num_nodes, row_begin=lo, row_end=hi, hub_chunk=hub_chunk)
+        super().__init__(edge_index, num_nodes, row_begin=lo, row_end=hi, hub_chunk=hub_chunk,
+                         local_out_edges=local_out_edges)
         self.rank, self.world, self.group = rank, world, group
         self.exchanged_bytes = 0
         self.peer = None
@@ -270,24 +291,24 @@ class SlicedGraph(GraphHandle):
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
             self.has_zero_in_degree = bool(int(flag))
 
-    def enable_push(self, max_d, panels=1, push_ctas=0):
+    def enable_push(self, max_d, panels=1, push_ctas=0, elem_bytes=4):
         """Switch the exchange from an NCCL all-gather after the producing kernel to peer stores from
         inside it (PeerExchange).  ``max_d``: widest matrix that will be exchanged; ``panels`` > 1 pipelines
         the exchange by column panels against the aggregation, ``push_ctas`` caps the grid of a pushing
         kernel so that the aggregation of the previous panel finds free SMs."""
         if self.world > 1 and self.peer is None:
-            self.peer = PeerExchange(self, max_d, self.group, panels, push_ctas)
+            self.peer = PeerExchange(self, max_d, self.group, panels, push_ctas, elem_bytes)
         return self.peer
 
-    def push_slot(self, side, d):
-        return self.peer.slot(side, d) if self.peer is not None else None
+    def push_slot(self, side, d, dtype=torch.float32):
+        return self.peer.slot(side, d, dtype) if self.peer is not None else None
 
     def exchange(self, local_rows):
         """[N, d] tensor of every rank's rows, or -- when the producer pushed them panel by panel -- the
         PushSlot whose panels become valid at its events."""
         s = self.peer.take(local_rows) if self.peer is not None else None
         if s is not None:
-            self.exchanged_bytes += s.pushed_rows * s.width * 4
+            self.exchanged_bytes += s.pushed_rows * s.width * (4 if s.dtype == torch.float32 else 2)
             # one panel: its barrier is already queued on this stream, stream order is enough
             return s.rows(0, self.num_nodes) if s.n_panels == 1 else s
         if local_rows.dim() == 3:

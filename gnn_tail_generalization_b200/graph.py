@@ -25,19 +25,30 @@ class GraphHandle:
 
     world = 1
 
-    def __init__(self, edge_index, num_nodes, row_begin=0, row_end=None, hub_chunk=0):
-        if not (torch.is_tensor(edge_index) and edge_index.is_cuda):
-            raise ValueError('edge_index must be a CUDA tensor (this path has no CPU implementation)')
-        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
-            raise ValueError(f'edge_index must be [2, E], got {tuple(edge_index.shape)}')
-        ei = edge_index.to(torch.int64).contiguous()
+    def __init__(self, edge_index, num_nodes, row_begin=0, row_end=None, hub_chunk=0, local_out_edges=None):
+        """edge_index [2, E] int64 on the device.  By default it is the whole edge list and the handle keeps the
+        edges of the rows [row_begin, row_end).  With ``local_out_edges`` (cb_graph_create_local) ``edge_index`` holds
+        only the edges whose DESTINATION is owned and ``local_out_edges`` those whose SOURCE is owned (for a symmetric
+        graph: the same list with its rows swapped) -- the full list of a 10^9-edge graph never exists."""
+        def check(t, what):
+            if not (torch.is_tensor(t) and t.is_cuda):
+                raise ValueError(f'{what} must be a CUDA tensor (this path has no CPU implementation)')
+            if t.dim() != 2 or t.shape[0] != 2:
+                raise ValueError(f'{what} must be [2, E], got {tuple(t.shape)}')
+            return t.to(torch.int64).contiguous()
+        ei = check(edge_index, 'edge_index')
         self.device = ei.device
         self.num_nodes = int(num_nodes)
         row_end = self.num_nodes if row_end is None else int(row_end)
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            C.call('cb_graph_create_sliced', C.ptr(ei), ei.shape[1], self.num_nodes, int(row_begin), row_end,
-                   int(hub_chunk), C.stream_ptr(self.device), ctypes.byref(self._h))
+            if local_out_edges is None:
+                C.call('cb_graph_create_sliced', C.ptr(ei), ei.shape[1], self.num_nodes, int(row_begin), row_end,
+                       int(hub_chunk), C.stream_ptr(self.device), ctypes.byref(self._h))
+            else:
+                eo = check(local_out_edges, 'local_out_edges')
+                C.call('cb_graph_create_local', C.ptr(ei), ei.shape[1], C.ptr(eo), eo.shape[1], self.num_nodes,
+                       int(row_begin), row_end, int(hub_chunk), C.stream_ptr(self.device), ctypes.byref(self._h))
         self.row_begin, self.row_end = int(row_begin), row_end
         self.rows = row_end - int(row_begin)
         self.num_edges = self._qi(C.Q_NUM_EDGES)
@@ -134,7 +145,7 @@ class GraphHandle:
         """Per-row byte flags of every rank's rows (identity on a whole graph)."""
         return local_flags
 
-    def push_slot(self, side, d):
+    def push_slot(self, side, d, dtype=torch.float32):
         """Exchange buffer the producing kernel should write into (node-sliced graphs with peer pushes)."""
         return None
 

@@ -80,6 +80,14 @@ def _featc(t, dtype):
     return t.contiguous()
 
 
+_STORAGE = (torch.float32, torch.bfloat16)
+
+
+def _sfx(dtype):
+    """C-ABI name suffix of the storage-type variant of a kernel."""
+    return '' if dtype == torch.float32 else '_bf16'
+
+
 def _pofs(t, elems):
     """Device address of element ``elems`` of a tensor (None stays NULL)."""
     return None if t is None else ctypes.c_void_p(t.data_ptr() + elems * t.element_size())
@@ -194,20 +202,23 @@ def backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, relu, mixed, a
     """d_x0_accum: an existing [rows, d] buffer that receives ``+= alpha * dtot`` instead of a fresh d_x0."""
     ref = d_out if d_out is not None else d_out_scaled
     _need_cuda(ref)
-    d_out, d_out_scaled, relu_out = _f32c(d_out), _f32c(d_out_scaled), _f32c(relu_out)
+    st = ref.dtype
+    if st not in _STORAGE:
+        raise TypeError(f'expected float32 or bfloat16, got {st}')
+    d_out, d_out_scaled, relu_out = _featc(d_out, st), _featc(d_out_scaled, st), _featc(relu_out, st)
     rows, d = ref.shape
-    G = torch.empty((rows, d), dtype=torch.float32, device=ref.device)
+    G = torch.empty((rows, d), dtype=st, device=ref.device)
     d_bias = torch.empty(d, dtype=torch.float32, device=ref.device) if want_bias else None
     accumulate = int(want_x0 and d_x0_accum is not None)
-    d_x0 = (d_x0_accum if accumulate else torch.empty((rows, d), dtype=torch.float32, device=ref.device)) \
+    d_x0 = (d_x0_accum if accumulate else torch.empty((rows, d), dtype=st, device=ref.device)) \
         if want_x0 else None
     ws_bytes = int(C.lib().cb_prep_workspace_bytes(rows, d)) if want_bias else 0
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ref.device) if ws_bytes else None
     mats = int(d_out is not None) + int(d_out_scaled is not None) + 1 + int(want_x0) + accumulate + \
         int(relu_out is not None)
-    alg = mats * rows * d * 4 + (rows * d if mask is not None else 0) + 2 * rows * 4
-    with torch.cuda.device(ref.device), _Timed('backward_prep', alg, ref.device):
-        C.call('cb_agg_backward_prep', graph.handle, C.ptr(d_out), C.ptr(d_out_scaled), d, C.ptr(mask),
+    alg = mats * rows * d * ref.element_size() + (rows * d if mask is not None else 0) + 2 * rows * 4
+    with torch.cuda.device(ref.device), _Timed('backward_prep' + _sfx(st), alg, ref.device):
+        C.call('cb_agg_backward_prep' + _sfx(st), graph.handle, C.ptr(d_out), C.ptr(d_out_scaled), d, C.ptr(mask),
                C.ptr(relu_out), C.CB_ACT_RELU if relu else C.CB_ACT_NONE, int(bool(mixed)), float(alpha),
                C.ptr(G), C.ptr(d_bias), C.ptr(d_x0), accumulate, C.ptr(ws), ws_bytes, C.stream_ptr(ref.device))
     return G, d_bias, d_x0
@@ -236,7 +247,8 @@ def sumsq_raw(x):
 
 
 class SplitWeight:
-    """The weight operand of cb_gemm_rows: K-major [N, K] TF32 hi/lo halves (hi + lo ~= W to 2^-22)."""
+    """The weight operand of cb_gemm_rows: K-major [N, K] TF32 hi/lo halves (hi + lo ~= W to 2^-22), or -- for the
+    bf16 transform -- one bf16 [N, K] matrix (``lo`` is None)."""
 
     __slots__ = ('hi', 'lo', 'n', 'k')
 
@@ -244,13 +256,23 @@ class SplitWeight:
         self.hi, self.lo = hi, lo
         self.n, self.k = hi.shape
 
+    @property
+    def dtype(self):
+        return self.hi.dtype
 
-def split_weight(W, transpose):
+
+def split_weight(W, transpose, dtype=torch.float32):
     """transpose=False: W is already [N, K] (nn.Linear.weight; or the GCNConv weight for the adjoint).
-    transpose=True: W is [K, N] (GCNConv.weight used forward) and is transposed while splitting."""
+    transpose=True: W is [K, N] (GCNConv.weight used forward) and is transposed while splitting.
+    dtype: storage type of the matrix the weight will multiply (fp32 master weights are rounded to bf16 per call)."""
     _need_cuda(W)
     W = _f32c(W.detach())
     n, k = (W.shape[1], W.shape[0]) if transpose else W.shape
+    if dtype == torch.bfloat16:
+        out = torch.empty((n, k), dtype=torch.bfloat16, device=W.device)
+        with torch.cuda.device(W.device):
+            C.call('cb_gemm_weight_to_bf16', C.ptr(W), n, k, int(bool(transpose)), C.ptr(out), C.stream_ptr(W.device))
+        return SplitWeight(out, None)
     buf = torch.empty((2, n, k), dtype=torch.float32, device=W.device)
     with torch.cuda.device(W.device):
         C.call('cb_gemm_split_weight', C.ptr(W), n, k, int(bool(transpose)), C.ptr(buf[0]), C.ptr(buf[1]),
@@ -258,33 +280,49 @@ def split_weight(W, transpose):
     return SplitWeight(buf[0], buf[1])
 
 
-def gemm_supported(M, N, K):
+def gemm_supported(M, N, K, dtype=torch.float32):
     """Shape test of cb_gemm_rows / cb_gemm_rows_grad.  M == 0 (a rank of a node-sliced graph that owns no rows)
     counts as supported: the raw wrappers then launch nothing but still take part in the exchange barriers."""
-    return bool(C.lib().cb_gemm_rows_supported(max(int(M), 1), int(N), int(K)))
+    if dtype not in _STORAGE:
+        return False
+    return bool(getattr(C.lib(), 'cb_gemm_rows_supported' + _sfx(dtype))(max(int(M), 1), int(N), int(K)))
+
+
+def _weight_args(wt, c0, K):
+    """The weight operand(s) of a rows GEMM starting at output column c0: (hi, lo) for fp32, (Bt,) for bf16."""
+    if wt.lo is None:
+        return (_pofs(wt.hi, c0 * K),)
+    return (_pofs(wt.hi, c0 * K), _pofs(wt.lo, c0 * K))
 
 
 def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_scale=None, want_out=True,
                   want_out2=False, push=None):
-    """act(row_scale * (A @ W^T) + bias + add) on the tcgen05 tensor cores (3xTF32, fp32-class accuracy).
+    """act(row_scale * (A @ W^T) + bias + add) on the tcgen05 tensor cores: fp32 A -> 3xTF32 (fp32-class accuracy),
+    bf16 A -> kind::f16 on the operands as stored (add / out / out2 then bf16 too, epilogue in fp32).
     Returns out, or (out, out2) when want_out2 (out2 = out2_scale[:,None] * out).
 
     push (dist.PushSlot, multi-GPU): ``out`` is written into the exchange buffer -- one launch per column
     panel of the slot, each storing its rows also into the peers that gather them and followed by the
     slot's stream barrier -- and the slot's local view is returned ([M, N], or [M, panels, N/panels])."""
     _need_cuda(A, row_scale, bias, add, out2_scale)
-    A, row_scale, bias, add, out2_scale = _f32c(A), _f32c(row_scale), _f32c(bias), _f32c(add), _f32c(out2_scale)
+    st = A.dtype
+    if st not in _STORAGE or wt.dtype != st:
+        raise TypeError(f'A is {st}, the weight operand {wt.dtype}')
+    A, row_scale, bias, add, out2_scale = A.contiguous(), _f32c(row_scale), _f32c(bias), _featc(add, st), _f32c(out2_scale)
+    es = A.element_size()
     M, K = A.shape
     if K != wt.k:
         raise ValueError(f'A is [{M},{K}] but the weight operand is [{wt.n},{wt.k}]')
     N = wt.n
-    if push is not None and (not want_out or push.width != N or push.local_rows != M):
+    if push is not None and (not want_out or push.width != N or push.local_rows != M or push.dtype != st):
         raise ValueError('push: the exchange slot does not match the kernel output')
     out = None
     if push is None and want_out:
-        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
-    out2 = torch.empty((M, N), dtype=torch.float32, device=A.device) if want_out2 else None
+        out = torch.empty((M, N), dtype=st, device=A.device)
+    out2 = torch.empty((M, N), dtype=st, device=A.device) if want_out2 else None
     act = C.CB_ACT_RELU if relu else C.CB_ACT_NONE
+    fn, mma = 'cb_gemm_rows' + _sfx(st), (6 if st == torch.float32 else 2)
+    wbytes = (2 if wt.lo is not None else 1) * es
     if M == 0:
         if push is not None:      # a rank that owns no rows still takes part in every panel's barrier
             for p in range(push.n_panels):
@@ -292,18 +330,18 @@ def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_s
             out = push.local
         return (out, out2) if want_out2 else out
     if push is None:
-        alg = 4 * (M * K + 2 * N * K + M * N * (int(want_out) + int(want_out2) + int(add is not None)))
-        with torch.cuda.device(A.device), _Timed('gemm_rows', alg, A.device, flops=6 * M * N * K):
-            C.call('cb_gemm_rows', C.ptr(A), M, K, K, C.ptr(wt.hi), C.ptr(wt.lo), N, C.ptr(row_scale), C.ptr(bias),
+        alg = es * (M * K + M * N * (int(want_out) + int(want_out2) + int(add is not None))) + wbytes * N * K
+        with torch.cuda.device(A.device), _Timed('gemm_rows' + _sfx(st), alg, A.device, flops=mma * M * N * K):
+            C.call(fn, C.ptr(A), M, K, K, *_weight_args(wt, 0, K), N, C.ptr(row_scale), C.ptr(bias),
                    C.ptr(add), N, act, C.ptr(out), N, C.ptr(out2_scale), C.ptr(out2), N, None,
                    C.stream_ptr(A.device))
         return (out, out2) if want_out2 else out
     pw = push.panel_width
     for p in range(push.n_panels):
         c0 = p * pw
-        alg = 4 * (M * K + 2 * pw * K + M * pw * (1 + int(want_out2) + int(add is not None))) + push.pushed_rows * pw * 4
-        with torch.cuda.device(A.device), _Timed('gemm_rows_push', alg, A.device, flops=6 * M * pw * K):
-            C.call('cb_gemm_rows', C.ptr(A), M, K, K, _pofs(wt.hi, c0 * K), _pofs(wt.lo, c0 * K), pw,
+        alg = es * (M * K + M * pw * (1 + int(want_out2) + int(add is not None)) + push.pushed_rows * pw) + wbytes * pw * K
+        with torch.cuda.device(A.device), _Timed('gemm_rows_push' + _sfx(st), alg, A.device, flops=mma * M * pw * K):
+            C.call(fn, C.ptr(A), M, K, K, *_weight_args(wt, c0, K), pw,
                    C.ptr(row_scale), _pofs(bias, c0), _pofs(add, c0), N, act, C.ptr(push.panel_local[p]), pw,
                    C.ptr(out2_scale), _pofs(out2, c0), N, ctypes.byref(push.descs[p]), C.stream_ptr(A.device))
         push.pushed(p)
@@ -317,19 +355,27 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
     Returns (out, col_sum or None, d_x0 or None); with ``push`` the output goes to the exchange slot
     (see gemm_rows_raw) and its local view is returned.  row_live: zeroed uint8 [M] that receives 1 for
     every output row holding a non-zero element.  push_live: uint8 [M], 0 for rows known to come out all-zero
-    (their A row is zero): those are not pushed to the peers."""
+    (their A row is zero): those are not pushed to the peers.  gate_f32: the relu output in the storage type of A
+    (gate = value > 0)."""
     _need_cuda(A, row_scale, add, gate_u8, gate_f32, d_x0, post_scale)
-    A, row_scale, add, gate_f32, post_scale = _f32c(A), _f32c(row_scale), _f32c(add), _f32c(gate_f32), _f32c(post_scale)
+    st = A.dtype
+    if st not in _STORAGE or wt.dtype != st:
+        raise TypeError(f'A is {st}, the weight operand {wt.dtype}')
+    A, row_scale, add, gate_f32, post_scale = A.contiguous(), _f32c(row_scale), _featc(add, st), _featc(gate_f32, st), \
+        _f32c(post_scale)
+    if d_x0 is not None and d_x0.dtype != st:
+        raise TypeError('d_x0 must have the storage type of A')
+    es = A.element_size()
     M, K = A.shape
     if K != wt.k:
         raise ValueError(f'A is [{M},{K}] but the weight operand is [{wt.n},{wt.k}]')
     N = wt.n
-    if push is not None and (push.width != N or push.local_rows != M):
+    if push is not None and (push.width != N or push.local_rows != M or push.dtype != st):
         raise ValueError('push: the exchange slot does not match the kernel output')
-    out = torch.empty((M, N), dtype=torch.float32, device=A.device) if push is None else push.local
+    out = torch.empty((M, N), dtype=st, device=A.device) if push is None else push.local
     col_sum = torch.empty(N, dtype=torch.float32, device=A.device) if want_col_sum else None
     if want_x0 and d_x0 is None:
-        d_x0, accumulate_x0 = torch.empty((M, N), dtype=torch.float32, device=A.device), False
+        d_x0, accumulate_x0 = torch.empty((M, N), dtype=st, device=A.device), False
     gate = gate_u8 if gate_u8 is not None else gate_f32
     ws_bytes = int(C.lib().cb_gemm_rows_grad_workspace_bytes(M, N)) if want_col_sum else 0
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=A.device) if ws_bytes else None
@@ -341,14 +387,16 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
         return out, (col_sum.zero_() if col_sum is not None else None), d_x0
     panels = [(0, N, None, out)] if push is None else \
         [(p * push.panel_width, push.panel_width, push.descs[p], push.panel_local[p]) for p in range(push.n_panels)]
+    fn, mma = 'cb_gemm_rows_grad' + _sfx(st), (6 if st == torch.float32 else 2)
+    wbytes = (2 if wt.lo is not None else 1) * es
     for p, (c0, w, desc, dst) in enumerate(panels):
         if desc is not None:
             desc.row_live = push_live.data_ptr() if push_live is not None else None
-        alg = 4 * (M * K + 2 * w * K + M * w * (1 + extra)) + (M * w if gate_u8 is not None else 0) + \
-            (push.pushed_rows * w * 4 if push is not None else 0)
-        with torch.cuda.device(A.device), _Timed('gemm_rows_grad_push' if push is not None else 'gemm_rows_grad', alg,
-                                                 A.device, flops=6 * M * w * K):
-            C.call('cb_gemm_rows_grad', C.ptr(A), M, K, K, _pofs(wt.hi, c0 * K), _pofs(wt.lo, c0 * K), w,
+        alg = es * (M * K + M * w * (1 + extra)) + wbytes * w * K + (M * w if gate_u8 is not None else 0) + \
+            (push.pushed_rows * w * es if push is not None else 0)
+        with torch.cuda.device(A.device), _Timed(('gemm_rows_grad_push' if push is not None else 'gemm_rows_grad') +
+                                                 _sfx(st), alg, A.device, flops=mma * M * w * K):
+            C.call(fn, C.ptr(A), M, K, K, *_weight_args(wt, c0, K), w,
                    C.ptr(row_scale), _pofs(add, c0), N, _pofs(gate_u8, c0), _pofs(gate_f32, c0),
                    N if gate is not None else 0, int(bool(mixed)), float(alpha), _pofs(d_x0, c0), N,
                    int(bool(accumulate_x0)), C.ptr(post_scale), C.ptr(dst), dst.shape[1], _pofs(col_sum, c0),
@@ -359,16 +407,21 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
     return out, col_sum, d_x0
 
 
-def gemm_tn_supported(M, Ka, Nb):
-    return bool(C.lib().cb_gemm_tn_supported(max(int(M), 1), int(Ka), int(Nb)))
+def gemm_tn_supported(M, Ka, Nb, dtype=torch.float32):
+    if dtype not in _STORAGE:
+        return False
+    return bool(getattr(C.lib(), 'cb_gemm_tn_supported' + _sfx(dtype))(max(int(M), 1), int(Ka), int(Nb)))
 
 
 def gemm_tn_raw(A, B, a_row_scale=None, b_row_scale=None):
-    """A^T @ B for row-major A [M, Ka], B [M, Nb] (the weight gradient), 3xTF32 on the tensor cores.
-    A per-row scale s[m] of either operand (sum_m s[m] A[m,:]^T B[m,:]) is applied while the operand is
-    split in shared memory."""
+    """A^T @ B for row-major A [M, Ka], B [M, Nb] (the weight gradient), fp32 result: fp32 operands -> 3xTF32, bf16
+    operands -> kind::f16 as stored.  A per-row scale s[m] of either operand (sum_m s[m] A[m,:]^T B[m,:]) is applied
+    while the fp32 operand is split in shared memory (the bf16 variant takes pre-scaled operands)."""
     _need_cuda(A, B, a_row_scale, b_row_scale)
-    A, B = _f32c(A), _f32c(B)
+    st = A.dtype
+    if st not in _STORAGE or B.dtype != st:
+        raise TypeError(f'operands must both be float32 or bfloat16, got {A.dtype} / {B.dtype}')
+    A, B = A.contiguous(), B.contiguous()
     if a_row_scale is not None and b_row_scale is not None:
         raise ValueError('one row scale at most')
     scale, scale_b = (_f32c(b_row_scale), 1) if b_row_scale is not None else (_f32c(a_row_scale), 0)
@@ -379,13 +432,30 @@ def gemm_tn_raw(A, B, a_row_scale=None, b_row_scale=None):
     if M == 0:
         return torch.zeros((Ka, Nb), dtype=torch.float32, device=A.device)
     out = torch.empty((Ka, Nb), dtype=torch.float32, device=A.device)
-    nb = int(C.lib().cb_gemm_tn_workspace_bytes(M, Ka, Nb))
+    nb = int(getattr(C.lib(), 'cb_gemm_tn_workspace_bytes' + _sfx(st))(M, Ka, Nb))
     ws = torch.empty(nb, dtype=torch.uint8, device=A.device)
-    alg = 4 * (M * Ka + M * Nb + Ka * Nb)
-    with torch.cuda.device(A.device), _Timed('gemm_tn', alg, A.device, flops=6 * M * Ka * Nb):
-        C.call('cb_gemm_tn', C.ptr(A), Ka, C.ptr(B), Nb, M, Ka, Nb, C.ptr(scale), scale_b, C.ptr(out), Nb,
-               C.ptr(ws), nb, C.stream_ptr(A.device))
+    alg = A.element_size() * (M * Ka + M * Nb) + 4 * Ka * Nb
+    mma = 6 if st == torch.float32 else 2
+    with torch.cuda.device(A.device), _Timed('gemm_tn' + _sfx(st), alg, A.device, flops=mma * M * Ka * Nb):
+        if st == torch.float32:
+            C.call('cb_gemm_tn', C.ptr(A), Ka, C.ptr(B), Nb, M, Ka, Nb, C.ptr(scale), scale_b, C.ptr(out), Nb,
+                   C.ptr(ws), nb, C.stream_ptr(A.device))
+        else:
+            if scale is not None:
+                raise ValueError('the bf16 weight-gradient kernel takes pre-scaled operands')
+            C.call('cb_gemm_tn_bf16', C.ptr(A), Ka, C.ptr(B), Nb, M, Ka, Nb, C.ptr(out), Nb, C.ptr(ws), nb,
+                   C.stream_ptr(A.device))
     return out
+
+
+def to_bf16_raw(x):
+    """bf16(x) for an fp32 tensor (cb_to_bf16, round to nearest even)."""
+    _need_cuda(x)
+    x = _f32c(x)
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        C.call('cb_to_bf16', C.ptr(x), x.numel(), C.ptr(y), C.stream_ptr(x.device))
+    return y
 
 
 # ---------------------------------------------------------------------------------------------
@@ -505,7 +575,7 @@ class BwdPlan:
         sink = self.x0_sink if self.want_x0 else None
         if add is not None and sink is not None and sink.buf is not None:
             return None     # the kernel keeps one [M, N] epilogue input: the caller runs the two-kernel path
-        slot = g.push_slot(C.CB_BY_SRC, wb.n)    # G is what the transposed aggregation gathers
+        slot = g.push_slot(C.CB_BY_SRC, wb.n, dtot_in.dtype)    # G is what the transposed aggregation gathers
         live = push_live = live_full = None
         if self.row_sparse_hint and slot is not None and add is None:
             # multi-GPU: a zero row of the incoming gradient gives a zero row of G -- known BEFORE the GEMM, so
@@ -576,7 +646,11 @@ def _w_as_kn(weight, layout):
 
 
 def _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, want_out, want_out2):
-    acc = x @ _w_as_kn(weight, layout)
+    """Library-GEMM path for the shapes the tcgen05 kernels do not cover; bf16 inputs: bf16 GEMM, fp32 epilogue."""
+    st = x.dtype
+    acc = x @ _w_as_kn(weight, layout).to(st)
+    if st != torch.float32:
+        acc = acc.float()
     if row_scale is not None:
         acc = acc * row_scale[:, None]
     if bias is not None:
@@ -585,24 +659,25 @@ def _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, 
         acc = acc + add
     if relu:
         acc = torch.relu(acc)
-    return (acc if want_out else None), (acc * out2_scale[:, None] if want_out2 else None)
+    out2 = (acc * out2_scale[:, None]).to(st) if want_out2 else None
+    return (acc.to(st) if want_out else None), out2
 
 
 class _Dense(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, add, row_scale, out2_scale, layout, relu, want_out, want_out2, dx_sink,
-                my_plan, dx_plan, push_graph):
-        ctx.dx_sink = dx_sink
+                my_plan, dx_plan, push_graph, add_sink):
+        ctx.dx_sink, ctx.add_sink = dx_sink, add_sink
         ctx.my_plan, ctx.dx_plan = my_plan, dx_plan
-        wt = split_weight(weight, transpose=(layout == 'kn'))
+        wt = split_weight(weight, transpose=(layout == 'kn'), dtype=x.dtype)
         # multi-GPU: the output is what the next aggregation gathers -> write it into the exchange buffer and
         # into the peers from the epilogue (graph.exchange() then only has to wait for everyone's pushes)
-        slot = push_graph.push_slot(C.CB_BY_DST, wt.n) if (push_graph is not None and want_out) else None
+        slot = push_graph.push_slot(C.CB_BY_DST, wt.n, x.dtype) if (push_graph is not None and want_out) else None
         res = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2, push=slot)
         out, out2 = res if want_out2 else (res, None)
         ctx.layout, ctx.relu = layout, relu
         ctx.has_bias, ctx.has_add = bias is not None, add is not None
-        need = any(ctx.needs_input_grad[:4])
+        need = any(ctx.needs_input_grad[:4]) or add_sink is not None
         keep_y = (out if out is not None else out2) if (relu and need) else None
         ctx.save_for_backward(x if need else None, weight if need else None, row_scale, out2_scale, keep_y)
         ctx.set_materialize_grads(False)
@@ -627,61 +702,82 @@ class _Dense(torch.autograd.Function):
         if dy2 is not None and dy2.dim() == 1:
             dy2 = None
         if dy is None and dy2 is None:
-            return (None,) * 14
+            return (None,) * 15
+        st = x.dtype
         done = ctx.my_plan.take_result() if ctx.my_plan is not None else None
         if done is not None:
             # the consumer's dX GEMM already applied the relu mask and summed the bias gradient
             dtot, d_bias = dy.contiguous(), done['d_bias']
         else:
             if dy2 is not None:
-                dy2 = dy2 * out2_scale[:, None]
+                dy2 = (dy2 * out2_scale[:, None]).to(st)
             dtot = dy2 if dy is None else (dy if dy2 is None else dy + dy2)
             if ctx.relu:
                 dtot = torch.where(y > 0, dtot, torch.zeros((), dtype=dtot.dtype, device=dtot.device))
             dtot = dtot.contiguous()
-            d_bias = dtot.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+            d_bias = dtot.sum(0, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         d_add = dtot if (ctx.has_add and ctx.needs_input_grad[3]) else None
+        if ctx.add_sink is not None:
+            # h = (D X) W + E: dL/dE is dL/dh itself.  Handed to the table's optimizer by reference (no autograd
+            # accumulation pass, no fp32 copy of a bf16 gradient): se_optim.FusedSEAdam reads it.
+            ctx.add_sink.grad = dtot
         M, K = x.shape
         N = dtot.shape[1]
         dx = dw = None
         if ctx.needs_input_grad[0]:
             parked = ctx.dx_sink.take() if ctx.dx_sink is not None else None   # other consumers' share of dx
             plan = ctx.dx_plan
-            if gemm_supported(M, K, N):
-                wb = split_weight(weight, transpose=(ctx.layout == 'nk'))
+            if gemm_supported(M, K, N, st):
+                wb = split_weight(weight, transpose=(ctx.layout == 'nk'), dtype=st)
                 dx = plan.run(dtot, wb, row_scale, parked) if (plan is not None and plan.kind is not None) else None
                 if dx is None:
                     dx = gemm_rows_raw(dtot, wb, row_scale=row_scale, add=parked)
             else:
-                dx = dtot @ _w_as_kn(weight, ctx.layout).t()
+                dx = dtot @ _w_as_kn(weight, ctx.layout).t().to(st)
                 if row_scale is not None:
-                    dx = dx * row_scale[:, None]
+                    dx = (dx * row_scale[:, None]).to(st)
                 if parked is not None:
                     dx = dx + parked
         if ctx.needs_input_grad[1]:
-            if gemm_tn_supported(M, K, N):
-                dw = gemm_tn_raw(x, dtot, a_row_scale=row_scale) if ctx.layout == 'kn' else \
-                    gemm_tn_raw(dtot, x, b_row_scale=row_scale)
+            if gemm_tn_supported(M, K, N, st):
+                if st != torch.float32 and row_scale is not None:
+                    # the bf16 kernel takes operands as stored: one extra [M, K] pass for the layer that reads an
+                    # unscaled input (layer 0 of the residual topologies); fp32 scale, one rounding
+                    xs, rs = (x.float() * row_scale[:, None]).to(st), None
+                else:
+                    xs, rs = x, row_scale
+                dw = gemm_tn_raw(xs, dtot, a_row_scale=rs) if ctx.layout == 'kn' else gemm_tn_raw(dtot, xs, b_row_scale=rs)
             else:
-                xs = x if row_scale is None else x * row_scale[:, None]
-                dw = xs.t() @ dtot if ctx.layout == 'kn' else dtot.t() @ xs
-        return dx, dw, d_bias, d_add, None, None, None, None, None, None, None, None, None, None
+                xs = x if row_scale is None else (x * row_scale[:, None]).to(st)
+                dw = (xs.t() @ dtot if ctx.layout == 'kn' else dtot.t() @ xs).float()
+        return dx, dw, d_bias, d_add, None, None, None, None, None, None, None, None, None, None, None
+
+
+class GradSlot:
+    """Receives the gradient of a non-autograd ``add`` operand of dense() (the SE table in fused-optimizer mode)."""
+    __slots__ = ('grad',)
+
+    def __init__(self):
+        self.grad = None
 
 
 def dense(x, weight, layout, bias=None, add=None, relu=False, row_scale=None, out2_scale=None, want_out=True,
-          want_out2=False, dx_sink=None, my_plan=None, dx_plan=None, push_graph=None):
+          want_out2=False, dx_sink=None, my_plan=None, dx_plan=None, push_graph=None, add_sink=None):
     """act(row_scale[:,None] * (x @ W) + bias + add); also out2_scale[:,None] * that when want_out2.
     layout 'kn': weight is [in, out] (GCNConv.weight, GCN.py:170); 'nk': [out, in] (nn.Linear.weight).
     my_plan / dx_plan: BwdPlan of this op's own backward prologue / of the op that produced ``x``.
+    add_sink: GradSlot that receives dL/d(add) when ``add`` is not an autograd leaf (fused SE optimizer).
     push_graph: node-sliced graph whose next aggregation gathers ``out`` (the exchange rides on the epilogue).
     Returns (out, out2); the one not asked for is None."""
     M, K = x.shape
     N = weight.shape[1] if layout == 'kn' else weight.shape[0]
-    if _dense_backend == 'tcgen05' and x.is_cuda and gemm_supported(M, N, K):
+    if _dense_backend == 'tcgen05' and x.is_cuda and gemm_supported(M, N, K, x.dtype):
         out, out2 = _Dense.apply(x, weight, bias, add, row_scale, out2_scale, layout, bool(relu), bool(want_out),
-                                 bool(want_out2), dx_sink, my_plan, dx_plan, push_graph)
+                                 bool(want_out2), dx_sink, my_plan, dx_plan, push_graph, add_sink)
         return (out if want_out else None), (out2 if want_out2 else None)
     _need_cuda(x)
+    if add_sink is not None:
+        raise RuntimeError('the fused SE optimizer needs the tcgen05 transform (shape not covered by cb_gemm_rows)')
     if my_plan is not None:   # library GEMM path: no fused backward prologue
         my_plan.kind = None
     return _dense_composite(x, weight, layout, bias, add, relu, row_scale, out2_scale, want_out, want_out2)
@@ -723,8 +819,8 @@ def aggregate_forward(graph, H, bias, x0, alpha, relu, want_out, want_scaled, wa
     shape, dev, pw = (graph.rows, ex.width), graph.device, ex.panel_width
 
     def make():
-        return (torch.empty(shape, dtype=torch.float32, device=dev) if want_out else None,
-                torch.empty(shape, dtype=torch.float32, device=dev) if want_scaled else None,
+        return (torch.empty(shape, dtype=H.dtype, device=dev) if want_out else None,
+                torch.empty(shape, dtype=H.dtype, device=dev) if want_scaled else None,
                 torch.empty(shape, dtype=torch.uint8, device=dev) if want_mask else None)
 
     return _panelled(graph, ex, make, lambda p, Hp, outs: agg_forward_raw(

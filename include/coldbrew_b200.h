@@ -106,6 +106,18 @@ int cb_graph_create_sliced(const int64_t* edge_index, int64_t num_edges, int64_t
                            int64_t row_begin, int64_t row_end, int hub_chunk, void* stream,
                            cb_graph_t** out);
 
+/*
+ * Same slice, built from the rank's OWN edges only (BASELINE.json configs[4]: 10^9 edges never exist as one list):
+ *   in_edges   [2, E_in]  every edge whose destination is in [row_begin, row_end)  -> BY_DST structure
+ *   out_edges  [2, E_out] every edge whose source is in [row_begin, row_end)       -> BY_SRC structure
+ * (row 0 = sources, row 1 = destinations, global ids).  For a symmetric graph out_edges is in_edges with its two
+ * rows swapped.  Stored order inside a row = order in the respective list; the perm arrays index that list.  An
+ * edge outside the owned range is an error (CB_E_RANGE).  Scratch is ~16 bytes per edge of one list at a time.
+ */
+int cb_graph_create_local(const int64_t* in_edges, int64_t num_in_edges, const int64_t* out_edges,
+                          int64_t num_out_edges, int64_t num_nodes, int64_t row_begin, int64_t row_end, int hub_chunk,
+                          void* stream, cb_graph_t** out);
+
 int cb_graph_destroy(cb_graph_t* g);
 int cb_graph_query(const cb_graph_t* g, int what, void* out);
 
@@ -190,6 +202,30 @@ int cb_agg_backward_prep(const cb_graph_t* g, const float* d_out, const float* d
                          float* G, float* d_bias, float* d_x0, int accumulate_x0, void* workspace,
                          int64_t workspace_bytes, void* stream);
 
+/* bf16 storage of every streamed matrix (d_out, d_out_scaled, relu_out, G, d_x0); same arithmetic in fp32 */
+int cb_agg_backward_prep_bf16(const cb_graph_t* g, const uint16_t* d_out, const uint16_t* d_out_scaled, int64_t d,
+                              const uint8_t* mask, const uint16_t* relu_out, int act, int mixed, double alpha,
+                              uint16_t* G, float* d_bias, uint16_t* d_x0, int accumulate_x0, void* workspace,
+                              int64_t workspace_bytes, void* stream);
+
+/*
+ * Optimizer step of one Structural-Embedding table (GCN.py:181-182 `self.le`; trainer_node_classification.py:310
+ * Adam(lr, weight_decay), :393-394 loss += se_reg * ||E||_F, :428-430 zero_grad / backward / step), one pass over
+ * the table instead of autograd's norm backward + gradient add + torch.optim.Adam's passes:
+ *   g  = grad[i] + reg_coef * E[i] / sqrt(*sumsq) + weight_decay * E[i]        (grad = dL/dh of the layer's transform:
+ *                                                                               h = (D X) W + E  =>  dL/dE = dL/dh)
+ *   m  = m + (1-beta1) (g - m);  v = beta2 v + (1-beta2) g^2                   (torch.optim.Adam, amsgrad off)
+ *   E -= lr / (1-beta1^step) * m / (sqrt(v) / sqrt(1-beta2^step) + eps)
+ *   shadow_bf16[i] = bf16(E[i])                                                (the copy a bf16 forward reads)
+ * grad: fp32 (CB_F32) or bf16 (CB_BF16) or NULL; sumsq: device scalar holding sum(E^2) over EVERY rank's rows as
+ * computed by this step's forward (cb_sumsq + all-reduce), or NULL for no regulariser; step counts from 1.
+ */
+int cb_se_adam_step(float* E, const void* grad, int grad_dtype, float* m, float* v, uint16_t* shadow_bf16, int64_t n,
+                    double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                    const float* sumsq, double reg_coef, void* stream);
+/* y = bf16(x), round to nearest even (initialises a shadow table; casts fp32 inputs of a bf16 forward) */
+int cb_to_bf16(const float* x, int64_t n, uint16_t* y, void* stream);
+
 /* y[r,:] = s[r] * x[r,:]   (GCN.py:205-213 `feat_src * norm`; also its adjoint) */
 int cb_row_scale(const float* x, const float* s, int64_t rows, int64_t d, float* y, void* stream);
 
@@ -219,10 +255,10 @@ typedef struct {
     int32_t n_peers;             /* 0 .. CB_MAX_PEERS */
     int32_t max_ctas;            /* > 0: cap the kernel's grid (a pushing kernel is NVLink-bound; the SMs it
                                     leaves free run the aggregation of the previous column panel) */
-    float* peer[CB_MAX_PEERS];   /* peer-mapped base of each remote [N_global, ld] buffer */
+    void* peer[CB_MAX_PEERS];    /* peer-mapped base of each remote [N_global, ld] buffer (element type of `out`) */
     const uint8_t* need;         /* [M] device: bit j set = remote j gathers local row m */
     int64_t row0;                /* global index of local row 0 */
-    int64_t ld;                  /* row pitch of the remote buffers, floats */
+    int64_t ld;                  /* row pitch of the remote buffers, elements */
     const uint8_t* row_live;     /* [M] device or NULL: rows with 0 are known to be all-zero and are not pushed
                                     (the receivers skip them with the same flags, cb_agg_gather row_live) */
 } cb_peer_push_t;
@@ -282,6 +318,25 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
                       void* stream);
 
 /*
+ * bf16 storage (BASELINE.json configs[4]): A, add, gate_val, d_x0, out, out2 and the weight operand Bt [N, K] hold
+ * bf16; the MMA is tcgen05.mma.kind::f16 on the operands as stored (no split: twice the TF32 rate, half the bytes),
+ * accumulation in fp32 in tensor memory, the same fp32 epilogues, one round-to-nearest-even at each store.
+ * K, lda multiples of 8; N and the epilogue pitches multiples of 4.  cb_gemm_weight_to_bf16 prepares Bt.
+ */
+int cb_gemm_weight_to_bf16(const float* W, int64_t n_rows, int64_t k_cols, int transpose, uint16_t* out, void* stream);
+int cb_gemm_rows_supported_bf16(int64_t M, int64_t N, int64_t K);
+int cb_gemm_rows_bf16(const uint16_t* A, int64_t M, int64_t K, int64_t lda, const uint16_t* Bt, int64_t N,
+                      const float* row_scale, const float* bias, const uint16_t* add, int64_t ld_add, int act,
+                      uint16_t* out, int64_t ld_out, const float* out2_scale, uint16_t* out2, int64_t ld_out2,
+                      const cb_peer_push_t* push, void* stream);
+int cb_gemm_rows_grad_bf16(const uint16_t* A, int64_t M, int64_t K, int64_t lda, const uint16_t* Bt, int64_t N,
+                           const float* row_scale, const uint16_t* add, int64_t ld_add, const uint8_t* gate_u8,
+                           const uint16_t* gate_val, int64_t ld_gate, int mixed, double alpha, uint16_t* d_x0,
+                           int64_t ld_dx0, int accumulate_x0, const float* post_scale, uint16_t* out, int64_t ld_out,
+                           float* col_sum, uint8_t* row_live, void* workspace, int64_t workspace_bytes,
+                           const cb_peer_push_t* push, void* stream);
+
+/*
  * Weight gradient on the tcgen05 tensor cores (3xTF32): out[Ka, Nb] = A[M, Ka]^T . B[M, Nb], the reduction
  * running over the M node rows (autograd of GCN.py:225: dW = (D X)^T dH; and of the Linear layers).
  * Split-K over the SMs with a fixed-order second pass, so the result is bit-stable from run to run.
@@ -296,6 +351,13 @@ int64_t cb_gemm_tn_workspace_bytes(int64_t M, int64_t Ka, int64_t Nb);
 int cb_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Nb,
                const float* row_scale, int scale_b, float* out, int64_t ld_out, void* workspace,
                int64_t workspace_bytes, void* stream);
+
+/* bf16 operands as stored (MN-major, SWIZZLE_128B, kind::f16), fp32 result; Ka, Nb multiples of 64; no row scale
+ * (a bf16 forward hands the pre-scaled copy on).  Same segmenting and fixed-order fp64 second pass. */
+int cb_gemm_tn_supported_bf16(int64_t M, int64_t Ka, int64_t Nb);
+int64_t cb_gemm_tn_workspace_bytes_bf16(int64_t M, int64_t Ka, int64_t Nb);
+int cb_gemm_tn_bf16(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Nb,
+                    float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
 int64_t cb_launch_count(void);

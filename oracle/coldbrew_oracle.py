@@ -513,6 +513,59 @@ def teacher_loss(model: OracleTeacherGNN, x, edge_index, y, train_mask, se_reg_c
     return loss
 
 
+# --------------------------------------------------------------------------------------
+# bf16 STORAGE restatement (BASELINE.json configs[4]: "128-dim bf16"): the reference arithmetic of the Initial
+# topology (GCN.py:91-142 with type_trick 'Initial', no norm layer, no dropout) with every matrix that the CUDA
+# path keeps in HBM rounded to bf16 where it is stored -- features, the SE tables as read by the forward pass, the
+# dense weights as fed to the tensor cores -- and every sum, scale, bias, relu and mix in fp32.  Gradients crossing
+# the same storage points are rounded too (the CUDA path keeps dlogits, G, dH and dX in bf16).
+# --------------------------------------------------------------------------------------
+class _RoundBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def rbf16(x):
+    """Value as stored in bf16 (round to nearest even), carried on in fp32; the gradient is rounded the same way."""
+    return _RoundBf16.apply(x)
+
+
+def bf16_storage_forward(model: 'OracleTeacherGNN', x: torch.Tensor, edge_index: torch.Tensor):
+    """logits [N, C] (fp32 values representable in bf16) and se_reg_all for an 'Initial' TeacherGNN."""
+    tc = model.model.model
+    a = tc.args
+    assert 'Initial' in a.type_trick and not contains_any(a.type_trick, _EXACT_NORM_NAMES + ('Jumping', 'Dense', 'Residual'))
+    n = x.shape[0]
+    dout_is, din_is = degree_inv_sqrt(edge_index, n)
+    lin0, head = tc.layers_MLP[0], tc.layers_MLP[-1]
+    x = rbf16(x)
+    x0 = rbf16(F.relu(x @ rbf16(lin0.weight).t() + lin0.bias))                 # GCN.py:104-107
+    cur_scaled, se_reg_all, out = None, None, None
+    for i in range(a.num_layers):
+        lyr = tc.layers_GCN[i]
+        w = rbf16(lyr.weight)
+        if cur_scaled is None:
+            h = dout_is.reshape(-1, 1) * (x0 @ w)                               # GCN.py:205-225 ((D X) W = D (X W))
+        else:
+            h = cur_scaled @ w
+        if lyr.has_se:
+            h = h + rbf16(lyr.le)                                               # GCN.py:231 (bf16 shadow of the table)
+            reg = torch.linalg.vector_norm(lyr.le, dtype=torch.float64).to(lyr.le.dtype)   # fp32 master
+            se_reg_all = reg if se_reg_all is None else se_reg_all + reg
+        h = rbf16(h)
+        z = aggregate_sum(h, edge_index, n) * din_is.reshape(-1, 1) + lyr.bias  # GCN.py:238-253
+        o = (1 - a.res_alpha) * F.relu(z) + a.res_alpha * x0                    # GCN.py:127-131, res_tricks.py:23
+        out = rbf16(o)
+        cur_scaled = rbf16(dout_is.reshape(-1, 1) * o)                          # next layer's (D X), stored
+    logits = rbf16(out @ rbf16(head.weight).t() + head.bias)                    # GCN.py:137-138
+    return logits, se_reg_all
+
+
 def make_args(**kw):
     """Namespace with the fields TricksComb/TeacherGNN read, reference defaults."""
     d = dict(type_trick='NoRes', type_model='GCN', num_layers=2, dim_hidden=64, num_feats=16, num_classes=7,

@@ -106,3 +106,35 @@ def test_need_masks_match_brute_force(tmp_path, world, n):
     """Host logic of the fused exchange: which local rows each peer gathers (dist.need_masks)."""
     mp.spawn(_need_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f'need{r}') for r in range(world))
+
+
+def _shard_worker(rank, world, port, n, und, out_dir):
+    from gnn_tail_generalization_b200 import synth
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        ei = synth.powerlaw_graph_sharded(n, und, rank, world, seed=5, device='cpu')
+        lo, hi = cbdist.slice_bounds(n, world, rank)
+        src, dst = ei
+        assert bool(((dst >= lo) & (dst < hi)).all())                      # every in-edge sits at the owner of its dst
+        key = dst * n + src
+        assert bool((key[1:] > key[:-1]).all())                            # sorted by (dst, src), no duplicates
+        torch.save(ei, os.path.join(out_dir, f'shard{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n,und', [(2, 3001, 12000), (3, 500, 4000)])
+def test_sharded_generator_builds_one_canonical_graph(tmp_path, world, n, und):
+    """synth.powerlaw_graph_sharded (configs[4]'s per-shard generation): the union of the shards is symmetric, free of
+    duplicates, has exactly one self loop per node and the requested size."""
+    mp.spawn(_shard_worker, args=(world, _free_port(), n, und, str(tmp_path)), nprocs=world, join=True)
+    ei = torch.cat([torch.load(tmp_path / f'shard{r}.pt') for r in range(world)], 1)
+    src, dst = ei
+    assert int((src == dst).sum()) == n and torch.equal(torch.sort(src[src == dst]).values, torch.arange(n))
+    fwd, bwd = dst * n + src, src * n + dst
+    assert torch.unique(fwd).numel() == fwd.numel()
+    assert torch.equal(torch.sort(fwd).values, torch.sort(bwd).values)      # symmetric
+    assert abs(ei.shape[1] - (2 * und + n)) <= 2 * world
+    deg = torch.bincount(dst, minlength=n)
+    assert int(deg.max()) > 20 * int(deg.median())                           # power law: hubs exist

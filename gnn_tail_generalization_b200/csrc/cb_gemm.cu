@@ -1168,11 +1168,12 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             float* part = g.partial + (size_t)sg * g.ka * g.nb;
             for (int h = 0; h < halves; ++h) {
                 const int row = h * 128 + q * 32 + lane;
-                for (int j = 0; j < g.gb; ++j) {
+                const int n_slabs = g.nb >> 5;          // 32 accumulator columns per tcgen05.ld
+                for (int j = 0; j < n_slabs; ++j) {
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + j * 32), r);
                     tmem_ld_wait();
-                    if (h == halves - 1 && j == g.gb - 1) {
+                    if (h == halves - 1 && j == n_slabs - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(drained_bar);

@@ -417,7 +417,8 @@ static int agg_forward_impl(const cb_graph* g, int dtype, const void* H, int64_t
                             int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream) {
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_forward: graph is NULL");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_forward: d must be positive");
-    CB_REQUIRE(g->rows == 0 || H != nullptr, CB_E_INVALID, "cb_agg_forward: H is NULL");
+    if (g->rows == 0) return CB_OK;       // a slice that owns no rows: nothing to aggregate (buffers may be NULL)
+    CB_REQUIRE(H != nullptr, CB_E_INVALID, "cb_agg_forward: H is NULL");
     CB_REQUIRE(out != nullptr || out_scaled != nullptr, CB_E_INVALID, "cb_agg_forward: no output buffer");
     CB_REQUIRE(act == CB_ACT_NONE || act == CB_ACT_RELU, CB_E_INVALID, "cb_agg_forward: unknown activation");
     CB_REQUIRE((ld_h == 0 || ld_h >= d) && (ld_out == 0 || ld_out >= d), CB_E_INVALID,
@@ -446,7 +447,8 @@ static int agg_gather_impl(const cb_graph* g, int side, int dtype, const void* X
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_gather: graph is NULL");
     CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_agg_gather: unknown side");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_gather: d must be positive");
-    CB_REQUIRE(g->rows == 0 || (X != nullptr && out != nullptr), CB_E_INVALID, "cb_agg_gather: NULL buffer");
+    if (g->rows == 0) return CB_OK;
+    CB_REQUIRE(X != nullptr && out != nullptr, CB_E_INVALID, "cb_agg_gather: NULL buffer");
     CB_REQUIRE((ld_x == 0 || ld_x >= d) && (ld_out == 0 || ld_out >= d), CB_E_INVALID,
                "cb_agg_gather: a row pitch is smaller than d");
     AggArgs a{};

@@ -465,6 +465,10 @@ static int backward_prep_impl(const cb_graph_t* g, int dtype, const void* d_out,
     using namespace cb;
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_backward_prep: graph is NULL");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_backward_prep: d must be positive");
+    if (g->rows == 0) {                   // a slice that owns no rows: the bias gradient is zero, nothing else exists
+        if (d_bias) CB_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)d * sizeof(float), (cudaStream_t)stream));
+        return CB_OK;
+    }
     CB_REQUIRE(d_out != nullptr || d_out_scaled != nullptr, CB_E_INVALID, "cb_agg_backward_prep: no incoming gradient");
     CB_REQUIRE(G != nullptr, CB_E_INVALID, "cb_agg_backward_prep: G is NULL");
     CB_REQUIRE(act == CB_ACT_NONE || mask != nullptr || relu_out != nullptr, CB_E_INVALID,

@@ -1347,7 +1347,14 @@ static void tn_plan(int64_t M, int64_t* chunks, int* seg_chunks, int64_t* n_segs
     const int64_t ch = ceil_div(M, Tn<S>::BKR);
     const int sms = sm_count();
     int64_t sc = ceil_div(ch, sms);
-    static const int64_t max_sc = getenv("CB_TN_SEG_CHUNKS") ? atoll(getenv("CB_TN_SEG_CHUNKS")) : TN_MAX_SEG_CHUNKS;
+    // Chain length vs workspace.  The accumulator error grows with the number of MMAs chained into one TMEM
+    // accumulation (measured on B200, fp32 operands, M = 1.7e5: max error / sum|a||b| = 3.2e-7 / 6.8e-7 / 4.4e-6 for
+    // segments of 4 / 16 / 64 chunks; cuBLAS sgemm: 2.4e-6), every segment costs one [Ka, Nb] partial in HBM.  Up to
+    // 8 segments per SM the segments stay at <= 16 chunks (256 rows); beyond that they grow to the cap of 64 chunks
+    // (the partials of BASELINE configs[3], 10^7 rows, are then 12 % of the operand bytes).
+    static const int64_t forced = getenv("CB_TN_SEG_CHUNKS") ? atoll(getenv("CB_TN_SEG_CHUNKS")) : 0;
+    int64_t max_sc = forced > 0 ? forced : ceil_div(ch, (int64_t)8 * sms);
+    if (forced <= 0) max_sc = max_sc < 16 ? 16 : (max_sc > TN_MAX_SEG_CHUNKS ? TN_MAX_SEG_CHUNKS : max_sc);
     if (sc > max_sc) sc = max_sc;
     if (sc < 1) sc = 1;
     *chunks = ch;

@@ -748,8 +748,16 @@ class _Dense(torch.autograd.Function):
                     xs, rs = x, row_scale
                 dw = gemm_tn_raw(xs, dtot, a_row_scale=rs) if ctx.layout == 'kn' else gemm_tn_raw(dtot, xs, b_row_scale=rs)
             else:
-                xs = x if row_scale is None else (x * row_scale[:, None]).to(st)
-                dw = (xs.t() @ dtot if ctx.layout == 'kn' else dtot.t() @ xs).float()
+                group = 32 if st == torch.float32 else 64
+                Kp, Np = -(-K // group) * group, -(-N // group) * group
+                xs = x if row_scale is None else (x.float() * row_scale[:, None]).to(st)
+                if gemm_tn_supported(M, Kp, Np, st):
+                    # whole 128-byte feature groups for the tensor-core kernel: zero columns, sliced off the result
+                    xs = torch.nn.functional.pad(xs, (0, Kp - K)) if Kp != K else xs
+                    dp = torch.nn.functional.pad(dtot, (0, Np - N)) if Np != N else dtot
+                    dw = gemm_tn_raw(xs, dp)[:K, :N] if ctx.layout == 'kn' else gemm_tn_raw(dp, xs)[:N, :K]
+                else:
+                    dw = (xs.t() @ dtot if ctx.layout == 'kn' else dtot.t() @ xs).float()
         return dx, dw, d_bias, d_add, None, None, None, None, None, None, None, None, None, None, None
 
 
@@ -771,10 +779,29 @@ def dense(x, weight, layout, bias=None, add=None, relu=False, row_scale=None, ou
     Returns (out, out2); the one not asked for is None."""
     M, K = x.shape
     N = weight.shape[1] if layout == 'kn' else weight.shape[0]
-    if _dense_backend == 'tcgen05' and x.is_cuda and gemm_supported(M, N, K, x.dtype):
+    tc = _dense_backend == 'tcgen05' and x.is_cuda and x.dtype in _STORAGE
+    group = 32 if x.dtype == torch.float32 else 64      # feature group (128 bytes) of the weight-gradient kernel
+    if tc and gemm_supported(M, N, K, x.dtype):
         out, out2 = _Dense.apply(x, weight, bias, add, row_scale, out2_scale, layout, bool(relu), bool(want_out),
                                  bool(want_out2), dx_sink, my_plan, dx_plan, push_graph, add_sink)
         return (out if want_out else None), (out2 if want_out2 else None)
+    Kp, Np = -(-K // group) * group, -(-N // group) * group
+    if tc and add_sink is None and gemm_supported(M, Np, Kp, x.dtype):
+        # Ragged widths (Cora F = 1433 / C = 7, Pubmed C = 3): TMA needs 16-byte row pitches and the epilogue 4-element
+        # accesses, so the operands are zero-padded to the next 128-byte feature group (autograd slices the gradients
+        # back) and the SAME tensor-core kernels run -- no library GEMM.  The padded layer keeps its own backward
+        # prologue (no hand-off plans, no epilogue push).  Widths the rows kernels take but the weight-gradient kernel
+        # does not (Pubmed F = 500, ogbn-arxiv C = 40) are padded inside _Dense.backward only.
+        F = torch.nn.functional
+        xp = F.pad(x, (0, Kp - K)) if Kp != K else x
+        wp = F.pad(weight, (0, Np - N, 0, Kp - K)) if layout == 'kn' else F.pad(weight, (0, Kp - K, 0, Np - N))
+        bp = F.pad(bias, (0, Np - N)) if (bias is not None and Np != N) else bias
+        ap = F.pad(add, (0, Np - N)) if (add is not None and Np != N) else add
+        if my_plan is not None:
+            my_plan.kind = None
+        out, out2 = _Dense.apply(xp, wp, bp, ap, row_scale, out2_scale, layout, bool(relu), bool(want_out),
+                                 bool(want_out2), None, None, None, None, None)
+        return (out[:, :N] if want_out else None), (out2[:, :N] if want_out2 else None)
     _need_cuda(x)
     if add_sink is not None:
         raise RuntimeError('the fused SE optimizer needs the tcgen05 transform (shape not covered by cb_gemm_rows)')

@@ -253,3 +253,40 @@ def test_compacted_gather_bit_identical_incl_hub_rows(d, frac, dtype):
         off = al((n + 1) * 8) + 2 * al((nch + 1) * 8)
         got_col = ws[off:off + 4 * int(want_col.numel())].view(torch.int32)
         assert torch.equal(got_col, want_col)
+
+
+@pytest.mark.parametrize('M,K,N,layout', [(2708, 1433, 64, 'nk'), (2708, 64, 7, 'kn'), (1900, 500, 256, 'nk'),
+                                          (1900, 256, 3, 'nk'), (5000, 256, 40, 'nk'), (700, 9, 10, 'kn')])
+def test_ragged_widths_stay_on_the_tensor_core_kernels(M, K, N, layout):
+    """BASELINE configs[0..2] widths (Cora 1433 -> 64 -> 7, Pubmed 500 / 3, ogbn-arxiv 40): ops.dense pads to whole
+    128-byte feature groups instead of handing the GEMM to cuBLAS; forward and all three gradients against fp64."""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(M + K + N)
+    x = torch.randn(M, K, device='cuda', generator=g, requires_grad=True)
+    W = (torch.randn((K, N) if layout == 'kn' else (N, K), device='cuda', generator=g) / K ** 0.5).requires_grad_(True)
+    b = torch.randn(N, device='cuda', generator=g, requires_grad=True)
+    rs = torch.rand(M, device='cuda', generator=g) + 0.5
+    sink = []
+    ops.set_timing_sink(sink)
+    out, _ = ops.dense(x, W, layout, bias=b, relu=True, row_scale=rs)
+    dy = torch.randn(M, N, device='cuda', generator=g)
+    out.backward(dy)
+    ops.set_timing_sink(None)
+    names = [s[0] for s in sink]
+    assert names.count('gemm_rows') == 2 and names.count('gemm_tn') == 1, names      # fwd, dX, dW: all ours
+    xd, Wd, bd = x.detach().double().requires_grad_(True), W.detach().double().requires_grad_(True), \
+        b.detach().double().requires_grad_(True)
+    ref = torch.relu(rs.double()[:, None] * (xd @ (Wd if layout == 'kn' else Wd.t())) + bd)
+    ref.backward(dy.double())
+    # the bound of the tensor-core kernels everywhere in this file: 2e-6 of sum |a||b| (K = 1433 makes a long chain)
+    Wkn = (W if layout == 'kn' else W.t()).detach().double().abs()
+    bound = 3e-6 * (rs.double()[:, None] * (x.detach().double().abs() @ Wkn) + b.detach().double().abs()) + 1e-6
+    assert out.shape == (M, N) and bool(((out.double() - ref).abs() <= bound).all()), float((out.double() - ref).abs().max())
+    gate = (ref > 0).double() * dy.double().abs() * rs.double()[:, None]
+    bx = 3e-6 * (gate @ Wkn.t()) + 1e-6
+    bw = 3e-6 * (x.detach().double().abs().t() @ gate) + 1e-6
+    if layout == 'nk':
+        bw = bw.t()
+    assert x.grad.shape == xd.grad.shape and bool(((x.grad.double() - xd.grad).abs() <= bx).all())
+    assert W.grad.shape == Wd.grad.shape and bool(((W.grad.double() - Wd.grad).abs() <= bw).all())
+    assert float((b.grad.double() - bd.grad).abs().max()) <= 2e-5 * max(1.0, float(bd.grad.abs().max()))

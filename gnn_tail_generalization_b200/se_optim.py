@@ -96,7 +96,9 @@ class FusedSEAdam:
                 if g.shape != st.master.shape or not g.is_contiguous():
                     raise RuntimeError('FusedSEAdam: gradient layout does not match the table')
             dev = st.master.device
-            with torch.cuda.device(dev):
+            n = st.master.numel()
+            alg = n * (24 + (2 if st.shadow is not None else 0) + (0 if g is None else g.element_size()))
+            with torch.cuda.device(dev), ops._Timed('se_adam_step', alg, dev):
                 C.call('cb_se_adam_step', C.ptr(st.master), C.ptr(g),
                        C.CB_BF16 if (g is not None and g.dtype == torch.bfloat16) else C.CB_F32, C.ptr(st.m), C.ptr(st.v),
                        C.ptr(st.shadow), st.master.numel(), self.lr, self.betas[0], self.betas[1], self.eps,

@@ -431,13 +431,21 @@ class OracleTricksComb(nn.Module):
         else:
             self.layers_MLP.append(nn.Linear(H, C))
 
-    def forward(self, x, edge_index, want_les=False):
+    def forward(self, x, edge_index, want_les=False, relu_masks=None):
+        """relu_masks (tests only): a list of 0/1 tensors, consumed in order, that replace every ``F.relu(v)`` by
+        ``v * mask`` -- the gates of ANOTHER run of the same model.  A pre-activation within rounding distance of 0
+        gates differently in fp32 and fp64; with the gates pinned, a gradient comparison measures the arithmetic and
+        not the handful of flipped gates."""
         a, t = self.args, self.args.type_trick
         n = x.shape[0]
         xs, les, se_reg_all = [], [], None
+        masks = list(relu_masks) if relu_masks is not None else None
+
+        def relu(v):
+            return F.relu(v) if masks is None else v * masks.pop(0).to(v.dtype)
         if self.has_residual_MLP:                                                         # GCN.py:103-107
             x = F.dropout(x, p=a.dropout, training=self.training)
-            x = F.relu(self.layers_MLP[0](x))
+            x = relu(self.layers_MLP[0](x))
             xs.append(x)
         for i in range(a.num_layers):                                                     # GCN.py:109-131
             x = F.dropout(x, p=a.dropout, training=self.training)
@@ -450,7 +458,7 @@ class OracleTricksComb(nn.Module):
             if want_les:
                 les.append(x.clone().detach())
             if self.has_residual_MLP or i < a.num_layers - 1:
-                x = F.relu(x)
+                x = relu(x)
             xs.append(x)
             if contains_any(t, ('Initial', 'Dense', 'Residual')):
                 x = self.layers_res[i](xs)

@@ -356,18 +356,80 @@ def test_config_shapes_match_oracle(cfg):
         ours = float((p.grad.cpu().double() - rg64[k].grad).abs().max()) / scale
         cpu32 = float((rg[k].grad.double() - rg64[k].grad).abs().max()) / scale
         worst[k] = (ours, cpu32)
-        # Bars (fraction of the largest entry of the gradient; measured values in profiles/r02_summary.md):
-        #   * 1e-4 -- the logit bar of north_star carried over -- for everything whose reduction is short;
-        #   * 3e-4 for the weight gradients, which reduce ~1e5 rows through tensor-core accumulation chains: the
-        #     accumulator's biased rounding leaves 7e-7 of sum|a||b| (cuBLAS sgemm: 2.4e-6) and these entries are what
-        #     is left of sum|a||b| after a ~400-fold cancellation (random-sign gradients);
-        #   * where the fp32 CPU oracle itself is further than that from fp64 (cfg2: 2.2e-4 and 7.4e-4 on two weight
-        #     matrices whose entries are the remainder of ~2e4 cancelling fp32 products -- the error is in the fp32
-        #     operands, not in either summation), 2.5x the oracle's own distance.
-        bar = 3e-4 if (k.endswith('weight') and p.dim() == 2) else 1e-4
+        # UNPINNED relu gates: a handful of pre-activations within 1e-5 of zero gate differently in this fp32 path and in
+        # fp64, and each flip is worth ~1e-3 of the largest entry of a cancelling reduction (see
+        # test_config_shapes_gradients_with_pinned_relu_gates, which pins them and holds 1e-4).  Here: 1e-2, as before.
+        bar = 1e-2
         assert ours <= max(bar, 2.5 * cpu32) + 1e-7 / scale, (k, ours, cpu32)
     print(cfg, 'max grad error / largest entry (ours vs fp64, fp32 CPU oracle vs fp64):',
           {k.split('model.model.')[-1]: (f'{a:.1e}', f'{b:.1e}') for k, (a, b) in worst.items()})
+
+
+@pytest.mark.parametrize('cfg', sorted(CONFIG_SHAPES))
+def test_config_shapes_gradients_with_pinned_relu_gates(cfg):
+    """The gradient ARITHMETIC of the CUDA path at the BASELINE shapes against the fp64 oracle, with the relu gates
+    of the fp64 run pinned to the ones the CUDA forward took.
+
+    Why pinned: on ogbn-arxiv shape ~4e6 pre-activations belong to train rows; the 3xTF32 transform is ~1e-5 away
+    from fp64, so a few tens of them land on the other side of zero.  One flipped gate moves a bias-gradient entry
+    (a sum of ~1.7e4 cancelling terms) by ~1e-3 of the largest entry -- measured unpinned: 1.3e-3 / 1.5e-3 on
+    layers_GCN.1.{weight,bias}, 6e-3 on layers_MLP.0.weight, while every GEMM involved is within 1e-6 of fp64
+    (scripts/grad_error_probe.py, scripts/gemm_k40_probe.py).  With the gates pinned what is left is the summation
+    and GEMM error, and the bar is north_star's 1e-4 of the largest entry."""
+    from gnn_tail_generalization_b200 import ops
+    c = CONFIG_SHAPES[cfg]
+    torch.manual_seed(3)
+    ei = O.powerlaw_graph(c['n'], c['und'], seed=0)
+    kw = dict(type_trick=c['trick'], whetherHasSE=c['se'], num_layers=2, dim_hidden=c['H'], num_feats=c['F'],
+              num_classes=c['C'], N_nodes=c['n'], dataset=c['ds'], res_alpha=0.1)
+    ref64 = O.OracleTeacherGNN(O.make_args(**kw), None)
+    a = O.make_args(**kw)
+    a.device = DEV
+    model = _teacher(a)
+    model.load_state_dict(ref64.state_dict(), strict=True)
+    model.to(DEV).train()
+    ref64.double().train()
+    x = torch.randn(c['n'], c['F'], generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, c['C'], (c['n'],), generator=torch.Generator().manual_seed(2))
+    mask = torch.zeros(c['n'], dtype=torch.bool)
+    mask[: c['n'] // 10] = True
+    tc = model.model.model
+    xg, eg = x.to(DEV), ei.to(DEV)
+    # CUDA run with the pre-activations exposed (want_les: relu and the residual mix run as torch ops on the kernels'
+    # outputs; transforms, aggregations and their adjoints are the same kernels as on the fused path)
+    logits, se_reg, les = tc.forward(xg, eg, want_les=True)
+    loss = F.nll_loss(F.log_softmax(logits[mask.to(DEV)], 1), y.to(DEV)[mask.to(DEV)])
+    if se_reg is not None:
+        loss = loss + 0.5 * se_reg
+    loss.backward()
+    L, H = 2, c['H']
+    gates = []
+    if tc.has_residual_MLP:
+        with torch.no_grad():
+            lin = tc.layers_MLP[0]
+            x0, _ = ops.dense(xg, lin.weight, 'nk', bias=lin.bias, relu=True)
+        gates.append((x0 > 0).cpu())
+    widths = [H] * (L if tc.has_residual_MLP else L - 1)
+    off = 0
+    for w in widths:                                  # les = cat of every layer's pre-activation (GCN.py:124-125)
+        gates.append((les[:, off:off + w] > 0).cpu())
+        off += w
+    out64, reg64 = ref64.model.model(x.double(), ei, relu_masks=gates)
+    l64 = F.nll_loss(F.log_softmax(out64[mask], 1), y[mask])
+    if reg64 is not None:
+        l64 = l64 + 0.5 * reg64
+    l64.backward()
+    assert float(loss) == pytest.approx(float(l64), rel=2e-6)
+    rg64 = dict(ref64.named_parameters())
+    worst = {}
+    for k, p in model.named_parameters():
+        if rg64[k].grad is None:
+            continue
+        scale = max(1e-6, float(rg64[k].grad.abs().max()))
+        worst[k.split('model.model.')[-1]] = float((p.grad.cpu().double() - rg64[k].grad).abs().max()) / scale
+    print(cfg, 'pinned gates, max grad error / largest entry:', {k: f'{v:.1e}' for k, v in worst.items()})
+    for k, v in worst.items():
+        assert v <= 1e-4, (k, v)
 
 
 def test_zero_in_degree_raises_dglerror():

@@ -260,7 +260,10 @@ def run_ours(a):
         graph = cbdist.SlicedGraph(ei, N, rank, world)
     del ei
     if a.panels <= 0:
-        a.panels = 4 if world >= 8 else 1
+        # panels pay where the push dominates AND a panel row is still a decent gather: 4 x 256-byte rows at cfg4 on
+        # 8 GPUs (measured: 48.2 -> 44.7 ms); a 128-dim bf16 row cut in 4 is 64 bytes per gather (cfg5, measured:
+        # 220.6 ms with 4 panels)
+        a.panels = 4 if (world >= 8 and d * es // 4 >= 256) else 1
     if world > 1 and a.exchange == 'push':
         try:
             graph.enable_push(d, a.panels, a.push_ctas, elem_bytes=es)

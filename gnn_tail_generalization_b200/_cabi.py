@@ -47,6 +47,7 @@ SYMBOLS = {
     'cb_agg_gather': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_agg_forward_bf16': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_agg_gather_bf16': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    'cb_agg_propagate': (_int, [_vp, _int, _vp, _i64, _vp, _vp, _dbl, _dbl, _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp]),
     'cb_graph_live_workspace_bytes': (_i64, [_vp, _int]),
     'cb_graph_compact_live': (_int, [_vp, _int, _vp, _vp, _i64, _vp]),
     'cb_agg_gather_compacted': (_int, [_vp, _int, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
@@ -83,6 +84,8 @@ SYMBOLS = {
     'cb_gemm_tn_supported_bf16': (_int, [_i64, _i64, _i64]),
     'cb_gemm_tn_workspace_bytes_bf16': (_i64, [_i64, _i64, _i64]),
     'cb_gemm_tn_bf16': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
+    'cb_topk_merge': (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _int, _vp]),
+    'cb_topk_softmax_mix': (_int, [_vp, _vp, _i64, _int, _vp, _i64, _i64, _vp, _vp]),
     'cb_launch_count': (_i64, []),
 }
 

@@ -51,6 +51,9 @@ struct AggArgs {
     // the association of the uncompacted walk) and chunk_end bounds each chunk explicitly
     const int64_t* hub_rowptr;  // null: rowptr
     const int64_t* chunk_end;   // null: min(chunk_beg + hub_chunk, row end)
+    // label-propagation epilogue (cb_agg_propagate): out = clamp(one_minus_alpha * r + alpha * x0, lo, hi)
+    int clamp;
+    float clamp_lo, clamp_hi;
 };
 
 template <int VEC>
@@ -195,6 +198,7 @@ __device__ __forceinline__ void epilogue_store(const AggArgs& a, int64_t row, in
         z[i] = t;
         float r = (a.act == CB_ACT_RELU) ? fmaxf(t, 0.f) : t;
         if (a.x0) r = __fadd_rn(__fmul_rn(a.one_minus_alpha, r), __fmul_rn(a.alpha, x0[i]));
+        if (a.clamp) r = fminf(fmaxf(r, a.clamp_lo), a.clamp_hi);
         o[i] = r;
     }
     if (a.out) Elem<S, VEC>::store(a.out, off, o);
@@ -501,6 +505,36 @@ int cb_agg_gather_compacted(const cb_graph_t* g, int side, int dtype, const void
     CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_agg_gather_compacted: unknown dtype");
     return cb::agg_gather_impl(g, side, dtype, X, ld_x, d, row_scale, nullptr, out, ld_out, workspace,
                                workspace_bytes, stream, live_ws);
+}
+
+int cb_agg_propagate(const cb_graph_t* g, int side, const float* X, int64_t d, const float* row_scale, const float* y,
+                     double c_agg, double c_y, int clamp, double clamp_lo, double clamp_hi, float* out,
+                     const float* out2_scale, float* out2, void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace cb;
+    CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_propagate: graph is NULL");
+    CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_agg_propagate: unknown side");
+    CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_propagate: d must be positive");
+    if (g->rows == 0) return CB_OK;
+    CB_REQUIRE(X != nullptr && y != nullptr && (out != nullptr || out2 != nullptr), CB_E_INVALID,
+               "cb_agg_propagate: NULL buffer");
+    CB_REQUIRE(!out2 || out2_scale, CB_E_INVALID, "cb_agg_propagate: out2 needs out2_scale");
+    AggArgs a{};
+    a.X = X;
+    a.d = d;
+    a.x_ld = d;
+    a.o_ld = d;
+    a.row_scale = row_scale;
+    a.act = CB_ACT_NONE;
+    a.x0 = y;
+    a.one_minus_alpha = (float)c_agg;
+    a.alpha = (float)c_y;
+    a.clamp = clamp;
+    a.clamp_lo = (float)clamp_lo;
+    a.clamp_hi = (float)clamp_hi;
+    a.out = out;
+    a.out2_scale = out2_scale;
+    a.out2 = out2;
+    return run_agg(g, side, CB_F32, a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int cb_agg_gather_bf16(const cb_graph_t* g, int side, const uint16_t* X, int64_t ld_x, int64_t d,

@@ -170,6 +170,21 @@ int cb_agg_gather_bf16(const cb_graph_t* g, int side, const uint16_t* X, int64_t
                        int64_t workspace_bytes, void* stream);
 
 /*
+ * One label-propagation / outcome-correlation iteration in one kernel (Label_propagation_model/
+ * outcome_correlation.py:139-145: result = alpha * (adj @ result); result += (1 - alpha) * y; result = post_step(result)
+ * with adj = D^-1/2 A D^-1/2 | D^-1 A | A D^-1, outcome_correlation.py:50-54).  The edge values of adj are products of
+ * per-node factors, so adj @ x is the unit-weight gather between two row scalings and no edge-value array exists:
+ *   v[r,:]    = c_agg * (row_scale ? row_scale[r] : 1) * sum_{j in row r} X[col[j],:]  +  c_y * y[r,:]
+ *   v         = clamp ? min(max(v, clamp_lo), clamp_hi) : v
+ *   out[r,:]  = v                                   (if out)
+ *   out2[r,:] = out2_scale[r] * v                   (if out2: the pre-scaled iterate the next step gathers)
+ * X: [N_global, d] fp32, y / out / out2: [rows, d] fp32, contiguous.
+ */
+int cb_agg_propagate(const cb_graph_t* g, int side, const float* X, int64_t d, const float* row_scale, const float* y,
+                     double c_agg, double c_y, int clamp, double clamp_lo, double clamp_hi, float* out,
+                     const float* out2_scale, float* out2, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Row-sparse gather without walking the dead columns.  cb_graph_compact_live builds, in the caller's workspace
  * (cb_graph_live_workspace_bytes, 256-byte aligned), a second CSR of one side that keeps only the columns s with
  * row_live[s] != 0, in the stored order; cb_agg_gather_compacted then gathers over it (dtype CB_F32 / CB_BF16 of X
@@ -358,6 +373,20 @@ int cb_gemm_tn_supported_bf16(int64_t M, int64_t Ka, int64_t Nb);
 int64_t cb_gemm_tn_workspace_bytes_bf16(int64_t M, int64_t Ka, int64_t Nb);
 int cb_gemm_tn_bf16(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int64_t M, int64_t Ka, int64_t Nb,
                     float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * SEMLP "virtual neighbour" replacement (MLP_model/__init__.py:143-156: per node, le_guess[i] . teacherSE^T -> the K
+ * largest scores -> soft-max -> weighted sum of those K teacher rows) without the [B, N] score matrix:
+ *   cb_topk_merge        folds one score tile [B, width] (row pitch ld; column c is teacher row col_base + c; computed
+ *                        by cb_gemm_rows with the teacher table as the weight operand) into the running per-row lists
+ *                        top_val / top_idx [B, 32] (descending; first != 0 starts them).  K <= 32.
+ *   cb_topk_softmax_mix  out[b,:] = sum_k softmax(top_val[b,:K])[k] * table[top_idx[b,k],:], added in ascending score
+ *                        order like the reference's [1, K] x [K, d] product.
+ */
+int cb_topk_merge(const float* scores, int64_t B, int64_t width, int64_t ld, int64_t col_base, int K, float* top_val,
+                  int32_t* top_idx, int first, void* stream);
+int cb_topk_softmax_mix(const float* top_val, const int32_t* top_idx, int64_t B, int K, const float* table, int64_t d,
+                        int64_t ld_table, float* out, void* stream);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
 int64_t cb_launch_count(void);

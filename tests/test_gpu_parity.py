@@ -654,5 +654,23 @@ def test_label_propagation_matches_edge_valued_spmm(mode):
     for _ in range(iters):
         want = torch.clamp(alpha * torch.sparse.mm(adj, want) + (1 - alpha) * y, 0, 1)
     g = G.GraphHandle(ei.to(DEV), n)
+    from gnn_tail_generalization_b200 import ops
+    sink = []
+    ops.set_timing_sink(sink)
     got = LP.label_propagation(g, labels.to(DEV), idx.to(DEV), alpha, iters, mode)
+    ops.set_timing_sink(None)
+    # one kernel per iteration (cb_agg_propagate: source factor on the iterate, destination factor, axpy and clamp in
+    # the gather's epilogue), plus at most one row scaling before the loop
+    names = [s_[0] for s_ in sink]
+    assert names.count('agg_propagate') == iters and len(names) <= iters + 1, names
     assert float((got.cpu().double() - want).abs().max()) <= 2e-5
+    # the same loop with separate gather / axpy / clamp kernels (any post_step callable takes that path)
+    yg = y.float().to(DEV)
+    unfused = LP.general_outcome_correlation(g, yg, alpha, iters, lambda t: torch.clamp(t, 0, 1), True, mode)
+    assert float((got - unfused).abs().max()) <= 2e-6
+    # residual correlation flavour: coefficient 1 on y, no clamp (outcome_correlation.py:141-144)
+    want2 = y.clone()
+    for _ in range(5):
+        want2 = 0.5 * torch.sparse.mm(adj, want2) + y
+    got2 = LP.general_outcome_correlation(g, yg, 0.5, 5, None, False, mode)
+    assert float((got2.cpu().double() - want2).abs().max()) <= 2e-5

@@ -66,14 +66,15 @@ __global__ void __launch_bounds__(256) k_topk_softmax_mix(const float* __restric
     float sum = 0.f;
     for (int k = K - 1; k >= 0; --k) sum += __shfl_sync(0xffffffffu, e, k);    // ascending score order
     const float p = e / sum;
-    for (int64_t c = lane; c < d; c += 32) {
+    for (int64_t c0 = 0; c0 < d; c0 += 32) {       // warp-uniform trip count: the shuffles below need every lane
+        const int64_t c = c0 + lane;
         float acc = 0.f;
         for (int k = K - 1; k >= 0; --k) {
             const float pk = __shfl_sync(0xffffffffu, p, k);
             const int32_t ik = __shfl_sync(0xffffffffu, id, k);
-            if (ik >= 0) acc += pk * __ldg(table + (int64_t)ik * ld_table + c);
+            if (ik >= 0 && c < d) acc += pk * __ldg(table + (int64_t)ik * ld_table + c);
         }
-        out[row * d + c] = acc;
+        if (c < d) out[row * d + c] = acc;
     }
 }
 

@@ -68,4 +68,7 @@ def test_replacement_matches_reference_loop(n, d, k, block):
     assert float((got_all[some].cpu().double() - exact).abs().max()) <= 3e-5 * scale
     assert float((got_all[some].cpu() - want).abs().max()) <= 5e-5 * scale
     sub = replacement(table.cuda(), guess.cuda(), k, node_idx=some, block=block)
-    assert torch.equal(sub, got_all[some])
+    if min(k, n) <= 32:
+        assert torch.equal(sub, got_all[some])            # per-row work: independent of how the queries are blocked
+    else:
+        assert float((sub - got_all[some]).abs().max()) <= 1e-5 * scale

@@ -221,7 +221,9 @@ def test_gemm_rows_grad_row_live_flags_and_sparse_gather():
 
 @pytest.mark.parametrize('d,frac,dtype', [(256, 0.1, torch.float32), (64, 0.5, torch.float32), (12, 0.02, torch.float32),
                                           (128, 0.1, torch.bfloat16), (256, 0.0, torch.float32),
-                                          (256, 1.0, torch.float32)])
+                                          (256, 1.0, torch.float32), (128, 0.05, torch.float32),
+                                          (512, 0.3, torch.float32), (256, 0.1, torch.bfloat16),
+                                          (640, 0.02, torch.float32)])
 def test_compacted_gather_bit_identical_incl_hub_rows(d, frac, dtype):
     """cb_graph_compact_live + cb_agg_gather_compacted against the dense gather of a row-sparse matrix, on a graph
     with hub rows (chunked sums keep their association), both CSR sides, and the compacted lists themselves

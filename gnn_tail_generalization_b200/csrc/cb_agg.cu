@@ -16,6 +16,7 @@
 // The neighbour ids of a task are read LPR at a time with one coalesced load and handed round with
 // warp shuffles; UNROLL independent row loads are in flight per group before the first add.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "cb_internal.cuh"
 
@@ -54,7 +55,8 @@ struct AggArgs {
     // label-propagation epilogue (cb_agg_propagate): out = clamp(one_minus_alpha * r + alpha * x0, lo, hi)
     int clamp;
     float clamp_lo, clamp_hi;
-    int64_t task0;              // first task of a k_agg launch (0, or n_rows when the rows went to k_agg_rows_batched)
+    int64_t task0;              // first task of a k_agg launch (0, or n_rows when the rows went to k_gather_sparse_rows)
+    const int2* row_be;         // compacted plain gather: (begin, end) per row with hub rows emptied, else null
 };
 
 template <int VEC>
@@ -302,92 +304,57 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
     }
 }
 
-// Row-sparse gathers (live-column compacted lists): most rows keep 0-3 neighbours, so one warp per row spends its
-// time in three dependent round trips (offsets -> column ids -> one 1 KB row) with almost nothing in flight.  Here a
-// warp owns R consecutive rows: their offsets and all their column ids arrive with one coalesced load each, and the
-// flat neighbour list of the batch is walked UNROLL rows-in-flight at a time across row boundaries; a row's sum is
-// still the in-order sum of its own neighbours (bit-identical to k_agg).  Hub rows are left to their chunk tasks.
-template <typename S, int VEC, int NCH, int UNROLL, int R>
-__global__ void __launch_bounds__(256) k_agg_rows_batched(const AggArgs a) {
+// Row-sparse gathers over the live-column compacted lists: most rows keep 0-3 neighbours, so the per-row overhead is
+// the whole cost (ncu, 10 % live rows at the bench shape: the general kernel executes ~310 warp instructions per row
+// and sits at 44 % issue utilisation, 3 TB/s).  This kernel does only what a compacted gather needs: one 8-byte
+// (begin, end) per row -- hub rows are empty there, their chunks and k_combine produce them afterwards -- the column
+// ids, the rows, one scaled store.  A row's sum is the in-order sum of its live neighbours (bit-identical to k_agg).
+template <typename S, int VEC, int LPR, int NCH>
+__global__ void __launch_bounds__(256) k_gather_sparse_rows(const AggArgs a, const int2* __restrict__ row_be) {
+    constexpr int GROUPS = 32 / LPR;
     const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t row0 = warp * R;
-    if (row0 >= a.n_rows) return;
-    const int nr = (int)(a.n_rows - row0 < R ? a.n_rows - row0 : R);
-    // lane k <= nr: offset of row row0 + k in the compacted list; hub rows are emptied (their chunks produce them)
-    int64_t rp = 0;
-    if (lane <= nr) rp = __ldg(a.rowptr + row0 + lane);
-    bool hub = false;
-    if (lane < nr) hub = __ldg(a.hub_rowptr + row0 + lane + 1) - __ldg(a.hub_rowptr + row0 + lane) > a.hub_chunk;
-    const unsigned hub_mask = __ballot_sync(0xffffffffu, hub);
-    const int64_t beg = __shfl_sync(0xffffffffu, rp, 0);
-    const int64_t end = __shfl_sync(0xffffffffu, rp, nr);
-
-    int64_t cofs[NCH];
-    bool cval[NCH];
+    const int sub = lane % LPR;
+    const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS + lane / LPR;
+    if (row >= a.n_rows) return;
+    const int2 be = __ldg(row_be + row);
     float acc[NCH][VEC];
+    int64_t cofs[NCH];
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
-        cofs[ch] = a.col0 + (int64_t)(ch * 32 + lane) * VEC;
-        cval[ch] = cofs[ch] < a.d;
+        cofs[ch] = a.col0 + (int64_t)(ch * LPR + sub) * VEC;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
     }
-    int cur = 0;    // row of the batch whose sum is being built
-    auto flush_to = [&](int upto) {     // store rows cur .. upto-1 (the first one holds acc, the others are empty)
-        for (; cur < upto; ++cur) {
-            if (!((hub_mask >> cur) & 1u)) {
+    for (int e = be.x; e < be.y; e += 2) {          // two rows in flight per group
+        const int s0 = __ldg(a.col + e);
+        const bool two = e + 1 < be.y;
+        const int s1 = two ? __ldg(a.col + e + 1) : s0;
+        typename Elem<S, VEC>::Raw v0[NCH], v1[NCH];
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch)
-                    if (cval[ch]) epilogue_store<S, VEC>(a, row0 + cur, cofs[ch], acc[ch]);
+        for (int ch = 0; ch < NCH; ++ch) {
+            if (cofs[ch] < a.d) {
+                Elem<S, VEC>::load_raw(v0[ch], a.X, (int64_t)s0 * a.x_ld + cofs[ch]);
+                if (two) Elem<S, VEC>::load_raw(v1[ch], a.X, (int64_t)s1 * a.x_ld + cofs[ch]);
             }
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
         }
-    };
-
-    for (int64_t base = beg; base < end; base += 32) {
-        const int n = (int)(end - base < 32 ? end - base : 32);
-        const int64_t e = base + lane;
-        int my = lane < n ? __ldg(a.col + e) : 0;
-        // row of my edge = number of row starts rp[1..nr] that are <= e; hub rows' edges are marked dead
-        int myrow = 0;
 #pragma unroll
-        for (int k = 1; k <= R; ++k) {
-            const int64_t start = __shfl_sync(0xffffffffu, rp, k < nr ? k : nr);
-            if (k <= nr && start <= e) myrow = k;
-        }
-        if (lane < n && ((hub_mask >> myrow) & 1u)) my |= (int)0x80000000;
-        for (int k = 0; k < n; k += UNROLL) {
-            typename Elem<S, VEC>::Raw v[UNROLL][NCH];
-            int rw[UNROLL];
-            bool on[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int src = __shfl_sync(0xffffffffu, my, (k + u) & 31);
-                rw[u] = __shfl_sync(0xffffffffu, myrow, (k + u) & 31);
-                on[u] = (k + u < n) && src >= 0;
-                if (on[u]) {
-                    const int64_t xr = (int64_t)src * a.x_ld;
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch)
-                        if (cval[ch]) Elem<S, VEC>::load_raw(v[u][ch], a.X, xr + cofs[ch]);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                if (on[u]) {
-                    if (rw[u] != cur) flush_to(rw[u]);
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch)
-                        if (cval[ch]) Elem<S, VEC>::add(acc[ch], v[u][ch]);
-                }
+        for (int ch = 0; ch < NCH; ++ch) {
+            if (cofs[ch] < a.d) {
+                Elem<S, VEC>::add(acc[ch], v0[ch]);
+                if (two) Elem<S, VEC>::add(acc[ch], v1[ch]);
             }
         }
     }
-    flush_to(nr);
+    const float rs = a.row_scale ? __ldg(a.row_scale + row) : 1.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        if (cofs[ch] < a.d) {
+            float o[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = a.row_scale ? __fmul_rn(acc[ch][i], rs) : acc[ch][i];
+            Elem<S, VEC>::store(a.out, row * a.o_ld + cofs[ch], o);
+        }
+    }
 }
 
 // Adds the chunk partials of every hub row in chunk order and applies the epilogue.
@@ -429,12 +396,12 @@ static int launch_cfg(const AggArgs& a_in, cudaStream_t st) {
     constexpr int UNROLL = NCH >= 2 ? 4 : 8;   // >= 128 bytes of gathered rows in flight per lane
     constexpr int U = UNROLL < LPR ? UNROLL : LPR;
     AggArgs a = a_in;
-    if (LPR == 32 && a.hub_rowptr != nullptr && a.n_rows > 0) {
-        // compacted (row-sparse) lists with full-warp rows: R rows per warp, see k_agg_rows_batched
-        constexpr int R = 8;
-        const int64_t blocks = ceil_div(ceil_div(a.n_rows, (int64_t)R), (int64_t)WARPS);
+    static const bool lean_rows = !(getenv("CB_SPARSE_LEAN") && atoi(getenv("CB_SPARSE_LEAN")) == 0);   // A/B switch
+    if (lean_rows && a.row_be != nullptr && a.n_rows > 0 && LPR >= 16) {
+        // compacted (row-sparse) plain gather: the lean per-row kernel, then the hub chunks through k_agg / k_combine
+        const int64_t blocks = ceil_div(a.n_rows, (int64_t)WARPS * GROUPS);
         CB_REQUIRE(blocks < (int64_t)INT32_MAX, CB_E_UNSUPPORTED, "aggregation grid too large");
-        k_agg_rows_batched<S, VEC, NCH, (NCH >= 2 ? 4 : 8), R><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+        k_gather_sparse_rows<S, VEC, LPR, NCH><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a, a.row_be);
         CB_LAUNCH_CHECK();
         a.task0 = a.n_rows;      // k_agg below: the hub chunks only
     }
@@ -496,6 +463,8 @@ static int run_agg(const cb_graph* g, int side_id, int dtype, AggArgs a, void* w
         a.col = v.col;
         a.chunk_beg = v.chunk_beg;
         a.chunk_end = v.chunk_end;
+        // the lean kernel covers what cb_agg_gather_compacted can ask for: out = row_scale * sum
+        if (!a.bias && !a.x0 && a.act == CB_ACT_NONE && !a.out2 && !a.mask && !a.clamp && a.out) a.row_be = v.row_be;
     }
     a.hub_chunk = g->hub_chunk;
     a.col0 = 0;

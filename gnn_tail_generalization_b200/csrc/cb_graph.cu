@@ -382,6 +382,7 @@ LiveView live_view(const cb_graph* g, int side_id, void* workspace) {
     v.bits = (uint32_t*)(p + o);     o += align256(groups * (int64_t)sizeof(uint32_t));
     v.posw = (int32_t*)(p + o);      o += align256(groups * (int64_t)sizeof(int32_t));
     v.spine = (int32_t*)(p + o);     o += align256((tiles + 1) * (int64_t)sizeof(int32_t));
+    v.row_be = (int2*)(p + o);       o += align256((g->rows + 1) * (int64_t)sizeof(int2));
     v.bytes = o;
     return v;
 }
@@ -488,12 +489,20 @@ __global__ void __launch_bounds__(256) k_live_offsets(const int64_t* __restrict_
                                                       int hub_chunk, const uint32_t* __restrict__ bits,
                                                       const int32_t* __restrict__ posw, const int32_t* __restrict__ spine,
                                                       int64_t n_tiles, int64_t* __restrict__ rowptr_c,
-                                                      int64_t* __restrict__ chunk_beg_c, int64_t* __restrict__ chunk_end_c) {
+                                                      int64_t* __restrict__ chunk_beg_c, int64_t* __restrict__ chunk_end_c,
+                                                      int2* __restrict__ row_be) {
     const int32_t total = __ldg(spine + n_tiles);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= rows + n_chunks; i += stride) {
         if (i <= rows) {
-            rowptr_c[i] = live_pos(__ldg(rowptr + i), E, bits, posw, total);
+            const int64_t b0 = __ldg(rowptr + i);
+            const int64_t pb = live_pos(b0, E, bits, posw, total);
+            rowptr_c[i] = pb;
+            if (i < rows) {
+                const int64_t e0 = __ldg(rowptr + i + 1);
+                const bool hub = e0 - b0 > hub_chunk;       // a row is a hub by its ORIGINAL degree
+                row_be[i] = make_int2((int)pb, hub ? (int)pb : (int)live_pos(e0, E, bits, posw, total));
+            }
         } else {
             const int64_t c = i - rows - 1;
             const int64_t b = __ldg(chunk_beg + c);
@@ -679,7 +688,7 @@ int cb_graph_compact_live(const cb_graph_t* g, int side_id, const uint8_t* row_l
     CB_LAUNCH_CHECK();
     k_live_offsets<<<grid_for(g->rows + 1 + s.n_chunks, 256), 256, 0, st>>>(
         s.rowptr, g->rows, E, s.chunk_row, s.chunk_beg, s.n_chunks, g->hub_chunk, v.bits, v.posw, v.spine, tiles,
-        v.rowptr, v.chunk_beg, v.chunk_end);
+        v.rowptr, v.chunk_beg, v.chunk_end, v.row_be);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -51,6 +51,7 @@ struct LiveView {
     uint32_t* bits;      // [ceil(n_edges/32)] live bit per stored edge
     int32_t* posw;       // [ceil(n_edges/32)] number of live edges before each 32-edge group
     int32_t* spine;      // [ceil(n_edges/LIVE_TILE)+1] exclusive prefix of the tile counts, total in the last slot
+    int2* row_be;        // [rows] (begin, end) of every row in col; hub rows are EMPTY here (their chunks produce them)
     int64_t bytes;
 };
 constexpr int LIVE_TILE = 4096;

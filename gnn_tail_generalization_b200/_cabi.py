@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcoldbrew_b200.so')
 
 CB_OK = 0
-ABI_VERSION = 3
+ABI_VERSION = 4
 CB_ACT_NONE, CB_ACT_RELU = 0, 1
 CB_BY_DST, CB_BY_SRC = 0, 1
 CB_F32, CB_BF16 = 0, 1
@@ -71,7 +71,8 @@ SYMBOLS = {
     'cb_peer_free': (_int, [_vp]),
     'cb_gemm_rows_grad_workspace_bytes': (_i64, [_i64, _i64]),
     'cb_gemm_rows_grad': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _int, _dbl,
-                                 _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
+                                 _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'cb_row_any_nonzero': (_int, [_vp, _int, _i64, _i64, _i64, _vp, _vp]),
     'cb_gemm_tn_supported': (_int, [_i64, _i64, _i64]),
     'cb_gemm_tn_workspace_bytes': (_i64, [_i64, _i64, _i64]),
     'cb_gemm_tn': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp, _i64, _vp, _i64, _vp]),
@@ -80,7 +81,7 @@ SYMBOLS = {
     'cb_gemm_rows_bf16': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _int, _vp, _i64, _vp, _vp, _i64,
                                  _vp, _vp]),
     'cb_gemm_rows_grad_bf16': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _int, _dbl,
-                                      _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
+                                      _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'cb_gemm_tn_supported_bf16': (_int, [_i64, _i64, _i64]),
     'cb_gemm_tn_workspace_bytes_bf16': (_i64, [_i64, _i64, _i64]),
     'cb_gemm_tn_bf16': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),

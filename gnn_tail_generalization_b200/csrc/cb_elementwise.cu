@@ -354,6 +354,31 @@ __global__ void __launch_bounds__(256) k_to_bf16(const float* __restrict__ x, in
         y[i] = __float2bfloat16_rn(x[i]);
 }
 
+// flags[r] = any(x[r, :] != 0): one warp per row, 16 bytes per lane per step (-0.0 counts as zero)
+template <int ES>
+__global__ void __launch_bounds__(256) k_row_any_nonzero(const void* __restrict__ x, int64_t rows, int64_t d, int64_t ld,
+                                                         uint8_t* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const char* p = reinterpret_cast<const char*>(x) + row * ld * ES;
+    const int64_t bytes = d * ES;
+    uint32_t any = 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
+    const int64_t n16 = vec ? bytes / 16 : 0;
+    for (int64_t i = lane; i < n16; i += 32) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
+        if (ES == 4) any |= (v.x | v.y | v.z | v.w) << 1;                      // drop the sign bits
+        else any |= (v.x | v.y | v.z | v.w) & 0x7fff7fffu;
+    }
+    for (int64_t b = n16 * 16 + lane * ES; b < bytes; b += 32 * ES) {
+        if (ES == 4) any |= *reinterpret_cast<const uint32_t*>(p + b) << 1;
+        else any |= (uint32_t)(*reinterpret_cast<const uint16_t*>(p + b) & 0x7fffu);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, any != 0u);
+    if (lane == 0) flags[row] = m != 0u;
+}
+
 static int prep_blocks(int64_t rows) {
     const int64_t cap = (int64_t)sm_count() * 8;
     const int64_t want = ceil_div(rows > 0 ? rows : 1, 64);
@@ -435,6 +460,21 @@ int cb_se_adam_step(float* E, const void* grad, int grad_dtype, float* m, float*
         k_se_adam<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     else
         k_se_adam<float><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_row_any_nonzero(const void* x, int dtype, int64_t rows, int64_t d, int64_t ld, uint8_t* flags, void* stream) {
+    using namespace cb;
+    CB_REQUIRE(rows >= 0 && d > 0 && ld >= d, CB_E_INVALID, "cb_row_any_nonzero: bad shape");
+    CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_row_any_nonzero: unknown dtype");
+    if (rows == 0) return CB_OK;
+    CB_REQUIRE(x && flags, CB_E_INVALID, "cb_row_any_nonzero: NULL buffer");
+    const unsigned grid = (unsigned)ceil_div(rows, 8);
+    if (dtype == CB_BF16)
+        k_row_any_nonzero<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, d, ld, flags);
+    else
+        k_row_any_nonzero<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, d, ld, flags);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

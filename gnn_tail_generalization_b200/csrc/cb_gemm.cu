@@ -106,6 +106,9 @@ struct GemmArgs {
     const float* post_scale;  // [M] scale of the stored value (din^-1/2), or null
     float* col_partial;       // [gridDim.x, N] per-CTA column sums of dz, or null
     uint8_t* row_live;        // [M] set to 1 where the stored row has a non-zero element, or null
+    const uint8_t* a_live;    // [M] or null: rows with 0 have an all-zero A row (their dtot is 0): nothing of them is
+                              // loaded or stored -- out / d_x0 keep whatever the buffers held (the consumers skip them)
+    const uint8_t* x0_valid;  // [M] or null (with accumulate_x0): rows with 0 hold no valid d_x0 yet, read as 0
     // ---- multi-GPU: rows of `out` are also stored into the peers that gather them (cb_peer_push_t) ----
     cb_peer_push_t push;
 };
@@ -478,23 +481,36 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     float rsv[8], psv[8];
                     uint32_t gm[8];
                     const bool acc_x0 = g.d_x0 && g.accumulate_x0;
+                    // rows this lane really works on: inside M, and -- with a_live -- not known to be all-zero
+                    uint32_t lm = nval >= 8 ? 0xffu : ((1u << nval) - 1u);
+                    if (g.a_live) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (((lm >> itr) & 1u) && __ldg(g.a_live + rbase + itr * 4) == 0) lm &= ~(1u << itr);
+                    }
                     if (g.add || acc_x0) {
                         const int64_t ld = g.add ? g.ld_add : g.ld_dx0;
                         const S* p = reinterpret_cast<const S*>(g.add ? g.add : g.d_x0) + rbase * ld + col;
+                        uint32_t vm = lm;           // rows whose old d_x0 exists
+                        if (!g.add && g.x0_valid) {
+#pragma unroll
+                            for (int itr = 0; itr < 8; ++itr)
+                                if (((vm >> itr) & 1u) && __ldg(g.x0_valid + rbase + itr * 4) == 0) vm &= ~(1u << itr);
+                        }
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) av[itr] = ld4_cs(p + (int64_t)itr * 4 * ld);
+                            av[itr] = ((vm >> itr) & 1u) ? ld4_cs(p + (int64_t)itr * 4 * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     if (g.gate_u8) {
                         const uint8_t* p = g.gate_u8 + rbase * g.ld_gate + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) gm[itr] = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)itr * 4 * g.ld_gate));
+                            if ((lm >> itr) & 1u) gm[itr] = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)itr * 4 * g.ld_gate));
                     } else if (g.gate_f32) {
                         const S* p = reinterpret_cast<const S*>(g.gate_f32) + rbase * g.ld_gate + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) gy[itr] = ld4_g(p + (int64_t)itr * 4 * g.ld_gate);
+                            if ((lm >> itr) & 1u) gy[itr] = ld4_g(p + (int64_t)itr * 4 * g.ld_gate);
                     }
                     if (g.row_scale) {
 #pragma unroll
@@ -536,7 +552,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                                 x.x = __fadd_rn(av[itr].x, x.x); x.y = __fadd_rn(av[itr].y, x.y);
                                 x.z = __fadd_rn(av[itr].z, x.z); x.w = __fadd_rn(av[itr].w, x.w);
                             }
-                            if (itr < nval) st4_cs(p + (int64_t)itr * 4 * g.ld_dx0, x);
+                            if ((lm >> itr) & 1u) st4_cs(p + (int64_t)itr * 4 * g.ld_dx0, x);
                         }
                     }
                     if (g.mixed) {
@@ -562,10 +578,10 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         }
                     }
                     if (g.col_partial) {
-                        if (nval < 8) {
+                        if (lm != 0xffu) {      // rows outside M or skipped rows (whose gate words were not loaded)
 #pragma unroll
                             for (int itr = 0; itr < 8; ++itr)
-                                if (itr >= nval) v[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (!((lm >> itr) & 1u)) v[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                         float4 cs = v[0];
 #pragma unroll
@@ -595,7 +611,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         S* p = reinterpret_cast<S*>(g.out) + rbase * g.ld_out + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) st4_cs(p + (int64_t)itr * 4 * g.ld_out, v[itr]);
+                            if ((lm >> itr) & 1u) st4_cs(p + (int64_t)itr * 4 * g.ld_out, v[itr]);
                     }
                     if (g.push.n_peers) push_to_peers<S>(g.push, rbase, col, nval, v);
                     if (g.row_live) {
@@ -875,8 +891,8 @@ static int gemm_rows_grad_impl(const S* A, int64_t M, int64_t K, int64_t lda, co
                                const float* row_scale, const S* add, int64_t ld_add, const uint8_t* gate_u8,
                                const S* gate_val, int64_t ld_gate, int mixed, double alpha, S* d_x0, int64_t ld_dx0,
                                int accumulate_x0, const float* post_scale, S* out, int64_t ld_out, float* col_sum,
-                               uint8_t* row_live, void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push,
-                               void* stream) {
+                               uint8_t* row_live, const uint8_t* a_live, const uint8_t* x0_valid, void* workspace,
+                               int64_t workspace_bytes, const cb_peer_push_t* push, void* stream) {
     CB_REQUIRE(!push || (push->n_peers >= 0 && push->n_peers <= CB_MAX_PEERS && (push->n_peers == 0 ||
                          (push->need && push->ld >= N && push->ld % 4 == 0))), CB_E_INVALID,
                "cb_gemm_rows_grad: bad cb_peer_push_t");
@@ -884,6 +900,8 @@ static int gemm_rows_grad_impl(const S* A, int64_t M, int64_t K, int64_t lda, co
     CB_REQUIRE(!(gate_u8 && gate_val), CB_E_INVALID, "cb_gemm_rows_grad: one gate at most");
     CB_REQUIRE(!(add && d_x0 && accumulate_x0), CB_E_UNSUPPORTED,
                "cb_gemm_rows_grad: `add` and an accumulating d_x0 cannot be combined");
+    CB_REQUIRE(!(a_live && add), CB_E_INVALID,
+               "cb_gemm_rows_grad: a_live promises all-zero output rows, which `add` would break");
     CB_REQUIRE(rows_supported<S>(M, N, K), CB_E_UNSUPPORTED,
                "cb_gemm_rows_grad: needs N % 4 == 0, K a multiple of 16 bytes and M < 2^31");
     CB_REQUIRE(lda >= K && lda % vec16<S>() == 0 && al16(A) && al16(Bt_hi) && al16(Bt_lo), CB_E_UNSUPPORTED,
@@ -918,6 +936,8 @@ static int gemm_rows_grad_impl(const S* A, int64_t M, int64_t K, int64_t lda, co
     g.post_scale = post_scale;
     g.col_partial = col_sum ? (float*)workspace : nullptr;
     g.row_live = row_live;
+    g.a_live = a_live;
+    g.x0_valid = (d_x0 && accumulate_x0) ? x0_valid : nullptr;
     if (push) g.push = *push;
     cudaStream_t st = (cudaStream_t)stream;
     rc = bn == 64 ? launch_gemm<S, 64, true>(ma, mh, ml, g, st)
@@ -1311,24 +1331,25 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
                       int64_t N, const float* row_scale, const float* add, int64_t ld_add, const uint8_t* gate_u8,
                       const float* gate_f32, int64_t ld_gate, int mixed, double alpha, float* d_x0, int64_t ld_dx0,
                       int accumulate_x0, const float* post_scale, float* out, int64_t ld_out, float* col_sum,
-                      uint8_t* row_live, void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push,
-                      void* stream) {
+                      uint8_t* row_live, const uint8_t* a_live, const uint8_t* x0_valid, void* workspace,
+                      int64_t workspace_bytes, const cb_peer_push_t* push, void* stream) {
     return cb::tc::gemm_rows_grad_impl<float>(A, M, K, lda, Bt_hi, Bt_lo, N, row_scale, add, ld_add, gate_u8, gate_f32,
                                               ld_gate, mixed, alpha, d_x0, ld_dx0, accumulate_x0, post_scale, out,
-                                              ld_out, col_sum, row_live, workspace, workspace_bytes, push, stream);
+                                              ld_out, col_sum, row_live, a_live, x0_valid, workspace, workspace_bytes,
+                                              push, stream);
 }
 
 int cb_gemm_rows_grad_bf16(const uint16_t* A, int64_t M, int64_t K, int64_t lda, const uint16_t* Bt, int64_t N,
                            const float* row_scale, const uint16_t* add, int64_t ld_add, const uint8_t* gate_u8,
                            const uint16_t* gate_val, int64_t ld_gate, int mixed, double alpha, uint16_t* d_x0,
                            int64_t ld_dx0, int accumulate_x0, const float* post_scale, uint16_t* out, int64_t ld_out,
-                           float* col_sum, uint8_t* row_live, void* workspace, int64_t workspace_bytes,
-                           const cb_peer_push_t* push, void* stream) {
+                           float* col_sum, uint8_t* row_live, const uint8_t* a_live, const uint8_t* x0_valid,
+                           void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push, void* stream) {
     using B = __nv_bfloat16;
     return cb::tc::gemm_rows_grad_impl<B>((const B*)A, M, K, lda, (const B*)Bt, nullptr, N, row_scale, (const B*)add,
                                           ld_add, gate_u8, (const B*)gate_val, ld_gate, mixed, alpha, (B*)d_x0, ld_dx0,
-                                          accumulate_x0, post_scale, (B*)out, ld_out, col_sum, row_live, workspace,
-                                          workspace_bytes, push, stream);
+                                          accumulate_x0, post_scale, (B*)out, ld_out, col_sum, row_live, a_live, x0_valid,
+                                          workspace, workspace_bytes, push, stream);
 }
 
 }  // extern "C" (reopened below)

@@ -348,15 +348,30 @@ def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_s
     return (push.local, out2) if want_out2 else push.local
 
 
+def row_any_nonzero_raw(x):
+    """uint8 [rows]: 1 where the row of x (fp32 or bf16, [rows, d]) holds a non-zero element (cb_row_any_nonzero)."""
+    _need_cuda(x)
+    if x.dtype not in _STORAGE or x.dim() != 2:
+        raise TypeError('row_any_nonzero: a 2-D float32 / bfloat16 matrix')
+    x = x.contiguous()
+    flags = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device), _Timed('row_any_nonzero', x.numel() * x.element_size() + x.shape[0], x.device):
+        C.call('cb_row_any_nonzero', C.ptr(x), C.CB_F32 if x.dtype == torch.float32 else C.CB_BF16, x.shape[0],
+               x.shape[1], x.shape[1], C.ptr(flags), C.stream_ptr(x.device))
+    return flags
+
+
 def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=None, mixed=False, alpha=0.0,
                        d_x0=None, accumulate_x0=False, want_x0=False, post_scale=None, want_col_sum=False,
-                       push=None, row_live=None, push_live=None):
+                       push=None, row_live=None, push_live=None, a_live=None, x0_valid=None):
     """cb_gemm_rows_grad: the adjoint GEMM with the backward prologue of the layer below in its epilogue.
     Returns (out, col_sum or None, d_x0 or None); with ``push`` the output goes to the exchange slot
     (see gemm_rows_raw) and its local view is returned.  row_live: zeroed uint8 [M] that receives 1 for
     every output row holding a non-zero element.  push_live: uint8 [M], 0 for rows known to come out all-zero
     (their A row is zero): those are not pushed to the peers.  gate_f32: the relu output in the storage type of A
-    (gate = value > 0)."""
+    (gate = value > 0).  a_live: uint8 [M] from row_any_nonzero_raw(A): rows with 0 are skipped entirely -- their
+    rows of ``out`` / ``d_x0`` are NOT written (the consumers go by the same flags).  x0_valid: uint8 [M] flags of an
+    accumulating ``d_x0`` whose first writer skipped rows that way (0 = read as zero)."""
     _need_cuda(A, row_scale, add, gate_u8, gate_f32, d_x0, post_scale)
     st = A.dtype
     if st not in _STORAGE or wt.dtype != st:
@@ -400,8 +415,8 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
                    C.ptr(row_scale), _pofs(add, c0), N, _pofs(gate_u8, c0), _pofs(gate_f32, c0),
                    N if gate is not None else 0, int(bool(mixed)), float(alpha), _pofs(d_x0, c0), N,
                    int(bool(accumulate_x0)), C.ptr(post_scale), C.ptr(dst), dst.shape[1], _pofs(col_sum, c0),
-                   C.ptr(row_live), C.ptr(ws), ws_bytes, ctypes.byref(desc) if desc is not None else None,
-                   C.stream_ptr(A.device))
+                   C.ptr(row_live), C.ptr(a_live), C.ptr(x0_valid), C.ptr(ws), ws_bytes,
+                   ctypes.byref(desc) if desc is not None else None, C.stream_ptr(A.device))
         if push is not None:
             push.pushed(p)
     return out, col_sum, d_x0
@@ -510,13 +525,25 @@ def frob_norm(e, graph=None):
 # GEMM epilogue (or, failing that, the hub adds once).
 # ---------------------------------------------------------------------------------------------
 class GradSink:
-    __slots__ = ('buf',)
+    """``buf``: the accumulated gradient.  ``valid``: None, or uint8 [rows] flags left by a row-sparse first writer
+    (cb_gemm_rows_grad with a_live): rows with 0 were never written and count as zero.  The next cb_gemm_rows_grad
+    reads the buffer through those flags; every other consumer gets it materialised."""
+    __slots__ = ('buf', 'valid')
 
     def __init__(self):
-        self.buf = None
+        self.buf = self.valid = None
+
+    def dense(self):
+        """The buffer with the never-written rows zeroed (no-op when every row is valid)."""
+        if self.buf is not None and self.valid is not None:
+            self.buf = torch.where(self.valid.bool()[:, None], self.buf, torch.zeros((), dtype=self.buf.dtype,
+                                                                                     device=self.buf.device))
+            self.valid = None
+        return self.buf
 
     def take(self):
-        b, self.buf = self.buf, None
+        b = self.dense()
+        self.buf = self.valid = None
         return b
 
 
@@ -576,22 +603,38 @@ class BwdPlan:
         if add is not None and sink is not None and sink.buf is not None:
             return None     # the kernel keeps one [M, N] epilogue input: the caller runs the two-kernel path
         slot = g.push_slot(C.CB_BY_SRC, wb.n, dtot_in.dtype)    # G is what the transposed aggregation gathers
-        live = push_live = live_full = None
-        if self.row_sparse_hint and slot is not None and add is None:
-            # multi-GPU: a zero row of the incoming gradient gives a zero row of G -- known BEFORE the GEMM, so
-            # such rows are neither pushed to the peers nor gathered by anyone.  The flags of every rank are
-            # all-gathered HERE, ahead of the first panel's GEMM: the side-stream gathers wait only for their
-            # panel's event, which is recorded after this point, so they can never read a half-written flag array.
-            push_live = (dtot_in != 0).any(dim=1).to(torch.uint8)
-            live_full = compact_live_raw(g, C.CB_BY_SRC, g.exchange_flags(push_live))   # the compacted workspace
+        live = push_live = live_full = a_live = kernel_live = None
+        if self.row_sparse_hint and add is None:
+            # A zero row of the incoming gradient gives a zero row of dtot, of G and of the d_x0 contribution -- known
+            # BEFORE the GEMM (one pass over the [M, K] gradient).  Such rows are not computed on, not stored, not
+            # pushed to the peers and not gathered by anyone: the GEMM, the pushes and the compacted gather all go
+            # by the same flags.
+            a_live = row_any_nonzero_raw(dtot_in)
+            if slot is not None:
+                # multi-GPU: the flags of every rank are all-gathered HERE, ahead of the first panel's GEMM: the
+                # side-stream gathers wait only for their panel's event, which is recorded after this point, so
+                # they can never read a half-written flag array.
+                push_live = a_live
+                live_full = compact_live_raw(g, C.CB_BY_SRC, g.exchange_flags(a_live))   # the compacted workspace
+            else:
+                live = a_live
         elif self.row_sparse_hint:
-            live = torch.zeros(dtot_in.shape[0], dtype=torch.uint8, device=dtot_in.device)
+            # `add` makes rows non-zero that the incoming gradient does not: the kernel reports what it stored
+            live = kernel_live = torch.zeros(dtot_in.shape[0], dtype=torch.uint8, device=dtot_in.device)
+        accumulate = sink is not None and sink.buf is not None
         out, col, d_x0 = gemm_rows_grad_raw(
             dtot_in, wb, row_scale=rs, add=add, gate_u8=self.gate_u8, gate_f32=self.gate_f32 if self.relu else None,
             mixed=self.mixed, alpha=self.alpha, d_x0=sink.buf if sink is not None else None,
-            accumulate_x0=sink is not None and sink.buf is not None, want_x0=self.want_x0,
-            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot, row_live=live, push_live=push_live)
+            accumulate_x0=accumulate, want_x0=self.want_x0,
+            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot, row_live=kernel_live,
+            push_live=push_live, a_live=a_live, x0_valid=sink.valid if accumulate else None)
         if sink is not None:
+            if a_live is None:
+                sink.valid = None                    # a dense writer: every row holds its sum now
+            elif not accumulate:
+                sink.valid = a_live                  # first writer skipped the dead rows: they count as zero
+            elif sink.valid is not None:
+                sink.valid = sink.valid | a_live     # rows written now or before
             sink.buf, d_x0 = d_x0, None
         self.result = {'d_bias': col, 'd_x0': d_x0, 'G': out, 'live': live, 'live_full': live_full}
         if out.dim() == 3:
@@ -941,7 +984,7 @@ class _FusedAggregate(torch.autograd.Function):
             sink = ctx.x0_sink if want_x0 else None
             G, d_bias, d_x0 = backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, ctx.relu, ctx.mixed,
                                                 ctx.alpha, want_bias, want_x0,
-                                                d_x0_accum=sink.buf if sink is not None else None)
+                                                d_x0_accum=sink.dense() if sink is not None else None)
             if sink is not None:   # parked for the hub / the last consumer's GEMM epilogue
                 sink.buf, d_x0 = d_x0, None
         dH = None

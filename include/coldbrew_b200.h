@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 3   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build */
+#define CB_ABI_VERSION 4   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid */
 
 enum {
     CB_OK = 0,
@@ -322,6 +322,11 @@ int cb_gemm_rows(const float* A, int64_t M, int64_t K, int64_t lda, const float*
  *                                                                     `workspace`, added in CTA order)
  *   row_live[m] = 1 if any out[m,:] != 0                             (if row_live; the caller zeroes it first;
  *                                                                     feeds cb_agg_gather's row_live)
+ *   a_live [M] or NULL (not with `add`): 0 = the A row is all-zero (cb_row_any_nonzero), so dtot, dz, out and the d_x0
+ *            contribution of that row are zero: nothing of the row is loaded or STORED -- out / d_x0 keep whatever the
+ *            buffers held.  The gradient under a loss over the train rows only has ~|train|/N live rows; the consumers
+ *            of `out` (cb_agg_gather_compacted with the same flags, the peer pushes) never touch the others.
+ *   x0_valid [M] or NULL (with accumulate_x0): 0 = d_x0[m,:] was left unwritten by such a call; it is read as 0.
  * workspace: cb_gemm_rows_grad_workspace_bytes(M, N), needed when col_sum != NULL.
  */
 int64_t cb_gemm_rows_grad_workspace_bytes(int64_t M, int64_t N);
@@ -329,8 +334,11 @@ int cb_gemm_rows_grad(const float* A, int64_t M, int64_t K, int64_t lda, const f
                       int64_t N, const float* row_scale, const float* add, int64_t ld_add, const uint8_t* gate_u8,
                       const float* gate_f32, int64_t ld_gate, int mixed, double alpha, float* d_x0, int64_t ld_dx0,
                       int accumulate_x0, const float* post_scale, float* out, int64_t ld_out, float* col_sum,
-                      uint8_t* row_live, void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push,
-                      void* stream);
+                      uint8_t* row_live, const uint8_t* a_live, const uint8_t* x0_valid, void* workspace,
+                      int64_t workspace_bytes, const cb_peer_push_t* push, void* stream);
+
+/* flags[r] = 1 if row r of x [rows, d] (row pitch ld elements, dtype CB_F32 / CB_BF16) holds a non-zero element */
+int cb_row_any_nonzero(const void* x, int dtype, int64_t rows, int64_t d, int64_t ld, uint8_t* flags, void* stream);
 
 /*
  * bf16 storage (BASELINE.json configs[4]): A, add, gate_val, d_x0, out, out2 and the weight operand Bt [N, K] hold
@@ -348,8 +356,8 @@ int cb_gemm_rows_grad_bf16(const uint16_t* A, int64_t M, int64_t K, int64_t lda,
                            const float* row_scale, const uint16_t* add, int64_t ld_add, const uint8_t* gate_u8,
                            const uint16_t* gate_val, int64_t ld_gate, int mixed, double alpha, uint16_t* d_x0,
                            int64_t ld_dx0, int accumulate_x0, const float* post_scale, uint16_t* out, int64_t ld_out,
-                           float* col_sum, uint8_t* row_live, void* workspace, int64_t workspace_bytes,
-                           const cb_peer_push_t* push, void* stream);
+                           float* col_sum, uint8_t* row_live, const uint8_t* a_live, const uint8_t* x0_valid,
+                           void* workspace, int64_t workspace_bytes, const cb_peer_push_t* push, void* stream);
 
 /*
  * Weight gradient on the tcgen05 tensor cores (3xTF32): out[Ka, Nb] = A[M, Ka]^T . B[M, Nb], the reduction

@@ -295,3 +295,48 @@ def test_ragged_widths_stay_on_the_tensor_core_kernels(M, K, N, layout):
     assert x.grad.shape == xd.grad.shape and bool(((x.grad.double() - xd.grad).abs() <= bx).all())
     assert W.grad.shape == Wd.grad.shape and bool(((W.grad.double() - Wd.grad).abs() <= bw).all())
     assert float((b.grad.double() - bd.grad).abs().max()) <= 2e-5 * max(1.0, float(bd.grad.abs().max()))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gemm_rows_grad_skips_rows_flagged_dead_and_sink_stays_consistent(dtype):
+    """a_live: rows whose A row is all-zero are neither computed on nor stored (out / d_x0 keep what the buffers held);
+    x0_valid: the next, accumulating call reads such d_x0 rows as zero.  Everything that IS stored is bit-identical to
+    the dense calls."""
+    ops = _ops()
+    M, K, N, alpha = 3000, 64, 256, 0.1
+    g = torch.Generator(device='cuda').manual_seed(5)
+    dY = torch.randn(M, K, device='cuda', generator=g).to(dtype)
+    dead = torch.rand(M, device='cuda', generator=g) < 0.8
+    dY[dead] = 0
+    W = torch.randn(N, K, device='cuda', generator=g) / 8
+    mask = (torch.rand(M, N, device='cuda', generator=g) > 0.3).to(torch.uint8)
+    ps = torch.rand(M, device='cuda', generator=g) + 0.5
+    wt = ops.split_weight(W, transpose=False, dtype=dtype)
+    flags = ops.row_any_nonzero_raw(dY)
+    assert torch.equal(flags.bool(), ~dead)
+    # dense reference
+    G_d, col_d, x0_d = ops.gemm_rows_grad_raw(dY, wt, gate_u8=mask, mixed=True, alpha=alpha, post_scale=ps, want_x0=True,
+                                              want_col_sum=True)
+    assert float(G_d[dead].abs().max()) == 0.0 and float(x0_d[dead].abs().max()) == 0.0
+    # sparse first writer into a sentinel-filled d_x0
+    x0_s = torch.full((M, N), 777.0, device='cuda', dtype=dtype)
+    G_s, col_s, _ = ops.gemm_rows_grad_raw(dY, wt, gate_u8=mask, mixed=True, alpha=alpha, post_scale=ps, d_x0=x0_s,
+                                           accumulate_x0=False, want_col_sum=True, a_live=flags)
+    assert torch.equal(G_s[~dead], G_d[~dead]) and torch.equal(x0_s[~dead], x0_d[~dead])
+    assert bool((x0_s[dead] == 777.0).all())                      # never written
+    assert torch.equal(col_s, col_d)
+    # second, dense, accumulating writer: through x0_valid the unwritten rows count as zero
+    dY2 = torch.randn(M, K, device='cuda', generator=g).to(dtype)
+    x0_ref = x0_d.clone()
+    G2_d, _, _ = ops.gemm_rows_grad_raw(dY2, wt, gate_u8=mask, mixed=True, alpha=alpha, post_scale=ps, d_x0=x0_ref,
+                                        accumulate_x0=True)
+    G2_s, _, _ = ops.gemm_rows_grad_raw(dY2, wt, gate_u8=mask, mixed=True, alpha=alpha, post_scale=ps, d_x0=x0_s,
+                                        accumulate_x0=True, x0_valid=flags)
+    assert torch.equal(G2_s, G2_d) and torch.equal(x0_s, x0_ref)
+    # the sink materialises unwritten rows for every other consumer
+    sink = ops.GradSink()
+    sink.buf, sink.valid = torch.full((M, N), float('nan'), device='cuda', dtype=dtype), flags
+    sink.buf[~dead] = 1.0
+    taken = sink.take()
+    assert sink.buf is None and sink.valid is None
+    assert bool((taken[dead] == 0).all()) and bool((taken[~dead] == 1).all())

@@ -5,6 +5,8 @@ Tolerances: integer/index work bit-exact; the bare aggregation bit-exact against
 (same association, hub chunks included); fp32 model outputs within 1e-4 (north_star) -- observed ~1e-6.
 """
 import numpy as np
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -674,3 +676,39 @@ def test_label_propagation_matches_edge_valued_spmm(mode):
         want2 = 0.5 * torch.sparse.mm(adj, want2) + y
     got2 = LP.general_outcome_correlation(g, yg, 0.5, 5, None, False, mode)
     assert float((got2.cpu().double() - want2).abs().max()) <= 2e-5
+
+
+@pytest.mark.parametrize('mode', ['DAD', 'DA', 'AD'])
+def test_label_propagation_matches_the_reference_code(mode):
+    """SURVEY 8f-3 against the REFERENCE'S OWN functions (Label_propagation_model/outcome_correlation.py: process_adj,
+    gen_normalized_adjs, label_propagation -> general_outcome_correlation), imported from its checkout and run
+    unmodified; torch_sparse.SparseTensor and torch_geometric.utils.to_undirected come from shims/ (COO + index_add_).
+    Skipped where no checkout exists (/root/reference, or baseline/_ref/reference staged by scripts/stage_reference.sh)."""
+    import sys
+    from types import SimpleNamespace
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = next((c for c in ('/root/reference', os.path.join(root, 'baseline', '_ref', 'reference'))
+                if os.path.exists(os.path.join(c, 'Label_propagation_model', 'outcome_correlation.py'))), None)
+    if ref is None:
+        pytest.skip('no reference checkout')
+    for p_ in (ref, os.path.join(root, 'shims')):
+        if p_ not in sys.path:
+            sys.path.append(p_)
+    import importlib
+    OC = importlib.import_module('Label_propagation_model.outcome_correlation')
+    from gnn_tail_generalization_b200 import label_propagation as LP
+    _, G, _ = _pkg()
+    n, c, alpha, iters = 6000, 12, 0.5, 50                      # trainer_node_classification.py:36-37: alpha 0.5, 50 steps
+    ei = O.powerlaw_graph(n, 20000, seed=6)
+    ei = ei[:, ei[0] < ei[1]]                                    # one direction only: process_adj symmetrises it
+    ei = ei[:, (ei[0] != 9) & (ei[1] != 9)]                      # node 9 isolated: the inf -> 0 rule (:47-48)
+    labels = torch.randint(0, c, (n, 1), generator=torch.Generator().manual_seed(1)).to(DEV)
+    idx = torch.randperm(n, generator=torch.Generator().manual_seed(2))[: n // 4].to(DEV)
+    data = SimpleNamespace(num_nodes=n, edge_index=ei.to(DEV), y=labels)
+    adj, d_isqrt = OC.process_adj(data)                          # mutates data.edge_index (to_undirected)
+    A = dict(zip(('DAD', 'DA', 'AD'), OC.gen_normalized_adjs(adj, d_isqrt)))[mode]
+    want = OC.label_propagation(data, {'train': idx}, A=A, alpha=alpha, num_propagations=iters, idxs=['train'])
+    g = G.GraphHandle(data.edge_index, n)
+    got = LP.label_propagation(g, labels, idx, alpha, iters, mode)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-5

@@ -354,29 +354,46 @@ __global__ void __launch_bounds__(256) k_to_bf16(const float* __restrict__ x, in
         y[i] = __float2bfloat16_rn(x[i]);
 }
 
-// flags[r] = any(x[r, :] != 0): one warp per row, 16 bytes per lane per step (-0.0 counts as zero)
-template <int ES>
+// flags[r] = any(x[r, :] != 0): LPR lanes per row (so that narrow rows fill the warp), 16 bytes per lane per step
+// (-0.0 counts as zero)
+template <int ES, int LPR>
 __global__ void __launch_bounds__(256) k_row_any_nonzero(const void* __restrict__ x, int64_t rows, int64_t d, int64_t ld,
                                                          uint8_t* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const char* p = reinterpret_cast<const char*>(x) + row * ld * ES;
-    const int64_t bytes = d * ES;
+    const int sub = lane % LPR;
+    const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / LPR) + lane / LPR;
     uint32_t any = 0;
-    const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
-    const int64_t n16 = vec ? bytes / 16 : 0;
-    for (int64_t i = lane; i < n16; i += 32) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
-        if (ES == 4) any |= (v.x | v.y | v.z | v.w) << 1;                      // drop the sign bits
-        else any |= (v.x | v.y | v.z | v.w) & 0x7fff7fffu;
-    }
-    for (int64_t b = n16 * 16 + lane * ES; b < bytes; b += 32 * ES) {
-        if (ES == 4) any |= *reinterpret_cast<const uint32_t*>(p + b) << 1;
-        else any |= (uint32_t)(*reinterpret_cast<const uint16_t*>(p + b) & 0x7fffu);
+    if (row < rows) {
+        const char* p = reinterpret_cast<const char*>(x) + row * ld * ES;
+        const int64_t bytes = d * ES;
+        const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
+        const int64_t n16 = vec ? bytes / 16 : 0;
+        for (int64_t i = sub; i < n16; i += LPR) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
+            if (ES == 4) any |= (v.x | v.y | v.z | v.w) << 1;                      // drop the sign bits
+            else any |= (v.x | v.y | v.z | v.w) & 0x7fff7fffu;
+        }
+        for (int64_t b = n16 * 16 + sub * ES; b < bytes; b += LPR * ES) {
+            if (ES == 4) any |= *reinterpret_cast<const uint32_t*>(p + b) << 1;
+            else any |= (uint32_t)(*reinterpret_cast<const uint16_t*>(p + b) & 0x7fffu);
+        }
     }
     const unsigned m = __ballot_sync(0xffffffffu, any != 0u);
-    if (lane == 0) flags[row] = m != 0u;
+    const unsigned grp = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
+    if (sub == 0 && row < rows) flags[row] = (m & grp) != 0u;
+}
+
+template <int ES>
+static void launch_row_any(const void* x, int64_t rows, int64_t d, int64_t ld, uint8_t* flags, cudaStream_t st) {
+    const int64_t n16 = (d * ES + 15) / 16;      // 16-byte pieces per row
+    if (n16 <= 4)
+        k_row_any_nonzero<ES, 4><<<(unsigned)ceil_div(rows, 8 * 8), 256, 0, st>>>(x, rows, d, ld, flags);
+    else if (n16 <= 8)
+        k_row_any_nonzero<ES, 8><<<(unsigned)ceil_div(rows, 8 * 4), 256, 0, st>>>(x, rows, d, ld, flags);
+    else if (n16 <= 16)
+        k_row_any_nonzero<ES, 16><<<(unsigned)ceil_div(rows, 8 * 2), 256, 0, st>>>(x, rows, d, ld, flags);
+    else
+        k_row_any_nonzero<ES, 32><<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(x, rows, d, ld, flags);
 }
 
 static int prep_blocks(int64_t rows) {
@@ -470,11 +487,8 @@ int cb_row_any_nonzero(const void* x, int dtype, int64_t rows, int64_t d, int64_
     CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_row_any_nonzero: unknown dtype");
     if (rows == 0) return CB_OK;
     CB_REQUIRE(x && flags, CB_E_INVALID, "cb_row_any_nonzero: NULL buffer");
-    const unsigned grid = (unsigned)ceil_div(rows, 8);
-    if (dtype == CB_BF16)
-        k_row_any_nonzero<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, d, ld, flags);
-    else
-        k_row_any_nonzero<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, d, ld, flags);
+    if (dtype == CB_BF16) launch_row_any<2>(x, rows, d, ld, flags, (cudaStream_t)stream);
+    else launch_row_any<4>(x, rows, d, ld, flags, (cudaStream_t)stream);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

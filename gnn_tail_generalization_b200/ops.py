@@ -1,3 +1,28 @@
+        live = push_live = live_full = None
+        if self.row_sparse_hint and slot is not None and add is None:
+            # multi-GPU: a zero row of the incoming gradient gives a zero row of G -- known BEFORE the GEMM (one pass
+            # over the [M, K] gradient), so such rows are neither pushed to the peers nor gathered by anyone.  The
+            # flags of every rank are all-gathered HERE, ahead of the first panel's GEMM: the side-stream gathers wait
+            # only for their panel's event, which is recorded after this point, so they can never read a half-written
+            # flag array.
+            push_live = row_any_nonzero_raw(dtot_in)
+            live_full = compact_live_raw(g, C.CB_BY_SRC, g.exchange_flags(push_live))   # the compacted workspace
+        elif self.row_sparse_hint:
+            # one GPU: the kernel reports which rows of G it stored non-zero (free in its epilogue).  Measured
+            # alternative (scripts/grad_sparse_bench.py): flags from the input rows + skipping every load and store of
+            # the dead rows (a_live / x0_valid of cb_gemm_rows_grad) -- 6.79 vs 6.85 ms for the GEMM, plus 1.7 ms for
+            # the flag pass: this GEMM is not bound by the bytes it moves, so skipping them buys nothing here.
+            live = torch.zeros(dtot_in.shape[0], dtype=torch.uint8, device=dtot_in.device)
+        accumulate = sink is not None and sink.buf is not None
+        out, col, d_x0 = gemm_rows_grad_raw(
+            dtot_in, wb, row_scale=rs, add=add, gate_u8=self.gate_u8, gate_f32=self.gate_f32 if self.relu else None,
+            mixed=self.mixed, alpha=self.alpha, d_x0=sink.buf if sink is not None else None,
+            accumulate_x0=accumulate, want_x0=self.want_x0,
+            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot, row_live=live,
+            push_live=push_live, x0_valid=sink.valid if accumulate else None)
+        if sink is not None:
+            sink.valid = None                    # a dense writer: every row holds its sum now
+            sink.buf, d_x0 = d_x0, None
 """Autograd bindings of the C-ABI kernels: what the replacement GCNConv calls where the reference
 called DGL (GNN_model/GCN.py:198-253) and elementwise PyTorch ops.
 

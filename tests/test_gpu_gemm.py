@@ -340,3 +340,20 @@ def test_gemm_rows_grad_skips_rows_flagged_dead_and_sink_stays_consistent(dtype)
     taken = sink.take()
     assert sink.buf is None and sink.valid is None
     assert bool((taken[dead] == 0).all()) and bool((taken[~dead] == 1).all())
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('d', [1, 3, 16, 40, 64, 128, 300])
+def test_row_any_nonzero(d, dtype):
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(d)
+    M = 5003
+    x = torch.zeros(M, d, device='cuda')
+    rows = torch.randperm(M, device='cuda', generator=g)[: M // 3]
+    cols = torch.randint(0, d, (rows.numel(),), device='cuda', generator=g)
+    x[rows, cols] = torch.randn(rows.numel(), device='cuda', generator=g) + 3.0
+    x[rows[0], :] = 0
+    x[rows[0], d - 1] = -0.0                      # a negative zero is a zero
+    x = x.to(dtype)
+    flags = ops.row_any_nonzero_raw(x)
+    assert torch.equal(flags.bool(), (x != 0).any(1))

@@ -453,7 +453,51 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             tc_fence_after();
             const int64_t row0 = tile * BM + q * 32;
             const int n_slabs = min(BN, g.N - n0 + 31) / 32;
+            // Per-row epilogue operands do not depend on the slab: loaded once per tile (they used to be re-loaded in
+            // every slab, each time a dependent DRAM / L2 round trip in front of the slab's arithmetic).
+            const int64_t rbase = row0 + rsub;
+            const int64_t left = (g.M - rbase + 3) >> 2;
+            const int nrow = left <= 0 ? 0 : (left < 8 ? (int)left : 8);
+            float rsv[8], psv[8];         // GRAD: row_scale, post_scale; forward: row_scale, out2_scale
+            uint32_t lm_rows = nrow >= 8 ? 0xffu : ((1u << nrow) - 1u), vm_rows = 0xffu;
+            if (GRAD) {
+                if (g.a_live) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        if (((lm_rows >> itr) & 1u) && __ldg(g.a_live + rbase + itr * 4) == 0) lm_rows &= ~(1u << itr);
+                }
+                if (g.x0_valid) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        if (itr < nrow && __ldg(g.x0_valid + rbase + itr * 4) == 0) vm_rows &= ~(1u << itr);
+                }
+                if (g.post_scale) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        if (itr < nrow) psv[itr] = __ldg(g.post_scale + rbase + itr * 4);
+                }
+            } else if (g.out2) {
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr)
+                    if (itr < nrow) psv[itr] = __ldg(g.out2_scale + rbase + itr * 4);
+            }
+            if (g.row_scale) {
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr)
+                    if (itr < nrow) rsv[itr] = __ldg(g.row_scale + rbase + itr * 4);
+            }
             for (int j = 0; j < n_slabs; ++j) {
+                // the slab's streamed gate words are requested BEFORE the accumulator is read, so that their latency
+                // overlaps the TMEM load and the transpose
+                const int col_pre = n0 + j * 32 + c4 * 4;
+                const uint32_t lm_pre = col_pre < g.N ? lm_rows : 0u;
+                uint32_t gm[8];
+                if (GRAD && g.gate_u8) {
+                    const uint8_t* p = g.gate_u8 + rbase * g.ld_gate + col_pre;
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        if ((lm_pre >> itr) & 1u) gm[itr] = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)itr * 4 * g.ld_gate));
+                }
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + j * 32), r);
                 tmem_ld_wait();
@@ -474,53 +518,24 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     // (same operations, in the same order, as cb_gemm_rows followed by cb_agg_backward_prep).
                     // Every option is a uniform branch around a straight pass over the lane's 8 x float4
                     // register tile, so no per-element predicates are executed; rows are valid for itr < nval.
-                    const int64_t rbase = row0 + rsub;
-                    const int64_t left = (g.M - rbase + 3) >> 2;
-                    const int nval = !col_ok || left <= 0 ? 0 : (left < 8 ? (int)left : 8);
+                    const int nval = col_ok ? nrow : 0;
                     float4 av[8], gy[8];      // add or old d_x0 (mutually exclusive); fp32 gate source
-                    float rsv[8], psv[8];
-                    uint32_t gm[8];
                     const bool acc_x0 = g.d_x0 && g.accumulate_x0;
                     // rows this lane really works on: inside M, and -- with a_live -- not known to be all-zero
-                    uint32_t lm = nval >= 8 ? 0xffu : ((1u << nval) - 1u);
-                    if (g.a_live) {
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            if (((lm >> itr) & 1u) && __ldg(g.a_live + rbase + itr * 4) == 0) lm &= ~(1u << itr);
-                    }
+                    const uint32_t lm = col_ok ? lm_rows : 0u;
                     if (g.add || acc_x0) {
                         const int64_t ld = g.add ? g.ld_add : g.ld_dx0;
                         const S* p = reinterpret_cast<const S*>(g.add ? g.add : g.d_x0) + rbase * ld + col;
-                        uint32_t vm = lm;           // rows whose old d_x0 exists
-                        if (!g.add && g.x0_valid) {
-#pragma unroll
-                            for (int itr = 0; itr < 8; ++itr)
-                                if (((vm >> itr) & 1u) && __ldg(g.x0_valid + rbase + itr * 4) == 0) vm &= ~(1u << itr);
-                        }
+                        const uint32_t vm = g.add ? lm : (lm & vm_rows);           // rows whose old d_x0 exists
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
                             av[itr] = ((vm >> itr) & 1u) ? ld4_cs(p + (int64_t)itr * 4 * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    if (g.gate_u8) {
-                        const uint8_t* p = g.gate_u8 + rbase * g.ld_gate + col;
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            if ((lm >> itr) & 1u) gm[itr] = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)itr * 4 * g.ld_gate));
-                    } else if (g.gate_f32) {
+                    if (!g.gate_u8 && g.gate_f32) {
                         const S* p = reinterpret_cast<const S*>(g.gate_f32) + rbase * g.ld_gate + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
                             if ((lm >> itr) & 1u) gy[itr] = ld4_g(p + (int64_t)itr * 4 * g.ld_gate);
-                    }
-                    if (g.row_scale) {
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) rsv[itr] = __ldg(g.row_scale + rbase + itr * 4);
-                    }
-                    if (g.post_scale) {
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) psv[itr] = __ldg(g.post_scale + rbase + itr * 4);
                     }
                     float4 v[8];
 #pragma unroll
@@ -629,11 +644,8 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 }
                 {
                     // forward epilogue, same structure: v = act(rs*acc + bias + add); out = v; out2 = s2*v
-                    const int64_t rbase = row0 + rsub;
-                    const int64_t left = (g.M - rbase + 3) >> 2;
-                    const int nval = !col_ok || left <= 0 ? 0 : (left < 8 ? (int)left : 8);
+                    const int nval = col_ok ? nrow : 0;
                     float4 av[8];
-                    float rsv[8], s2v[8];
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (g.bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(g.bias + col));
                     if (g.add) {
@@ -641,16 +653,6 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr)
                             if (itr < nval) av[itr] = ld4_cs(p + (int64_t)itr * 4 * g.ld_add);
-                    }
-                    if (g.row_scale) {
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) rsv[itr] = __ldg(g.row_scale + rbase + itr * 4);
-                    }
-                    if (g.out2) {
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nval) s2v[itr] = __ldg(g.out2_scale + rbase + itr * 4);
                     }
                     float4 v[8];
 #pragma unroll
@@ -696,7 +698,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         S* p = reinterpret_cast<S*>(g.out2) + rbase * g.ld_out2 + col;
 #pragma unroll
                         for (int itr = 0; itr < 8; ++itr) {
-                            const float s_ = s2v[itr];
+                            const float s_ = psv[itr];
                             const float4 w = make_float4(__fmul_rn(v[itr].x, s_), __fmul_rn(v[itr].y, s_),
                                                          __fmul_rn(v[itr].z, s_), __fmul_rn(v[itr].w, s_));
                             if (itr < nval) st4_cs(p + (int64_t)itr * 4 * g.ld_out2, w);

@@ -603,30 +603,40 @@ class BwdPlan:
         if add is not None and sink is not None and sink.buf is not None:
             return None     # the kernel keeps one [M, N] epilogue input: the caller runs the two-kernel path
         slot = g.push_slot(C.CB_BY_SRC, wb.n, dtot_in.dtype)    # G is what the transposed aggregation gathers
-        live = push_live = live_full = None
-        if self.row_sparse_hint and slot is not None and add is None:
-            # multi-GPU: a zero row of the incoming gradient gives a zero row of G -- known BEFORE the GEMM (one pass
-            # over the [M, K] gradient), so such rows are neither pushed to the peers nor gathered by anyone.  The
-            # flags of every rank are all-gathered HERE, ahead of the first panel's GEMM: the side-stream gathers wait
-            # only for their panel's event, which is recorded after this point, so they can never read a half-written
-            # flag array.
-            push_live = row_any_nonzero_raw(dtot_in)
-            live_full = compact_live_raw(g, C.CB_BY_SRC, g.exchange_flags(push_live))   # the compacted workspace
+        live = push_live = live_full = a_live = kernel_live = None
+        if self.row_sparse_hint and add is None:
+            # A zero row of the incoming gradient gives a zero row of dtot, of G and of the d_x0 contribution -- known
+            # BEFORE the GEMM (one pass over the [M, K] gradient, cb_row_any_nonzero).  Such rows are not loaded, not
+            # stored, not pushed to the peers and not gathered by anyone: the GEMM, the pushes and the compacted
+            # gather all go by the same flags, and the x0 sink remembers which of its rows were never written.
+            # Measured at the bench shape (scripts/grad_sparse_bench.py): 7.48 -> 5.75 + 0.90 ms for this GEMM and
+            # 12.2 -> 10.2 ms for the next one, which no longer reads the 90 % of d_x0 that would have been zeros.
+            a_live = row_any_nonzero_raw(dtot_in)
+            if slot is not None:
+                # multi-GPU: the flags of every rank are all-gathered HERE, ahead of the first panel's GEMM: the
+                # side-stream gathers wait only for their panel's event, which is recorded after this point, so
+                # they can never read a half-written flag array.
+                push_live = a_live
+                live_full = compact_live_raw(g, C.CB_BY_SRC, g.exchange_flags(a_live))   # the compacted workspace
+            else:
+                live = a_live
         elif self.row_sparse_hint:
-            # one GPU: the kernel reports which rows of G it stored non-zero (free in its epilogue).  Measured
-            # alternative (scripts/grad_sparse_bench.py): flags from the input rows + skipping every load and store of
-            # the dead rows (a_live / x0_valid of cb_gemm_rows_grad) -- 6.79 vs 6.85 ms for the GEMM, plus 1.7 ms for
-            # the flag pass: this GEMM is not bound by the bytes it moves, so skipping them buys nothing here.
-            live = torch.zeros(dtot_in.shape[0], dtype=torch.uint8, device=dtot_in.device)
+            # `add` makes rows non-zero that the incoming gradient does not: the kernel reports what it stored
+            live = kernel_live = torch.zeros(dtot_in.shape[0], dtype=torch.uint8, device=dtot_in.device)
         accumulate = sink is not None and sink.buf is not None
         out, col, d_x0 = gemm_rows_grad_raw(
             dtot_in, wb, row_scale=rs, add=add, gate_u8=self.gate_u8, gate_f32=self.gate_f32 if self.relu else None,
             mixed=self.mixed, alpha=self.alpha, d_x0=sink.buf if sink is not None else None,
             accumulate_x0=accumulate, want_x0=self.want_x0,
-            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot, row_live=live,
-            push_live=push_live, x0_valid=sink.valid if accumulate else None)
+            post_scale=g.din_inv_sqrt, want_col_sum=self.want_bias, push=slot, row_live=kernel_live,
+            push_live=push_live, a_live=a_live, x0_valid=sink.valid if accumulate else None)
         if sink is not None:
-            sink.valid = None                    # a dense writer: every row holds its sum now
+            if a_live is None:
+                sink.valid = None                    # a dense writer: every row holds its sum now
+            elif not accumulate:
+                sink.valid = a_live                  # first writer skipped the dead rows: they count as zero
+            elif sink.valid is not None:
+                sink.valid = sink.valid | a_live     # rows written now or before
             sink.buf, d_x0 = d_x0, None
         self.result = {'d_bias': col, 'd_x0': d_x0, 'G': out, 'live': live, 'live_full': live_full}
         if out.dim() == 3:

@@ -12,12 +12,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcoldbrew_b200.so')
 
 CB_OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 CB_ACT_NONE, CB_ACT_RELU = 0, 1
 CB_BY_DST, CB_BY_SRC = 0, 1
 CB_F32, CB_BF16 = 0, 1
 
-Q_NUM_NODES, Q_NUM_EDGES, Q_ROW_BEGIN, Q_ROW_END, Q_HAS_ZERO_IN_DEG, Q_HUB_CHUNK = 0, 1, 2, 3, 4, 5
+Q_NUM_NODES, Q_NUM_EDGES, Q_ROW_BEGIN, Q_ROW_END, Q_HAS_ZERO_IN_DEG, Q_HUB_CHUNK, Q_SRC_PANELS = 0, 1, 2, 3, 4, 5, 6
+Q_DST_ROWPTR_EXP, Q_SRC_ROWPTR_EXP = 14, 25
 Q_DST_ROWPTR, Q_DST_COL, Q_DST_PERM, Q_DST_NUM_HUB_CHUNKS = 10, 11, 12, 13
 Q_SRC_ROWPTR, Q_SRC_COL, Q_SRC_PERM, Q_SRC_NUM_HUB_CHUNKS, Q_SRC_NUM_EDGES = 20, 21, 22, 23, 24
 Q_DIN_INV_SQRT, Q_DOUT_INV_SQRT, Q_IN_DEGREE, Q_OUT_DEGREE = 30, 31, 32, 33
@@ -29,7 +30,8 @@ class PeerPush(ctypes.Structure):
     """cb_peer_push_t: where the rows of a kernel output go besides its local `out`."""
     _fields_ = [('n_peers', ctypes.c_int32), ('max_ctas', ctypes.c_int32),
                 ('peer', ctypes.c_void_p * CB_MAX_PEERS), ('need', ctypes.c_void_p),
-                ('row0', ctypes.c_int64), ('ld', ctypes.c_int64), ('row_live', ctypes.c_void_p)]
+                ('row0', ctypes.c_int64), ('ld', ctypes.c_int64), ('row_live', ctypes.c_void_p),
+                ('tile_first', ctypes.c_int32), ('tile_step', ctypes.c_int32)]
 
 
 # every symbol include/coldbrew_b200.h declares: name -> (restype, argtypes)
@@ -40,6 +42,8 @@ SYMBOLS = {
     'cb_graph_create': (_int, [_vp, _i64, _i64, _int, _vp, ctypes.POINTER(_vp)]),
     'cb_graph_create_sliced': (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp, ctypes.POINTER(_vp)]),
     'cb_graph_create_local': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _vp, ctypes.POINTER(_vp)]),
+    'cb_graph_create_panelled': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _vp,
+                                        ctypes.POINTER(_vp)]),
     'cb_graph_destroy': (_int, [_vp]),
     'cb_graph_query': (_int, [_vp, _int, _vp]),
     'cb_graph_workspace_bytes': (_i64, [_vp, _int, _i64]),
@@ -47,6 +51,9 @@ SYMBOLS = {
     'cb_agg_gather': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_agg_forward_bf16': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     'cb_agg_gather_bf16': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    'cb_agg_forward_pass': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _i64, _int, _vp, _vp,
+                                   _i64, _vp]),
+    'cb_agg_gather_pass': (_int, [_vp, _int, _int, _vp, _i64, _i64, _vp, _vp, _i64, _int, _vp, _vp, _i64, _vp]),
     'cb_agg_propagate': (_int, [_vp, _int, _vp, _i64, _vp, _vp, _dbl, _dbl, _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp]),
     'cb_graph_live_workspace_bytes': (_i64, [_vp, _int]),
     'cb_graph_compact_live': (_int, [_vp, _int, _vp, _vp, _i64, _vp]),

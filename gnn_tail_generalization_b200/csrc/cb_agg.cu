@@ -56,6 +56,11 @@ struct AggArgs {
     int clamp;
     float clamp_lo, clamp_hi;
     int64_t task0;              // first task of a k_agg launch (0, or n_rows when the rows went to k_gather_sparse_rows)
+    // source-panel pass (cb_agg_*_pass on a graph built with src_panels S > 1): this launch walks only the group of
+    // panel `panel` of every row and continues the row's in-order sum through `carry` (fp32 [rows, d])
+    const int64_t* rowptr_exp;  // [rows*S+1] or null
+    int n_panels, panel;
+    float* carry;
     const int2* row_be;         // compacted plain gather: (begin, end) per row with hub rows emptied, else null
 };
 
@@ -232,13 +237,21 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
     int64_t row, beg, end;
     if (!is_chunk) {
         row = task;
-        beg = __ldg(a.rowptr + row);
-        end = __ldg(a.rowptr + row + 1);
-        // hub row: its chunks and k_combine produce it
-        if (a.hub_rowptr) {
-            if (__ldg(a.hub_rowptr + row + 1) - __ldg(a.hub_rowptr + row) > a.hub_chunk) return;
-        } else if (end - beg > a.hub_chunk) {
-            return;
+        if (a.rowptr_exp) {
+            const int64_t* re = a.rowptr_exp + row * a.n_panels;
+            // hub row (by its whole degree): its chunks and k_combine produce it, in the last pass
+            if (__ldg(re + a.n_panels) - __ldg(re) > a.hub_chunk) return;
+            beg = __ldg(re + a.panel);
+            end = __ldg(re + a.panel + 1);
+        } else {
+            beg = __ldg(a.rowptr + row);
+            end = __ldg(a.rowptr + row + 1);
+            // hub row: its chunks and k_combine produce it
+            if (a.hub_rowptr) {
+                if (__ldg(a.hub_rowptr + row + 1) - __ldg(a.hub_rowptr + row) > a.hub_chunk) return;
+            } else if (end - beg > a.hub_chunk) {
+                return;
+            }
         }
     } else {
         const int64_t c = task - a.n_rows;
@@ -261,6 +274,12 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
         cval[ch] = cofs[ch] < a.d;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
+    }
+    const bool pass_row = a.rowptr_exp != nullptr && !is_chunk;
+    if (pass_row && a.panel > 0) {       // continue the in-order sum of the earlier panels
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            if (cval[ch]) Vec<VEC>::load_plain(acc[ch], a.carry + row * a.d + cofs[ch]);
     }
 
     for (int64_t base = beg; base < end; base += LPR) {
@@ -297,6 +316,10 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch)
             if (cval[ch]) Vec<VEC>::store(pr + cofs[ch], acc[ch]);
+    } else if (pass_row && a.panel < a.n_panels - 1) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            if (cval[ch]) Vec<VEC>::store(a.carry + row * a.d + cofs[ch], acc[ch]);
     } else {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch)
@@ -405,6 +428,7 @@ static int launch_cfg(const AggArgs& a_in, cudaStream_t st) {
         CB_LAUNCH_CHECK();
         a.task0 = a.n_rows;      // k_agg below: the hub chunks only
     }
+    if (a.rowptr_exp && a.panel < a.n_panels - 1) a.n_chunks = 0;    // hub rows: whole, in the last pass
     const int64_t tasks = a.n_rows + a.n_chunks - a.task0;
     if (tasks > 0) {
         const int64_t blocks = ceil_div(tasks, (int64_t)WARPS * GROUPS);
@@ -448,8 +472,19 @@ static int launch_vec(AggArgs a, cudaStream_t st) {
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int run_agg(const cb_graph* g, int side_id, int dtype, AggArgs a, void* workspace, int64_t workspace_bytes,
-                   cudaStream_t st, const void* live_ws = nullptr) {
+                   cudaStream_t st, const void* live_ws = nullptr, int panel = -1, float* carry = nullptr) {
     const Side& s = side_id == CB_BY_DST ? g->by_dst : g->by_src;
+    if (panel >= 0) {
+        CB_REQUIRE(g->src_panels > 1 && s.rowptr_exp != nullptr, CB_E_INVALID,
+                   "aggregation pass: the graph was not built with source panels (cb_graph_create_panelled)");
+        CB_REQUIRE(panel < g->src_panels, CB_E_INVALID, "aggregation pass: panel out of range");
+        CB_REQUIRE(carry != nullptr || g->rows == 0, CB_E_INVALID, "aggregation pass: carry buffer is NULL");
+        CB_REQUIRE(live_ws == nullptr, CB_E_UNSUPPORTED, "aggregation pass over compacted lists is not supported");
+        a.rowptr_exp = s.rowptr_exp;
+        a.n_panels = g->src_panels;
+        a.panel = panel;
+        a.carry = carry;
+    }
     a.rowptr = s.rowptr;
     a.col = s.col;
     a.n_rows = g->rows;
@@ -486,7 +521,8 @@ static int run_agg(const cb_graph* g, int side_id, int dtype, AggArgs a, void* w
 
 static int agg_forward_impl(const cb_graph* g, int dtype, const void* H, int64_t ld_h, int64_t d, const float* bias,
                             const void* x0, double alpha, int act, void* out, void* out_scaled, uint8_t* mask,
-                            int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream) {
+                            int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream, int panel = -1,
+                            float* carry = nullptr) {
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_forward: graph is NULL");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_forward: d must be positive");
     if (g->rows == 0) return CB_OK;       // a slice that owns no rows: nothing to aggregate (buffers may be NULL)
@@ -510,12 +546,13 @@ static int agg_forward_impl(const cb_graph* g, int dtype, const void* H, int64_t
     a.out2_scale = g->dout_is;
     a.out2 = out_scaled;
     a.mask = mask;
-    return run_agg(g, CB_BY_DST, dtype, a, workspace, workspace_bytes, (cudaStream_t)stream);
+    return run_agg(g, CB_BY_DST, dtype, a, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, panel, carry);
 }
 
 static int agg_gather_impl(const cb_graph* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
                            const float* row_scale, const uint8_t* row_live, void* out, int64_t ld_out, void* workspace,
-                           int64_t workspace_bytes, void* stream, const void* live_ws = nullptr) {
+                           int64_t workspace_bytes, void* stream, const void* live_ws = nullptr, int panel = -1,
+                           float* carry = nullptr) {
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_gather: graph is NULL");
     CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_agg_gather: unknown side");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_gather: d must be positive");
@@ -532,7 +569,7 @@ static int agg_gather_impl(const cb_graph* g, int side, int dtype, const void* X
     a.act = CB_ACT_NONE;
     a.out = out;
     a.live = row_live;
-    return run_agg(g, side, dtype, a, workspace, workspace_bytes, (cudaStream_t)stream, live_ws);
+    return run_agg(g, side, dtype, a, workspace, workspace_bytes, (cudaStream_t)stream, live_ws, panel, carry);
 }
 
 }  // namespace cb
@@ -573,6 +610,24 @@ int cb_agg_gather_compacted(const cb_graph_t* g, int side, int dtype, const void
     CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_agg_gather_compacted: unknown dtype");
     return cb::agg_gather_impl(g, side, dtype, X, ld_x, d, row_scale, nullptr, out, ld_out, workspace,
                                workspace_bytes, stream, live_ws);
+}
+
+int cb_agg_forward_pass(const cb_graph_t* g, int dtype, const void* H, int64_t ld_h, int64_t d, const float* bias,
+                        const void* x0, double alpha, int act, void* out, void* out_scaled, uint8_t* mask, int64_t ld_out,
+                        int panel, float* carry, void* workspace, int64_t workspace_bytes, void* stream) {
+    CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_agg_forward_pass: unknown dtype");
+    CB_REQUIRE(panel >= 0, CB_E_INVALID, "cb_agg_forward_pass: negative panel");
+    return cb::agg_forward_impl(g, dtype, H, ld_h, d, bias, x0, alpha, act, out, out_scaled, mask, ld_out, workspace,
+                                workspace_bytes, stream, panel, carry);
+}
+
+int cb_agg_gather_pass(const cb_graph_t* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
+                       const float* row_scale, void* out, int64_t ld_out, int panel, float* carry, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+    CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_agg_gather_pass: unknown dtype");
+    CB_REQUIRE(panel >= 0, CB_E_INVALID, "cb_agg_gather_pass: negative panel");
+    return cb::agg_gather_impl(g, side, dtype, X, ld_x, d, row_scale, nullptr, out, ld_out, workspace, workspace_bytes,
+                               stream, nullptr, panel, carry);
 }
 
 int cb_agg_propagate(const cb_graph_t* g, int side, const float* X, int64_t d, const float* row_scale, const float* y,

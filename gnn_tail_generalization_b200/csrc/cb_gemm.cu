@@ -94,6 +94,7 @@ struct GemmArgs {
     void* out2;              // [M, ld_out2] or null (S)
     int64_t ld_out2;
     int64_t n_tiles_m;
+    int tile_first, tile_step;   // this launch's 128-row tiles: tile_first, tile_first + tile_step, ... (0, 1 = all)
     // ---- gradient epilogue (k_gemm_rows<S, BN, true>): the backward prologue of the layer below ----
     const uint8_t* gate_u8;   // [M, ld_gate] relu mask bytes, or null
     const void* gate_f32;     // [M, ld_gate] relu output in S (gate = value > 0), or null
@@ -338,7 +339,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (warp == 0) {
         // ===== TMA producer =====
         uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x) {
+        for (int64_t tile = g.tile_first + (int64_t)blockIdx.x * g.tile_step; tile < g.n_tiles_m; tile += (int64_t)gridDim.x * g.tile_step) {
             {   // epilogue operands of this tile -> L2 (the epilogue reads them about one tile later)
                 const int64_t r0 = tile * BM;
                 const int nr = (int)(g.M - r0 < BM ? g.M - r0 : BM);
@@ -367,7 +368,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // ===== MMA issuer =====
         constexpr uint32_t idesc = instr_desc<S, BN>();
         uint32_t it = 0, tl = 0;
-        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x, ++tl) {
+        for (int64_t tile = g.tile_first + (int64_t)blockIdx.x * g.tile_step; tile < g.n_tiles_m; tile += (int64_t)gridDim.x * g.tile_step, ++tl) {
             const int acc = tl & 1u;
             const uint32_t aph = (tl >> 1) & 1u;
             mbar_wait(tempty_bar(acc), aph ^ 1u);
@@ -409,7 +410,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // ===== split warps: raw fp32 A chunk -> TF32 hi (in place) + lo  (idle for bf16 operands) =====
         const int t = threadIdx.x - 64;
         uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; SPLIT && tile < g.n_tiles_m; tile += gridDim.x) {
+        for (int64_t tile = g.tile_first + (int64_t)blockIdx.x * g.tile_step; SPLIT && tile < g.n_tiles_m; tile += (int64_t)gridDim.x * g.tile_step) {
             for (int kc = 0; kc < nk; ++kc, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
@@ -446,7 +447,7 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             __syncwarp();
         }
         uint32_t tl = 0;
-        for (int64_t tile = blockIdx.x; tile < g.n_tiles_m; tile += gridDim.x, ++tl) {
+        for (int64_t tile = g.tile_first + (int64_t)blockIdx.x * g.tile_step; tile < g.n_tiles_m; tile += (int64_t)gridDim.x * g.tile_step, ++tl) {
             const int acc = tl & 1u;
             const uint32_t aph = (tl >> 1) & 1u;
             mbar_wait(tfull_bar(acc), aph);
@@ -814,7 +815,9 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mh, const CUten
                                      C::SMEM_BYTES));
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
-    dim3 grid((unsigned)gemm_grid_x(g.n_tiles_m, g.push.max_ctas), (unsigned)ceil_div(g.N, BN));
+    const int64_t my_tiles = g.n_tiles_m > g.tile_first ? ceil_div(g.n_tiles_m - g.tile_first, g.tile_step) : 0;
+    if (my_tiles == 0) return CB_OK;      // a panel without tiles on this rank
+    dim3 grid((unsigned)gemm_grid_x(my_tiles, g.push.max_ctas), (unsigned)ceil_div(g.N, BN));
     k_gemm_rows<S, BN, GRAD><<<grid, THREADS, C::SMEM_BYTES, st>>>(ma, mh, ml, g);
     CB_LAUNCH_CHECK();
     return CB_OK;
@@ -882,6 +885,8 @@ static int gemm_rows_impl(const S* A, int64_t M, int64_t K, int64_t lda, const S
     g.out = out; g.ld_out = ld_out; g.out2_scale = out2_scale; g.out2 = out2; g.ld_out2 = ld_out2;
     if (push) g.push = *push;
     g.n_tiles_m = ceil_div(M, BM);
+    g.tile_first = (push && push->tile_step > 0) ? push->tile_first : 0;
+    g.tile_step = (push && push->tile_step > 0) ? push->tile_step : 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (bn == 64) return launch_gemm<S, 64, false>(ma, mh, ml, g, st);
     if (bn == 128) return launch_gemm<S, 128, false>(ma, mh, ml, g, st);
@@ -941,14 +946,21 @@ static int gemm_rows_grad_impl(const S* A, int64_t M, int64_t K, int64_t lda, co
     g.a_live = a_live;
     g.x0_valid = (d_x0 && accumulate_x0) ? x0_valid : nullptr;
     if (push) g.push = *push;
+    g.tile_first = (push && push->tile_step > 0) ? push->tile_first : 0;
+    g.tile_step = (push && push->tile_step > 0) ? push->tile_step : 1;
     cudaStream_t st = (cudaStream_t)stream;
     rc = bn == 64 ? launch_gemm<S, 64, true>(ma, mh, ml, g, st)
                   : (bn == 128 ? launch_gemm<S, 128, true>(ma, mh, ml, g, st)
                                : launch_gemm<S, 256, true>(ma, mh, ml, g, st));
     if (rc) return rc;
     if (col_sum) {
+        const int64_t my_tiles = g.n_tiles_m > g.tile_first ? ceil_div(g.n_tiles_m - g.tile_first, g.tile_step) : 0;
+        if (my_tiles == 0) {
+            CB_CUDA(cudaMemsetAsync(col_sum, 0, (size_t)N * sizeof(float), st));
+            return CB_OK;
+        }
         k_col_final<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(
-            (const float*)workspace, (int)gemm_grid_x(g.n_tiles_m, g.push.max_ctas), (int)N, col_sum);
+            (const float*)workspace, (int)gemm_grid_x(my_tiles, g.push.max_ctas), (int)N, col_sum);
         CB_LAUNCH_CHECK();
     }
     return CB_OK;

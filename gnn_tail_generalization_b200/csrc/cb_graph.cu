@@ -49,21 +49,25 @@ __global__ void k_edge_keys(const int64_t* __restrict__ src, const int64_t* __re
 
 // One side only (cb_graph_create_local): sort key = local row of the owned endpoint, degree count, range check.
 __global__ void k_edge_keys_side(const int64_t* __restrict__ own_end, const int64_t* __restrict__ other_end, int64_t E,
-                                 int64_t N, int64_t row_begin, int64_t row_end, uint32_t* __restrict__ key,
-                                 int32_t* __restrict__ eid, int32_t* __restrict__ deg, int* __restrict__ err) {
+                                 int64_t N, int64_t row_begin, int64_t row_end, int panels, int filter,
+                                 uint32_t* __restrict__ key, int32_t* __restrict__ eid, int32_t* __restrict__ deg,
+                                 int32_t* __restrict__ deg_exp, int* __restrict__ err) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const uint32_t rows = (uint32_t)(row_end - row_begin);
+    const uint32_t sentinel = (uint32_t)(row_end - row_begin) * (uint32_t)panels;   // sorts behind every owned edge
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
         const int64_t o = own_end[e], t = other_end[e];
         if (o < 0 || o >= N || t < 0 || t >= N) {
             err[0] = 1;
-            key[e] = rows;
+            key[e] = sentinel;
         } else if (o < row_begin || o >= row_end) {
-            err[2] = 1;          // the caller promised edges of the owned rows only
-            key[e] = rows;
+            if (!filter) err[2] = 1;          // the caller promised edges of the owned rows only
+            key[e] = sentinel;
         } else {
-            key[e] = (uint32_t)(o - row_begin);
-            atomicAdd(deg + (o - row_begin), 1);
+            const uint32_t r = (uint32_t)(o - row_begin);
+            const uint32_t k = panels > 1 ? r * (uint32_t)panels + (uint32_t)((t >> CB_PANEL_SHIFT) % panels) : r;
+            key[e] = k;
+            atomicAdd(deg + r, 1);
+            if (deg_exp) atomicAdd(deg_exp + k, 1);
         }
         eid[e] = (int32_t)e;
     }
@@ -239,6 +243,7 @@ static void free_side(Side& s) {
     cudaFree(s.col);
     cudaFree(s.perm);
     cudaFree(s.deg);
+    cudaFree(s.rowptr_exp);
     cudaFree(s.chunk_row);
     cudaFree(s.chunk_beg);
     s = Side();
@@ -516,9 +521,15 @@ __global__ void __launch_bounds__(256) k_live_offsets(const int64_t* __restrict_
 
 // One CSR side from an edge list that holds exactly the edges of the owned rows on that side.
 static int build_side_local(cb_graph* g, Side& side, const int64_t* own_end, const int64_t* other_end, int64_t E,
-                            float* deg_is, int* zero_flag_host, cudaStream_t st) {
+                            float* deg_is, int* zero_flag_host, cudaStream_t st, int filter = 0) {
     const int64_t rows = g->rows;
+    const int panels = g->src_panels;
     Scratch tmp;
+    int32_t* deg_exp = nullptr;
+    if (panels > 1) {
+        CB_CUDA(tmp.alloc(&deg_exp, rows * panels));
+        CB_CUDA(cudaMemsetAsync(deg_exp, 0, (size_t)(rows * panels > 0 ? rows * panels : 1) * sizeof(int32_t), st));
+    }
     CB_CUDA(cudaMalloc((void**)&side.deg, (size_t)(rows > 0 ? rows : 1) * sizeof(int32_t)));
     CB_CUDA(cudaMemsetAsync(side.deg, 0, (size_t)(rows > 0 ? rows : 1) * sizeof(int32_t), st));
     uint32_t *key = nullptr, *key_alt = nullptr;
@@ -530,12 +541,17 @@ static int build_side_local(cb_graph* g, Side& side, const int64_t* own_end, con
     CB_CUDA(tmp.alloc(&eid, E));
     CB_CUDA(tmp.alloc(&eid_alt, E));
     CB_CUDA(tmp.alloc(&flags, 3));
-    CB_CUDA(tmp.alloc(&spine, ceil_div(rows > 0 ? rows : 1, SCAN_TILE) + 1));
+    CB_CUDA(tmp.alloc(&spine, ceil_div(rows * panels > 0 ? rows * panels : 1, SCAN_TILE) + 1));
     CB_CUDA(cudaMemsetAsync(flags, 0, 3 * sizeof(int), st));
     if (E > 0) {
         k_edge_keys_side<<<grid_for(E, 256), 256, 0, st>>>(own_end, other_end, E, g->n_nodes, g->row_begin, g->row_end,
-                                                           key, eid, side.deg, flags);
+                                                           panels, filter, key, eid, side.deg, deg_exp, flags);
         CB_LAUNCH_CHECK();
+    }
+    if (panels > 1) {
+        CB_CUDA(cudaMalloc((void**)&side.rowptr_exp, (size_t)(rows * panels + 1) * sizeof(int64_t)));
+        int rc_ = exclusive_scan(rows * panels, DegMap{deg_exp}, side.rowptr_exp, spine, st);
+        if (rc_) return rc_;
     }
     k_inv_sqrt_deg<<<grid_for(rows, 256), 256, 0, st>>>(side.deg, rows, deg_is, flags + 1);
     CB_LAUNCH_CHECK();
@@ -545,7 +561,7 @@ static int build_side_local(cb_graph* g, Side& side, const int64_t* own_end, con
     CB_REQUIRE(h_flags[0] == 0, CB_E_RANGE, "edge list holds a node id outside [0, num_nodes)");
     CB_REQUIRE(h_flags[2] == 0, CB_E_RANGE, "cb_graph_create_local: an edge does not belong to the owned row range");
     if (zero_flag_host) *zero_flag_host = h_flags[1];
-    const int end_bit = bits_for((uint32_t)rows);
+    const int end_bit = bits_for((uint32_t)(rows * panels));
     cub::DoubleBuffer<uint32_t> kb(key, key_alt);
     cub::DoubleBuffer<int32_t> vb(eid, eid_alt);
     if (E > 0) {
@@ -655,6 +671,51 @@ int cb_graph_create_local(const int64_t* in_edges, int64_t num_in_edges, const i
     return CB_OK;
 }
 
+int cb_graph_create_panelled(const int64_t* in_edges, int64_t num_in_edges, const int64_t* out_edges,
+                             int64_t num_out_edges, int64_t num_nodes, int64_t row_begin, int64_t row_end,
+                             int hub_chunk, int src_panels, int filter, void* stream, cb_graph_t** out) {
+    using namespace cb;
+    CB_REQUIRE(out != nullptr, CB_E_INVALID, "cb_graph_create_panelled: out is NULL");
+    *out = nullptr;
+    CB_REQUIRE(src_panels == 1 || src_panels == 2 || src_panels == 4, CB_E_INVALID,
+               "cb_graph_create_panelled: src_panels must be 1, 2 or 4");
+    CB_REQUIRE(num_in_edges >= 0 && num_out_edges >= 0 && num_nodes >= 0, CB_E_INVALID,
+               "cb_graph_create_panelled: negative size");
+    CB_REQUIRE((num_in_edges == 0 || in_edges) && (num_out_edges == 0 || out_edges), CB_E_INVALID,
+               "cb_graph_create_panelled: an edge list is NULL");
+    CB_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= num_nodes, CB_E_INVALID,
+               "cb_graph_create_panelled: row range outside [0, num_nodes]");
+    CB_REQUIRE(num_nodes < (int64_t)INT32_MAX && num_in_edges < (int64_t)INT32_MAX &&
+                   num_out_edges < (int64_t)INT32_MAX && (row_end - row_begin) * src_panels < (int64_t)INT32_MAX,
+               CB_E_UNSUPPORTED, "cb_graph_create_panelled: sizes must be < 2^31 per handle");
+    cb_graph* g = new cb_graph();
+    g->n_nodes = num_nodes;
+    g->row_begin = row_begin;
+    g->row_end = row_end;
+    g->rows = row_end - row_begin;
+    g->hub_chunk = hub_chunk > 0 ? hub_chunk : CB_DEFAULT_HUB_CHUNK;
+    g->src_panels = src_panels;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rows1 = g->rows > 0 ? g->rows : 1;
+    int rc = CB_OK;
+    cudaError_t e = cudaGetDevice(&g->device);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
+    if (!rc && (e = cudaMalloc((void**)&g->din_is, (size_t)rows1 * sizeof(float))) != cudaSuccess)
+        rc = cuda_fail(e, "cudaMalloc(din)", __FILE__, __LINE__);
+    if (!rc && (e = cudaMalloc((void**)&g->dout_is, (size_t)rows1 * sizeof(float))) != cudaSuccess)
+        rc = cuda_fail(e, "cudaMalloc(dout)", __FILE__, __LINE__);
+    if (!rc) rc = build_side_local(g, g->by_dst, in_edges + num_in_edges, in_edges, num_in_edges, g->din_is,
+                                   &g->has_zero_in_deg, st, filter);
+    if (!rc) rc = build_side_local(g, g->by_src, out_edges, out_edges + num_out_edges, num_out_edges, g->dout_is,
+                                   nullptr, st, filter);
+    if (rc != CB_OK) {
+        cb_graph_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return CB_OK;
+}
+
 int cb_graph_create(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int hub_chunk,
                     void* stream, cb_graph_t** out) {
     return cb_graph_create_sliced(edge_index, num_edges, num_nodes, 0, num_nodes, hub_chunk, stream, out);
@@ -715,6 +776,9 @@ int cb_graph_query(const cb_graph_t* g, int what, void* out) {
         case CB_Q_ROW_END: *i = g->row_end; break;
         case CB_Q_HAS_ZERO_IN_DEG: *i = g->has_zero_in_deg; break;
         case CB_Q_HUB_CHUNK: *i = g->hub_chunk; break;
+        case CB_Q_SRC_PANELS: *i = g->src_panels; break;
+        case CB_Q_DST_ROWPTR_EXP: *p = g->by_dst.rowptr_exp; break;
+        case CB_Q_SRC_ROWPTR_EXP: *p = g->by_src.rowptr_exp; break;
         case CB_Q_DST_ROWPTR: *p = g->by_dst.rowptr; break;
         case CB_Q_DST_COL: *p = g->by_dst.col; break;
         case CB_Q_DST_PERM: *p = g->by_dst.perm; break;

@@ -17,6 +17,7 @@ struct Side {
     int32_t* col = nullptr;        // [n_edges]
     int32_t* perm = nullptr;       // [n_edges] position of the stored edge in the caller's edge list
     int32_t* deg = nullptr;        // [rows]
+    int64_t* rowptr_exp = nullptr; // [rows*src_panels+1] or null: a row's list grouped by source panel (see cb_graph)
     int64_t n_edges = 0;
     // hub rows (deg > hub_chunk) are cut into chunks; chunk c covers col[chunk_beg[c] .. +hub_chunk)
     int32_t* chunk_row = nullptr;  // [n_chunks] local row of the chunk
@@ -31,6 +32,12 @@ struct cb_graph {
     int64_t row_begin = 0, row_end = 0;
     int64_t rows = 0;
     int hub_chunk = CB_DEFAULT_HUB_CHUNK;
+    // src_panels S > 1: inside every row the stored neighbours are grouped by panel(c) = (c >> CB_PANEL_SHIFT) % S of
+    // their column id c (stable inside a group), so that an aggregation can be run as S passes -- pass p needs only
+    // the source rows of panel p -- whose in-order partial sums continue each other: the exchange of panel p+1
+    // overlaps the aggregation of panel p at FULL row width.  The grouping does not depend on the slicing, so every
+    // world size sums in the same order.
+    int src_panels = 1;
     int has_zero_in_deg = 0;
     cb::Side by_dst, by_src;
     float* din_is = nullptr;      // [rows]

@@ -25,11 +25,15 @@ class GraphHandle:
 
     world = 1
 
-    def __init__(self, edge_index, num_nodes, row_begin=0, row_end=None, hub_chunk=0, local_out_edges=None):
+    def __init__(self, edge_index, num_nodes, row_begin=0, row_end=None, hub_chunk=0, local_out_edges=None,
+                 src_panels=1):
         """edge_index [2, E] int64 on the device.  By default it is the whole edge list and the handle keeps the
         edges of the rows [row_begin, row_end).  With ``local_out_edges`` (cb_graph_create_local) ``edge_index`` holds
         only the edges whose DESTINATION is owned and ``local_out_edges`` those whose SOURCE is owned (for a symmetric
-        graph: the same list with its rows swapped) -- the full list of a 10^9-edge graph never exists."""
+        graph: the same list with its rows swapped) -- the full list of a 10^9-edge graph never exists.
+        src_panels (1, 2, 4): group every row's stored neighbours by source panel (cb_graph_create_panelled) so that an
+        aggregation can run as that many passes, each needing only the source rows of its panel; the grouping (hence
+        the summation order) is the same for every slicing of the graph."""
         def check(t, what):
             if not (torch.is_tensor(t) and t.is_cuda):
                 raise ValueError(f'{what} must be a CUDA tensor (this path has no CPU implementation)')
@@ -41,8 +45,14 @@ class GraphHandle:
         self.num_nodes = int(num_nodes)
         row_end = self.num_nodes if row_end is None else int(row_end)
         self._h = ctypes.c_void_p()
+        self.src_panels = int(src_panels)
         with torch.cuda.device(self.device):
-            if local_out_edges is None:
+            if self.src_panels > 1:
+                eo = check(local_out_edges, 'local_out_edges') if local_out_edges is not None else ei
+                C.call('cb_graph_create_panelled', C.ptr(ei), ei.shape[1], C.ptr(eo), eo.shape[1], self.num_nodes,
+                       int(row_begin), row_end, int(hub_chunk), self.src_panels, int(local_out_edges is None),
+                       C.stream_ptr(self.device), ctypes.byref(self._h))
+            elif local_out_edges is None:
                 C.call('cb_graph_create_sliced', C.ptr(ei), ei.shape[1], self.num_nodes, int(row_begin), row_end,
                        int(hub_chunk), C.stream_ptr(self.device), ctypes.byref(self._h))
             else:
@@ -92,6 +102,21 @@ class GraphHandle:
             buf = torch.empty(need, dtype=torch.uint8, device=self.device)
             self._ws[key] = buf
         return buf, need
+
+    def carry(self, d):
+        """fp32 [rows, d] buffer through which the source-panel passes of one aggregation hand on the row sums."""
+        buf = self._ws.get(('carry', d))
+        if buf is None:
+            buf = torch.empty((self.rows, d), dtype=torch.float32, device=self.device)
+            self._ws[('carry', d)] = buf
+        return buf
+
+    def rowptr_exp(self, side=C.CB_BY_DST):
+        """int64 [rows*src_panels+1]: offsets of every (row, source panel) group (None when src_panels == 1)."""
+        if self.src_panels == 1:
+            return None
+        return self._view(C.Q_DST_ROWPTR_EXP if side == C.CB_BY_DST else C.Q_SRC_ROWPTR_EXP,
+                          self.rows * self.src_panels + 1, '<i8').clone()
 
     def close(self):
         if getattr(self, '_h', None):

@@ -94,14 +94,17 @@ def _pofs(t, elems):
 
 
 def agg_forward_raw(graph, H, bias=None, x0=None, alpha=0.0, relu=False, want_out=True, want_scaled=False,
-                    want_mask=False, outs=None, panel=None):
+                    want_mask=False, outs=None, panel=None, src_pass=None):
     """One fused forward aggregation over the owned rows.  H holds every source row ([N_global, d]).
 
     H fp32 -> cb_agg_forward; H bf16 -> cb_agg_forward_bf16 (x0 and the outputs are then bf16 too; the sums, the
     bias and the epilogue stay fp32).
     panel=(c0, w): H is the [N_global, w] column panel c0..c0+w of a wider matrix; bias / x0 / the outputs are
     the full-width [.., D] tensors (``outs`` = (out, out_scaled, mask) preallocated) and only their columns
-    c0..c0+w are read / written."""
+    c0..c0+w are read / written.
+    src_pass=p: source-panel pass p of a graph built with src_panels > 1 (cb_agg_forward_pass): only the neighbours of
+    that panel are added, the row sums travel through ``graph.carry(d)``; the last pass writes the outputs (``outs``
+    preallocated by the caller, shared by all passes)."""
     _need_cuda(H, bias, x0)
     if H.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError(f'H must be float32 or bfloat16, got {H.dtype}')
@@ -125,6 +128,16 @@ def agg_forward_raw(graph, H, bias=None, x0=None, alpha=0.0, relu=False, want_ou
     alg = gather_alg_bytes(graph, C.CB_BY_DST, d, int(out is not None) + int(out_scaled is not None),
                            1 + int(x0 is not None), mask is not None, 1 + int(out_scaled is not None), es)
     fn, name = ('cb_agg_forward', 'agg_forward') if st == torch.float32 else ('cb_agg_forward_bf16', 'agg_forward_bf16')
+    if src_pass is not None:
+        if panel is not None:
+            raise ValueError('source-panel passes work at full row width')
+        carry = graph.carry(d)
+        with torch.cuda.device(H.device), _Timed(name + '_pass', alg // graph.src_panels + 2 * graph.rows * d * 4, H.device):
+            C.call('cb_agg_forward_pass', graph.handle, C.CB_F32 if st == torch.float32 else C.CB_BF16, C.ptr(H), d, d,
+                   C.ptr(bias), C.ptr(x0), float(alpha), C.CB_ACT_RELU if relu else C.CB_ACT_NONE, C.ptr(out),
+                   C.ptr(out_scaled), C.ptr(mask), D, int(src_pass), C.ptr(carry), C.ptr(ws), ws_bytes,
+                   C.stream_ptr(H.device))
+        return out, out_scaled, mask
     with torch.cuda.device(H.device), _Timed(name, alg, H.device):
         C.call(fn, graph.handle, C.ptr(H), d, d, _pofs(bias, c0), _pofs(x0, c0), float(alpha),
                C.CB_ACT_RELU if relu else C.CB_ACT_NONE, _pofs(out, c0), _pofs(out_scaled, c0), _pofs(mask, c0), D,
@@ -151,7 +164,8 @@ def compact_live_raw(graph, side, live):
     return ws
 
 
-def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None, live=None, live_ws=None, flag_walk=False):
+def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None, live=None, live_ws=None, flag_walk=False,
+                   src_pass=None):
     """out[r] = row_scale[r] * sum_{j in row r} X[col[j]]  over one CSR side of the graph (X fp32 or bf16).
     panel=(c0, w): X is a [N_global, w] column panel; ``out`` is the preallocated full-width result.
     live: uint8 [N_global], 0 where the row of X is known to be all-zero (not gathered): the side is first
@@ -181,6 +195,15 @@ def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None, live=No
     sparse = live is not None or live_ws is not None
     name = ('agg_gather_dst' if side == C.CB_BY_DST else 'agg_gather_src') + ('_rowsparse' if sparse else '') + \
         ('' if st == torch.float32 else '_bf16')
+    if src_pass is not None:
+        if sparse or panel is not None:
+            raise ValueError('source-panel passes: dense gathers at full row width only')
+        carry = graph.carry(d)
+        with torch.cuda.device(X.device), _Timed(name + '_pass', alg // graph.src_panels + 2 * graph.rows * d * 4, X.device):
+            C.call('cb_agg_gather_pass', graph.handle, side, C.CB_F32 if st == torch.float32 else C.CB_BF16, C.ptr(X), d,
+                   d, C.ptr(row_scale), C.ptr(out), D, int(src_pass), C.ptr(carry), C.ptr(ws), ws_bytes,
+                   C.stream_ptr(X.device))
+        return out
     if sparse and not flag_walk:
         if live_ws is None:
             live_ws = compact_live_raw(graph, side, live)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 4   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid */
+#define CB_ABI_VERSION 5   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid; 5: source panels */
 
 enum {
     CB_OK = 0,
@@ -56,6 +56,9 @@ enum {
     CB_Q_ROW_END = 3,        /* int64: one past the last owned node */
     CB_Q_HAS_ZERO_IN_DEG = 4,/* int64: 1 if an owned node has no in-edge (GCN.py:187-188) */
     CB_Q_HUB_CHUNK = 5,      /* int64: rows longer than this are summed chunk-wise */
+    CB_Q_SRC_PANELS = 6,     /* int64: source panels the rows are grouped by (1 = plain order) */
+    CB_Q_DST_ROWPTR_EXP = 14,/* const int64_t* [rows*panels+1] or NULL: offsets of every (row, panel) group */
+    CB_Q_SRC_ROWPTR_EXP = 25,
     CB_Q_DST_ROWPTR = 10,    /* const int64_t* [rows+1] */
     CB_Q_DST_COL = 11,       /* const int32_t* [E_dst]  source id of every stored in-edge */
     CB_Q_DST_PERM = 12,      /* const int32_t* [E_dst]  position in the caller's edge list */
@@ -118,6 +121,21 @@ int cb_graph_create_local(const int64_t* in_edges, int64_t num_in_edges, const i
                           int64_t num_out_edges, int64_t num_nodes, int64_t row_begin, int64_t row_end, int hub_chunk,
                           void* stream, cb_graph_t** out);
 
+/*
+ * Same again, with the stored neighbours of every row grouped by SOURCE PANEL: panel(c) = (c >> CB_PANEL_SHIFT) %
+ * src_panels of the column id c (128-row blocks dealt round-robin; inside a group the order of the list is kept).
+ * An aggregation can then run as src_panels passes (cb_agg_forward_pass / cb_agg_gather_pass): pass p touches only
+ * source rows of panel p and continues the in-order partial sums of pass p-1, so on a node-sliced graph the exchange
+ * of panel p+1 (the producing GEMM launched on the row tiles of that panel, cb_peer_push_t.tile_first / tile_step)
+ * overlaps the aggregation of panel p at full row width.  The grouping is a property of the graph, not of the
+ * slicing: every world size, 1 included, sums in the same order.  src_panels in {1, 2, 4}; 1 = cb_graph_create_local.
+ * filter != 0: the lists may hold edges of other slices (e.g. the whole edge list twice), which are dropped.
+ */
+#define CB_PANEL_SHIFT 7
+int cb_graph_create_panelled(const int64_t* in_edges, int64_t num_in_edges, const int64_t* out_edges,
+                             int64_t num_out_edges, int64_t num_nodes, int64_t row_begin, int64_t row_end,
+                             int hub_chunk, int src_panels, int filter, void* stream, cb_graph_t** out);
+
 int cb_graph_destroy(cb_graph_t* g);
 int cb_graph_query(const cb_graph_t* g, int what, void* out);
 
@@ -167,6 +185,21 @@ int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, i
 
 int cb_agg_gather_bf16(const cb_graph_t* g, int side, const uint16_t* X, int64_t ld_x, int64_t d,
                        const float* row_scale, const uint8_t* row_live, uint16_t* out, int64_t ld_out, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
+/*
+ * One source-panel pass of cb_agg_forward / cb_agg_gather on a graph built by cb_graph_create_panelled (dtype CB_F32 /
+ * CB_BF16 of H, x0, out, out_scaled / of X, out): pass `panel` adds the neighbours of that panel, in stored order, to the
+ * row sums left in `carry` (fp32 [rows, d]; pass 0 starts them) and writes them back; the LAST pass (panel = src_panels -
+ * 1) applies the epilogue and stores the outputs, and also produces the hub rows (chunks over their whole lists, which
+ * need every panel).  After the last pass the outputs are bit-identical to the one-pass calls.  The caller runs the
+ * passes of one aggregation in order on one stream, each after the rows of its panel have arrived.
+ */
+int cb_agg_forward_pass(const cb_graph_t* g, int dtype, const void* H, int64_t ld_h, int64_t d, const float* bias,
+                        const void* x0, double alpha, int act, void* out, void* out_scaled, uint8_t* mask, int64_t ld_out,
+                        int panel, float* carry, void* workspace, int64_t workspace_bytes, void* stream);
+int cb_agg_gather_pass(const cb_graph_t* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
+                       const float* row_scale, void* out, int64_t ld_out, int panel, float* carry, void* workspace,
                        int64_t workspace_bytes, void* stream);
 
 /*
@@ -276,6 +309,8 @@ typedef struct {
     int64_t ld;                  /* row pitch of the remote buffers, elements */
     const uint8_t* row_live;     /* [M] device or NULL: rows with 0 are known to be all-zero and are not pushed
                                     (the receivers skip them with the same flags, cb_agg_gather row_live) */
+    int32_t tile_first;          /* source-panel exchange (cb_graph_create_panelled): this launch computes and pushes */
+    int32_t tile_step;           /* only the 128-row tiles tile_first, tile_first + tile_step, ...; 0 / 0 = every tile */
 } cb_peer_push_t;
 int cb_peer_alloc(int64_t bytes, void** ptr, void* handle_out /* CB_PEER_HANDLE_BYTES */);
 int cb_peer_open(const void* handle, void** ptr);

@@ -55,6 +55,14 @@ def parse():
                    help='N>1, push: column panels the exchange is pipelined in against the aggregation '
                         '(0 = auto: 4 at 8 GPUs where the push dominates, else 1; measured, see DESIGN.md 7)')
     p.add_argument('--push-ctas', type=int, default=64, help='N>1, panels>1: grid cap of a pushing GEMM')
+    p.add_argument('--src-panels', type=int, default=0,
+                   help='source panels the neighbour lists are grouped by (1, 2, 4; 0 = auto = 1: plain edge-list order; '
+                        'the same value must be used at every N for bit-identical sums)')
+    p.add_argument('--passes', default='auto', choices=['auto', 'on', 'off'],
+                   help='N>1, push, src-panels>1: pipeline every dense exchange by source panel at full row width '
+                        '(producing GEMM per panel, aggregation pass per panel through a carry buffer).  auto = off: '
+                        'measured slower than the one-launch exchange (2 x B200: 142 / 121 ms with 2 / 4 panels vs '
+                        '86 ms, profiles/r02w_*), kept as a tested feature of the library')
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--cpu-nodes', type=int, default=1_000_000, help='sample size of the CPU baseline / reference arm')
@@ -266,8 +274,15 @@ def run_ours(a):
     else:
         ei = synth.powerlaw_graph(N, und, seed=0, device=dev)          # identical on every rank, sliced by the build
         E = ei.shape[1]
-        graph = cbdist.SlicedGraph(ei, N, rank, world)
+        if a.src_panels <= 0:
+            a.src_panels = 1
+        graph = cbdist.SlicedGraph(ei, N, rank, world, src_panels=a.src_panels)
     del ei
+    a.src_panels = graph.src_panels
+    use_passes = a.src_panels > 1 and world > 1 and a.passes == 'on'
+    if use_passes:
+        a.panels = 1
+        a.push_ctas = a.push_ctas if a.push_ctas != 64 else 0     # the per-panel GEMMs run on the full grid by default
     if a.panels <= 0:
         # panels pay where the push dominates AND a panel row is still a decent gather: 4 x 256-byte rows at cfg4 on
         # 8 GPUs (measured: 48.2 -> 44.7 ms); a 128-dim bf16 row cut in 4 is 64 bytes per gather (cfg5, measured:
@@ -275,7 +290,7 @@ def run_ours(a):
         a.panels = 4 if (world >= 8 and d * es // 4 >= 256) else 1
     if world > 1 and a.exchange == 'push':
         try:
-            graph.enable_push(d, a.panels, a.push_ctas, elem_bytes=es)
+            graph.enable_push(d, a.panels, a.push_ctas, elem_bytes=es, src_passes=use_passes)
         except RuntimeError as e:   # raised on every rank together (PeerExchange); reported in config.parallelism
             if rank == 0:
                 print(f'bench: {e}; using the NCCL all-gather exchange', file=sys.stderr, flush=True)
@@ -502,8 +517,11 @@ def run_ours(a):
                 'vs_baseline': None, 'dtype': 'bf16' if bf16 else 'f32', 'data': 'synthetic',
                 'config': workload_config(a, E),
                 'impl_details': {
-                    'parallelism': (f'node-slice x{world}, exchange={a.exchange}, panels={a.panels}' if world > 1
+                    'parallelism': (f'node-slice x{world}, exchange={a.exchange}, panels={a.panels}, '
+                                    f'source-panel passes={"%d" % a.src_panels if use_passes else "off"}' if world > 1
                                     else 'single GPU'),
+                    'neighbour_order': (f'rows grouped by {a.src_panels} source panels (same order at every N)'
+                                        if a.src_panels > 1 else 'edge-list order'),
                     'gemm': ('tcgen05 kind::f16 on bf16 operands as stored, fp32 accumulate in TMEM' if bf16 else
                              'tcgen05 3xTF32 split (fp32-class accuracy), fp32 accumulate in TMEM'),
                     'se_optimizer': ('cb_se_adam_step (fused Adam + ||E|| gradient' +

@@ -16,6 +16,7 @@ ABI_VERSION = 5
 CB_ACT_NONE, CB_ACT_RELU = 0, 1
 CB_BY_DST, CB_BY_SRC = 0, 1
 CB_F32, CB_BF16 = 0, 1
+CB_PANEL_SHIFT = 7      # source-panel blocks are 128 rows (include/coldbrew_b200.h)
 
 Q_NUM_NODES, Q_NUM_EDGES, Q_ROW_BEGIN, Q_ROW_END, Q_HAS_ZERO_IN_DEG, Q_HUB_CHUNK, Q_SRC_PANELS = 0, 1, 2, 3, 4, 5, 6
 Q_DST_ROWPTR_EXP, Q_SRC_ROWPTR_EXP = 14, 25

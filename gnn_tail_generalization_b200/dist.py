@@ -25,25 +25,30 @@ from .graph import GraphHandle, _DevArray
 ROW_SHARDED_SUFFIXES = ('.le', 'embs')
 
 
-def rows_per_rank(num_nodes, world):
-    return (num_nodes + world - 1) // world
+PANEL_ROWS = 1 << C.CB_PANEL_SHIFT      # rows of one source-panel block (= the row tile of the producing GEMMs)
 
 
-def slice_bounds(num_nodes, world, rank):
+def rows_per_rank(num_nodes, world, align=1):
+    """Rows of every rank but the trailing ones; ``align`` > 1 rounds it up to whole blocks of that many rows."""
+    per = (num_nodes + world - 1) // world
+    return -(-per // align) * align
+
+
+def slice_bounds(num_nodes, world, rank, align=1):
     """[begin, end) of the nodes rank owns; trailing ranks may own fewer (or zero) rows."""
-    per = rows_per_rank(num_nodes, world)
+    per = rows_per_rank(num_nodes, world, align)
     lo = min(rank * per, num_nodes)
     return lo, min(lo + per, num_nodes)
 
 
-def exchange_rows(local, num_nodes, world, group=None):
+def exchange_rows(local, num_nodes, world, group=None, per=None):
     """All-gather of equally sized row blocks -> the [num_nodes, d] matrix of every rank's rows.
 
-    The last block is padded up to ceil(N/P) rows so that one all_gather_into_tensor moves everything;
-    the returned tensor is the contiguous N-row prefix of the gathered buffer."""
+    The last block is padded up to ``per`` (default ceil(N/P)) rows so that one all_gather_into_tensor moves
+    everything; the returned tensor is the contiguous N-row prefix of the gathered buffer."""
     if world == 1:
         return local
-    per = rows_per_rank(num_nodes, world)
+    per = rows_per_rank(num_nodes, world) if per is None else per
     d = local.shape[1]
     send = local
     if local.shape[0] != per:
@@ -91,13 +96,13 @@ def broadcast_dense_params(module, world, group=None, src=0):
             dist.broadcast(p.data, src=src, group=group)
 
 
-def need_masks(col_needed, num_nodes, world, rank, group=None):
+def need_masks(col_needed, num_nodes, world, rank, group=None, per=None):
     """Which local rows each peer gathers.
 
     col_needed: bool/uint8 [per*world] on this rank, 1 where this rank's CSR holds that global column id.
     Returns (mask uint8 [rows_per_rank]: bit j set = peer slot j gathers local row m, peers) where
     ``peers`` lists the remote ranks in slot order."""
-    per = rows_per_rank(num_nodes, world)
+    per = rows_per_rank(num_nodes, world) if per is None else per
     mine = col_needed.to(torch.uint8).contiguous()
     everyone = mine.new_empty((world, per * world))
     if world > 1:
@@ -120,9 +125,19 @@ class PushSlot:
     panel p (HBM-bound, side stream) run while panel p+1 is still crossing NVLink.
 
     ``local`` is what the producer hands to autograd: [rows, width] for one panel, else the
-    [rows, n_panels, panel_width] view of the panel-major buffer."""
+    [rows, n_panels, panel_width] view of the panel-major buffer.
+
+    Source-panel passes (``src_passes`` S > 1, graphs built with src_panels = S; one column panel): the producer is
+    launched S times on the 128-row tiles of source panel 0, 1, ... (``descs[p]``.tile_first / tile_step), each
+    launch followed by ``pushed(p)``; aggregation pass p (cb_agg_*_pass) needs only those rows, so it runs at FULL
+    row width on the side stream while the tiles of panel p+1 are still being computed and pushed."""
     __slots__ = ('owner', 'width', 'local_rows', 'n_panels', 'panel_width', 'panel_full', 'panel_local', 'descs',
-                 'local', 'events', 'pushed_rows', 'keep', 'dtype')
+                 'local', 'events', 'pushed_rows', 'keep', 'dtype', 'src_passes')
+
+    @property
+    def n_launches(self):
+        """Producer launches (= barriers = events) of this exchange."""
+        return self.n_panels if self.src_passes == 1 else self.src_passes
 
     def pushed(self, p):
         dist.all_reduce(self.owner._flag, op=dist.ReduceOp.SUM, group=self.owner.group)
@@ -146,14 +161,17 @@ class PeerExchange:
     exchange #i-1, which every rank enters only after its aggregation #i-2 -- the last reader of b -- is
     complete (the compute stream waits for the side stream that ran it)."""
 
-    def __init__(self, graph, max_d, group=None, panels=1, push_ctas=0, elem_bytes=4):
-        """elem_bytes: bytes per element of the widest matrix exchanged (4: fp32 features, 2: a bf16-only model)."""
+    def __init__(self, graph, max_d, group=None, panels=1, push_ctas=0, elem_bytes=4, src_passes=True):
+        """elem_bytes: bytes per element of the widest matrix exchanged (4: fp32 features, 2: a bf16-only model).
+        src_passes: on a graph built with src_panels > 1, run every dense exchange as that many source-panel passes
+        (False: the grouping of the neighbour lists is kept, the exchange is the one-launch / column-panel one)."""
         self.graph, self.group = graph, group
+        self.src_passes = bool(src_passes) and graph.src_panels > 1
         self.world, self.rank = graph.world, graph.rank
         if not 2 <= self.world <= C.CB_MAX_PEERS + 1:
             raise ValueError(f'PeerExchange supports 2..{C.CB_MAX_PEERS + 1} ranks, got {self.world}')
         self.dev = graph.device
-        self.per = rows_per_rank(graph.num_nodes, self.world)
+        self.per = graph.per
         self.n_pad = self.per * self.world
         self.max_d = int(max_d)
         self.panels, self.push_ctas = max(1, int(panels)), int(push_ctas)
@@ -205,7 +223,7 @@ class PeerExchange:
             col = graph.csr(side)[1]
             needed = torch.zeros(self.n_pad, dtype=torch.uint8, device=self.dev)
             needed[col.long()] = 1
-            mask, peers = need_masks(needed, graph.num_nodes, self.world, self.rank, group)
+            mask, peers = need_masks(needed, graph.num_nodes, self.world, self.rank, group, per=self.per)
             assert peers == self.peers
             self.need[side] = mask
             rows = mask[:graph.rows].to(torch.int32)
@@ -215,19 +233,22 @@ class PeerExchange:
         self._pending, self._views = {}, {}
         dist.barrier(group=group)   # every rank has mapped every buffer before the first push
 
-    def slot(self, side, d, dtype=torch.float32):
-        """The next exchange buffer laid out for a [., d] matrix of ``dtype``; None if it does not fit."""
+    def slot(self, side, d, dtype=torch.float32, passes=True):
+        """The next exchange buffer laid out for a [., d] matrix of ``dtype``; None if it does not fit.
+        passes=False: one producer launch even on a source-panelled graph (the consumer gathers in one go)."""
         es = 4 if dtype == torch.float32 else 2
         vec = 16 // es                 # the aggregation reads rows with 16-byte accesses
         if dtype not in (torch.float32, torch.bfloat16) or d * es > self.row_bytes or d % vec:
             return None
         b = self._turn & 1
         self._turn += 1
-        np_ = self.panels if (d % self.panels == 0 and (d // self.panels) % vec == 0) else 1
+        S = self.graph.src_panels if (passes and self.src_passes) else 1
+        np_ = self.panels if (S == 1 and d % self.panels == 0 and (d // self.panels) % vec == 0) else 1
         pw = d // np_
         lo, rows = self.graph.row_begin, self.graph.rows
         s = PushSlot()
         s.owner, s.width, s.local_rows, s.n_panels, s.panel_width, s.dtype = self, d, rows, np_, pw, dtype
+        s.src_passes = S
         full3 = self._views.get((b, d, np_, dtype))
         if full3 is None:
             if dtype == torch.float32:
@@ -240,16 +261,20 @@ class PeerExchange:
         s.panel_local = [full3[p, lo:lo + rows] for p in range(np_)]
         s.local = s.panel_local[0] if np_ == 1 else full3[:, lo:lo + rows].permute(1, 0, 2)
         s.descs = []
-        for p in range(np_):
+        for p in range(np_ if S == 1 else S):
             desc = C.PeerPush()
             desc.n_peers = len(self.peers)
-            desc.max_ctas = self.push_ctas if np_ > 1 else 0
+            desc.max_ctas = self.push_ctas if (np_ > 1 or S > 1) else 0
             for j, q in enumerate(self._theirs[b]):
-                desc.peer[j] = q + p * self.n_pad * pw * es
+                desc.peer[j] = q + (p * self.n_pad * pw * es if S == 1 else 0)
             desc.need = self.need[side].data_ptr()
             desc.row0, desc.ld = lo, pw
+            if S > 1:
+                # local tile t holds the rows of global block lo/128 + t (the slices are 128-row aligned), whose
+                # source panel is that block index mod S
+                desc.tile_first, desc.tile_step = (p - (lo >> C.CB_PANEL_SHIFT)) % S, S
             s.descs.append(desc)
-        s.events = [None] * np_
+        s.events = [None] * len(s.descs)
         s.pushed_rows, s.keep = self.pushed_rows[side], self.need[side]
         self._pending[s.local.data_ptr()] = s
         return s
@@ -275,12 +300,17 @@ class PeerExchange:
 class SlicedGraph(GraphHandle):
     """This rank's slice of the graph; ``exchange`` is the per-aggregation halo step."""
 
-    def __init__(self, edge_index, num_nodes, rank, world, group=None, hub_chunk=0, local_out_edges=None):
+    def __init__(self, edge_index, num_nodes, rank, world, group=None, hub_chunk=0, local_out_edges=None,
+                 src_panels=1):
         """edge_index: the whole edge list (every rank filters its slice), or -- with ``local_out_edges`` -- only this
-        rank's in-edges, ``local_out_edges`` being its out-edges (see GraphHandle)."""
-        lo, hi = slice_bounds(num_nodes, world, rank)
+        rank's in-edges, ``local_out_edges`` being its out-edges (see GraphHandle).
+        src_panels > 1: neighbour lists grouped by source panel (GraphHandle) and slices of whole 128-row blocks, so
+        that a row tile of the producing GEMM belongs to one panel (``slice_align``)."""
+        self.slice_align = PANEL_ROWS if src_panels > 1 else 1
+        self.per = rows_per_rank(num_nodes, world, self.slice_align)
+        lo, hi = slice_bounds(num_nodes, world, rank, self.slice_align)
         super().__init__(edge_index, num_nodes, row_begin=lo, row_end=hi, hub_chunk=hub_chunk,
-                         local_out_edges=local_out_edges)
+                         local_out_edges=local_out_edges, src_panels=src_panels)
         self.rank, self.world, self.group = rank, world, group
         self.exchanged_bytes = 0
         self.peer = None
@@ -291,17 +321,18 @@ class SlicedGraph(GraphHandle):
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
             self.has_zero_in_degree = bool(int(flag))
 
-    def enable_push(self, max_d, panels=1, push_ctas=0, elem_bytes=4):
+    def enable_push(self, max_d, panels=1, push_ctas=0, elem_bytes=4, src_passes=True):
         """Switch the exchange from an NCCL all-gather after the producing kernel to peer stores from
         inside it (PeerExchange).  ``max_d``: widest matrix that will be exchanged; ``panels`` > 1 pipelines
         the exchange by column panels against the aggregation, ``push_ctas`` caps the grid of a pushing
-        kernel so that the aggregation of the previous panel finds free SMs."""
+        kernel so that the aggregation of the previous panel finds free SMs; on a source-panelled graph the
+        pipelining is by source panel at full row width instead (``src_passes``)."""
         if self.world > 1 and self.peer is None:
-            self.peer = PeerExchange(self, max_d, self.group, panels, push_ctas, elem_bytes)
+            self.peer = PeerExchange(self, max_d, self.group, panels, push_ctas, elem_bytes, src_passes)
         return self.peer
 
-    def push_slot(self, side, d, dtype=torch.float32):
-        return self.peer.slot(side, d, dtype) if self.peer is not None else None
+    def push_slot(self, side, d, dtype=torch.float32, passes=True):
+        return self.peer.slot(side, d, dtype, passes) if self.peer is not None else None
 
     def exchange(self, local_rows):
         """[N, d] tensor of every rank's rows, or -- when the producer pushed them panel by panel -- the
@@ -309,20 +340,19 @@ class SlicedGraph(GraphHandle):
         s = self.peer.take(local_rows) if self.peer is not None else None
         if s is not None:
             self.exchanged_bytes += s.pushed_rows * s.width * (4 if s.dtype == torch.float32 else 2)
-            # one panel: its barrier is already queued on this stream, stream order is enough
-            return s.rows(0, self.num_nodes) if s.n_panels == 1 else s
+            # one launch: its barrier is already queued on this stream, stream order is enough
+            return s.rows(0, self.num_nodes) if s.n_launches == 1 else s
         if local_rows.dim() == 3:
             local_rows = local_rows.reshape(local_rows.shape[0], -1)
-        full = exchange_rows(local_rows, self.num_nodes, self.world, self.group)
+        full = exchange_rows(local_rows, self.num_nodes, self.world, self.group, per=self.per)
         if self.world > 1:
-            self.exchanged_bytes += (self.world - 1) * rows_per_rank(self.num_nodes, self.world) * \
-                local_rows.shape[1] * local_rows.element_size()
+            self.exchanged_bytes += (self.world - 1) * self.per * local_rows.shape[1] * local_rows.element_size()
         return full
 
     def exchange_flags(self, local_flags):
         if self.world == 1:
             return local_flags
-        per = rows_per_rank(self.num_nodes, self.world)
+        per = self.per
         send = local_flags
         if local_flags.shape[0] != per:
             send = local_flags.new_zeros(per)

@@ -348,10 +348,22 @@ def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_s
     wbytes = (2 if wt.lo is not None else 1) * es
     if M == 0:
         if push is not None:      # a rank that owns no rows still takes part in every panel's barrier
-            for p in range(push.n_panels):
+            for p in range(push.n_launches):
                 push.pushed(p)
             out = push.local
         return (out, out2) if want_out2 else out
+    if push is not None and push.src_passes > 1:
+        # source-panel passes: one launch per panel on that panel's 128-row tiles (desc.tile_first / tile_step), all
+        # columns; the rows of panel p are complete everywhere after barrier p
+        S = push.src_passes
+        alg = (es * (M * K + M * N * (1 + int(want_out2) + int(add is not None)) + push.pushed_rows * N)) // S + wbytes * N * K
+        for p in range(S):
+            with torch.cuda.device(A.device), _Timed('gemm_rows_push' + _sfx(st), alg, A.device, flops=mma * M * N * K // S):
+                C.call(fn, C.ptr(A), M, K, K, *_weight_args(wt, 0, K), N, C.ptr(row_scale), C.ptr(bias), C.ptr(add), N,
+                       act, C.ptr(push.local), N, C.ptr(out2_scale), C.ptr(out2), N, ctypes.byref(push.descs[p]),
+                       C.stream_ptr(A.device))
+            push.pushed(p)
+        return (push.local, out2) if want_out2 else push.local
     if push is None:
         alg = es * (M * K + M * N * (int(want_out) + int(want_out2) + int(add is not None))) + wbytes * N * K
         with torch.cuda.device(A.device), _Timed('gemm_rows' + _sfx(st), alg, A.device, flops=mma * M * N * K):
@@ -420,28 +432,40 @@ def gemm_rows_grad_raw(A, wt, row_scale=None, add=None, gate_u8=None, gate_f32=N
     extra = int(add is not None) + int(gate_f32 is not None) + int(d_x0 is not None) * (1 + int(bool(accumulate_x0)))
     if M == 0:
         if push is not None:      # a rank that owns no rows still takes part in every panel's barrier
-            for p in range(push.n_panels):
+            for p in range(push.n_launches):
                 push.pushed(p)
         return out, (col_sum.zero_() if col_sum is not None else None), d_x0
-    panels = [(0, N, None, out)] if push is None else \
-        [(p * push.panel_width, push.panel_width, push.descs[p], push.panel_local[p]) for p in range(push.n_panels)]
+    S = push.src_passes if push is not None else 1
+    if S > 1:       # source-panel passes: every launch covers all columns of its panel's row tiles
+        panels = [(0, N, push.descs[p], out) for p in range(S)]
+    elif push is None:
+        panels = [(0, N, None, out)]
+    else:
+        panels = [(p * push.panel_width, push.panel_width, push.descs[p], push.panel_local[p]) for p in range(push.n_panels)]
     fn, mma = 'cb_gemm_rows_grad' + _sfx(st), (6 if st == torch.float32 else 2)
     wbytes = (2 if wt.lo is not None else 1) * es
+    col_parts = []
     for p, (c0, w, desc, dst) in enumerate(panels):
         if desc is not None:
             desc.row_live = push_live.data_ptr() if push_live is not None else None
-        alg = es * (M * K + M * w * (1 + extra)) + wbytes * w * K + (M * w if gate_u8 is not None else 0) + \
-            (push.pushed_rows * w * es if push is not None else 0)
+        alg = (es * (M * K + M * w * (1 + extra)) + (M * w if gate_u8 is not None else 0) +
+               (push.pushed_rows * w * es if push is not None else 0)) // S + wbytes * w * K
+        # the column sums of a launch cover its row tiles only: one [N] vector per pass, added below in pass order
+        col_p = torch.empty(N, dtype=torch.float32, device=A.device) if (col_sum is not None and S > 1) else col_sum
         with torch.cuda.device(A.device), _Timed(('gemm_rows_grad_push' if push is not None else 'gemm_rows_grad') +
-                                                 _sfx(st), alg, A.device, flops=mma * M * w * K):
+                                                 _sfx(st), alg, A.device, flops=mma * M * w * K // S):
             C.call(fn, C.ptr(A), M, K, K, *_weight_args(wt, c0, K), w,
                    C.ptr(row_scale), _pofs(add, c0), N, _pofs(gate_u8, c0), _pofs(gate_f32, c0),
                    N if gate is not None else 0, int(bool(mixed)), float(alpha), _pofs(d_x0, c0), N,
-                   int(bool(accumulate_x0)), C.ptr(post_scale), C.ptr(dst), dst.shape[1], _pofs(col_sum, c0),
+                   int(bool(accumulate_x0)), C.ptr(post_scale), C.ptr(dst), dst.shape[1], _pofs(col_p, c0),
                    C.ptr(row_live), C.ptr(a_live), C.ptr(x0_valid), C.ptr(ws), ws_bytes,
                    ctypes.byref(desc) if desc is not None else None, C.stream_ptr(A.device))
         if push is not None:
             push.pushed(p)
+        if col_p is not col_sum:
+            col_parts.append(col_p)
+    if col_parts:
+        col_sum.copy_(torch.stack(col_parts).sum(0))
     return out, col_sum, d_x0
 
 
@@ -625,7 +649,9 @@ class BwdPlan:
         sink = self.x0_sink if self.want_x0 else None
         if add is not None and sink is not None and sink.buf is not None:
             return None     # the kernel keeps one [M, N] epilogue input: the caller runs the two-kernel path
-        slot = g.push_slot(C.CB_BY_SRC, wb.n, dtot_in.dtype)    # G is what the transposed aggregation gathers
+        # G is what the transposed aggregation gathers; a row-sparse G is gathered over the compacted lists in one go
+        # (no source-panel passes)
+        slot = g.push_slot(C.CB_BY_SRC, wb.n, dtot_in.dtype, passes=not self.row_sparse_hint)
         live = push_live = live_full = a_live = kernel_live = None
         if self.row_sparse_hint and add is None:
             # A zero row of the incoming gradient gives a zero row of dtot, of G and of the d_x0 contribution -- known
@@ -889,16 +915,16 @@ def _panelled(graph, ex, make_outputs, run_panel, after=None):
     side = ex.side_stream
     if os.environ.get('CB_PANEL_SERIAL'):       # debugging aid: no overlap, everything on the compute stream
         outputs = make_outputs()
-        for p in range(ex.n_panels):
-            run_panel(p, ex.rows(p, graph.num_nodes), outputs)
+        for p in range(ex.n_launches):
+            run_panel(p, ex.rows(p if ex.src_passes == 1 else 0, graph.num_nodes), outputs)
         return outputs
     with torch.cuda.stream(side):
         if after is not None:
             side.wait_event(after)
         outputs = make_outputs()
-        for p in range(ex.n_panels):
+        for p in range(ex.n_launches):
             side.wait_event(ex.events[p])
-            run_panel(p, ex.rows(p, graph.num_nodes), outputs)
+            run_panel(p, ex.rows(p if ex.src_passes == 1 else 0, graph.num_nodes), outputs)
     cur.wait_stream(side)
     for t in outputs:
         if t is not None:
@@ -918,6 +944,9 @@ def aggregate_forward(graph, H, bias, x0, alpha, relu, want_out, want_scaled, wa
                 torch.empty(shape, dtype=H.dtype, device=dev) if want_scaled else None,
                 torch.empty(shape, dtype=torch.uint8, device=dev) if want_mask else None)
 
+    if ex.src_passes > 1:     # source-panel passes at full row width, the sums carried from pass to pass
+        return _panelled(graph, ex, make, lambda p, Hf, outs: agg_forward_raw(
+            graph, Hf, bias, x0, alpha, relu, outs=outs, src_pass=p))
     return _panelled(graph, ex, make, lambda p, Hp, outs: agg_forward_raw(
         graph, Hp, bias, x0, alpha, relu, outs=outs, panel=(p * pw, pw)))
 
@@ -939,7 +968,14 @@ def aggregate_gather(graph, side, X, row_scale=None, live=None, live_full=None):
     if torch.is_tensor(ex):
         return agg_gather_raw(graph, side, ex, row_scale, live_ws=live_ws)
     pw = ex.panel_width
-    (out,) = _panelled(graph, ex, lambda: (torch.empty((graph.rows, ex.width), dtype=X.dtype, device=graph.device),),
+    make = lambda: (torch.empty((graph.rows, ex.width), dtype=X.dtype, device=graph.device),)   # noqa: E731
+    if ex.src_passes > 1:
+        if live_ws is not None:
+            raise RuntimeError('a row-sparse gather takes a one-launch exchange slot (push_slot(passes=False))')
+        (out,) = _panelled(graph, ex, make, lambda p, Xf, outs: agg_gather_raw(graph, side, Xf, row_scale, out=outs[0],
+                                                                                src_pass=p))
+        return out
+    (out,) = _panelled(graph, ex, make,
                        lambda p, Xp, outs: agg_gather_raw(graph, side, Xp, row_scale, out=outs[0], panel=(p * pw, pw),
                                                           live_ws=live_ws), after=flags_event)
     return out

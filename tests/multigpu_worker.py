@@ -105,6 +105,40 @@ def main():
     del whole, ref
     dist.barrier()
 
+    # ---- source-panel passes: neighbour lists grouped by source panel, 128-row aligned slices, the producing GEMMs
+    # launched per panel and the aggregation run as S full-width passes through the carry buffer.  Bit-identical to
+    # the all-gather exchange on the same slices and to ONE GPU on the same (grouped) graph.
+    for S in (2, 4):
+        sg3 = cbdist.SlicedGraph(ei, n, rank, world, src_panels=S)
+        lo3, hi3 = sg3.row_begin, sg3.row_end
+        assert lo3 % 128 == 0 and sg3.per % 128 == 0
+        m3 = make_model(hi3 - lo3, d, Cn, L, dev)
+        x3, y3 = x_all[lo3:hi3].clone(), y_all[lo3:hi3]
+        base3 = [run(m3, sg3, x3, y3, local_idx(t, lo3, hi3), t.numel(), world)[:2] for t in trains]
+        sg3.enable_push(d, push_ctas=ctas)
+        for rep, tv in enumerate((0, 1, 0, 1)):
+            t = trains[tv]
+            lg_p, gr_p, names_p = run(m3, sg3, x3, y3, local_idx(t, lo3, hi3), t.numel(), world)
+            assert names_p.count('agg_forward_pass') == L * S, names_p
+            assert names_p.count('gemm_rows_push') == L * S, names_p
+            assert 'agg_gather_src_pass' in names_p, names_p
+            assert torch.equal(lg_p, base3[tv][0]), f'rank {rank}: S={S} pass logits differ from the all-gather path'
+            for k in base3[tv][1]:
+                if k.endswith('bias'):              # column sums added per pass
+                    scale = float(base3[tv][1][k].abs().max()) + 1e-12
+                    assert float((gr_p[k] - base3[tv][1][k]).abs().max()) <= 1e-5 * scale, k
+                else:
+                    assert torch.equal(gr_p[k], base3[tv][1][k]), f'rank {rank}: S={S} rep {rep} grad {k} differs'
+        whole3 = G.GraphHandle(ei, n, src_panels=S)
+        ref3 = make_model(n, d, Cn, L, dev)
+        lg_one, gr_one, _ = run(ref3, whole3, x_all, y_all, trains[1], trains[1].numel(), 1)
+        assert torch.equal(lg_p, lg_one[lo3:hi3]), f'rank {rank}: S={S} sliced logits differ from the single-GPU run'
+        for k in gr_one:
+            scale = float(gr_one[k].abs().max()) + 1e-12
+            assert float((gr_p[k] - gr_one[k]).abs().max()) <= 2e-5 * scale, k
+        del whole3, ref3
+        dist.barrier()
+
     # ---- a rank without rows: N = world - 1 nodes => ceil(N/P) = 1 row per rank, the last rank owns none ----
     n2 = world - 1
     ring = torch.arange(n2, device=dev)
@@ -130,8 +164,8 @@ def main():
         assert float((gr_b[k] - gr_c[k]).abs().max()) <= 2e-5 * scale, k
     dist.barrier()
     if rank == 0:
-        print(f'multigpu parity ok: world {world}, panels 1 and 4 (push grid {ctas}), changing train rows, '
-              f'zero-row rank; pushed {pushed} bytes on rank 0', flush=True)
+        print(f'multigpu parity ok: world {world}, panels 1 and 4 (push grid {ctas}), source-panel passes 2 and 4, '
+              f'changing train rows, zero-row rank; pushed {pushed} bytes on rank 0', flush=True)
     dist.destroy_process_group()
 
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcoldbrew_b200.so')
 
 CB_OK = 0
-ABI_VERSION = 5
+ABI_VERSION = 6
 CB_ACT_NONE, CB_ACT_RELU = 0, 1
 CB_BY_DST, CB_BY_SRC = 0, 1
 CB_F32, CB_BF16 = 0, 1
@@ -93,6 +93,13 @@ SYMBOLS = {
     'cb_gemm_tn_supported_bf16': (_int, [_i64, _i64, _i64]),
     'cb_gemm_tn_workspace_bytes_bf16': (_i64, [_i64, _i64, _i64]),
     'cb_gemm_tn_bf16': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
+    'cb_prep_degrees': (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    'cb_prep_symmetrize': (_int, [_vp, _i64, _vp, ctypes.POINTER(_i64), _vp]),
+    'cb_prep_partial_sorted_idx': (_int, [_vp, _i64, _int, _int, _vp, ctypes.POINTER(_i64), _vp]),
+    'cb_prep_degree_stats': (_int, [_vp, _i64, ctypes.POINTER(_dbl), _vp]),
+    'cb_prep_sort_idx_by_value': (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    'cb_prep_mask_from_idx': (_int, [_vp, _i64, _i64, _vp, _vp]),
+    'cb_prep_drop_edges': (_int, [_vp, _i64, _vp, _i64, _vp, ctypes.POINTER(_i64), _vp]),
     'cb_topk_merge': (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _int, _vp]),
     'cb_topk_softmax_mix': (_int, [_vp, _vp, _i64, _int, _vp, _i64, _i64, _vp, _vp]),
     'cb_launch_count': (_i64, []),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcoldbrew_b200.so')
-SOURCES = ['cb_graph.cu', 'cb_agg.cu', 'cb_elementwise.cu', 'cb_gemm.cu', 'cb_peer.cu', 'cb_topk.cu']
+SOURCES = ['cb_graph.cu', 'cb_agg.cu', 'cb_elementwise.cu', 'cb_gemm.cu', 'cb_peer.cu', 'cb_topk.cu', 'cb_prep.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 

@@ -1,63 +1,128 @@
-"""Graph preparation either side of the TeacherGNN path, vectorised on the device.
+"""Graph preparation either side of the TeacherGNN path, on the device.
 
-The reference prepares its graphs with O(E) Python loops over ``.tolist()``-ed edge lists
-(``utils.py:300-334`` ``graph_analyze``, ``utils.py:667-674`` ``ensure_symmetric``, ``utils.py:680-752``
+The reference prepares its graphs with O(E) Python loops over ``.tolist()``-ed edge lists and numpy calls on the host
+(``utils.py:300-334`` ``graph_analyze``, ``utils.py:667-674`` ``ensure_symmetric``, ``utils.py:676-752``
 ``save_graph_analyze`` / ``craft_isolation_v2``, ``utils.py:910-943`` ``get_partial_sorted_idx``), which is what makes
-ogbn-arxiv slow and the 10^8-edge configurations impossible through ``main.py``.  These are the same functions --
-same names, arguments, results and result ORDER -- as tensor programs that run wherever their inputs live (the
-tests pin them against the reference's own code on the CPU; on a GPU they are a handful of sort / scan / scatter
-kernels, no host loop, no ``.tolist()``).
+ogbn-arxiv slow and the 10^8-edge configurations impossible through ``main.py``.  These are the same functions -- same
+names, arguments, results and result ORDER -- on the integer kernels of ``csrc/cb_prep.cu`` (C ABI ``cb_prep_*``):
+an atomic histogram pass, a 64-bit radix sort + adjacent-difference compaction, order statistics read off one sorted
+copy, flag / scan / scatter compactions.  CUDA tensors only: there is no host implementation behind these names (the
+CPU restatement the tests check them against lives in ``oracle/graph_prep_oracle.py``).
 """
+import ctypes
+
 import torch
+
+from . import _cabi as C
+
+_LEVELS = {'50': 1, '25': 2, '12': 3, '6': 4, '3': 5}
+
+
+def _edges(edge_index, what='edge_index'):
+    if not (torch.is_tensor(edge_index) and edge_index.is_cuda):
+        raise ValueError(f'{what} must be a CUDA tensor (graph_prep has no CPU implementation)')
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError(f'{what} must be [2, E], got {tuple(edge_index.shape)}')
+    return edge_index.to(torch.int64).contiguous()
+
+
+def _int_array(arr, what):
+    arr = torch.as_tensor(arr)
+    if not arr.is_cuda:
+        raise ValueError(f'{what} must be a CUDA tensor (graph_prep has no CPU implementation)')
+    if arr.is_floating_point() or arr.is_complex():
+        raise TypeError(f'{what}: integer values expected (the reference passes degree counts), got {arr.dtype}')
+    return arr.reshape(-1).to(torch.int64).contiguous()
 
 
 def graph_analyze(N_nodes, edge_index):
     """(degs_ori, degs_dst): edges per node as origin / as destination (utils.py:300-334), int64 tensors on the
-    device of ``edge_index``."""
-    ori, dst = edge_index[0].long(), edge_index[1].long()
-    return torch.bincount(ori, minlength=N_nodes)[:N_nodes], torch.bincount(dst, minlength=N_nodes)[:N_nodes]
+    device of ``edge_index`` (cb_prep_degrees)."""
+    ei = _edges(edge_index)
+    n = int(N_nodes)
+    ori = torch.empty(n, dtype=torch.int64, device=ei.device)
+    dst = torch.empty(n, dtype=torch.int64, device=ei.device)
+    with torch.cuda.device(ei.device):
+        C.call('cb_prep_degrees', C.ptr(ei), ei.shape[1], n, C.ptr(ori), C.ptr(dst), C.stream_ptr(ei.device))
+    return ori, dst
 
 
 def ensure_symmetric(edge_index):
-    """Coalesced indices of A + A^T (utils.py:667-674): every edge and its reverse once, sorted by (row, col)."""
-    ei = edge_index.long()
-    n = int(ei.max()) + 1 if ei.numel() else 0
-    both = torch.cat([ei, ei.flip(0)], dim=1)
-    key = torch.unique(both[0] * n + both[1])          # sorted: the order coalesce() yields
-    return torch.stack([torch.div(key, n, rounding_mode='floor'), key % n]) if n else ei
-
-
-def _np_median(v):
-    """numpy's median (mean of the two middle values for an even count) of a 1-D tensor."""
-    s = torch.sort(v.double()).values
-    k = s.numel()
-    return (s[(k - 1) // 2] + s[k // 2]) / 2
+    """Coalesced indices of A + A^T (utils.py:667-674): every edge and its reverse once, sorted by (row, col)
+    (cb_prep_symmetrize)."""
+    ei = _edges(edge_index)
+    e = ei.shape[1]
+    if e == 0:
+        return ei
+    out = torch.empty((2, 2 * e), dtype=torch.int64, device=ei.device)
+    count = ctypes.c_int64()
+    with torch.cuda.device(ei.device):
+        C.call('cb_prep_symmetrize', C.ptr(ei), e, C.ptr(out), ctypes.byref(count), C.stream_ptr(ei.device))
+    return out[:, :count.value].contiguous()
 
 
 def get_partial_sorted_idx(arr, mode='top25'):
     """Indices of the smallest ('top*') / largest ('bottom*') share of ``arr`` by the reference's repeated-median
-    rule (utils.py:910-943); ascending index order, like ``np.where``."""
-    arr = torch.as_tensor(arr).reshape(-1)
-    a = arr.double()
+    rule (utils.py:910-943); ascending index order, like ``np.where`` (cb_prep_partial_sorted_idx)."""
+    a = _int_array(arr, 'arr')
     top = 'top' in mode
-    levels = {'50': 1, '25': 2, '12': 3, '6': 4, '3': 5}[mode.replace('top', '').replace('bottom', '')]
-    idx = torch.arange(a.numel(), device=a.device)
-    for _ in range(levels):
-        m = _np_median(a[idx])
-        idx = torch.nonzero(a <= m if top else a >= m).reshape(-1)
-    return idx
+    levels = _LEVELS[mode.replace('top', '').replace('bottom', '')]
+    idx = torch.empty(a.numel(), dtype=torch.int64, device=a.device)
+    count = ctypes.c_int64()
+    with torch.cuda.device(a.device):
+        C.call('cb_prep_partial_sorted_idx', C.ptr(a), a.numel(), int(top), levels, C.ptr(idx), ctypes.byref(count),
+               C.stream_ptr(a.device))
+    return idx[:count.value]
+
+
+def degree_stats(degs):
+    """[N, sum, max, mean, median, % zeros] of a degree array: the Table-1 record of utils.py:676-678
+    (cb_prep_degree_stats)."""
+    d = _int_array(degs, 'degs')
+    out = (ctypes.c_double * 6)()
+    with torch.cuda.device(d.device):
+        C.call('cb_prep_degree_stats', C.ptr(d), d.numel(), out, C.stream_ptr(d.device))
+    return [int(out[0]), int(out[1]), int(out[2]), out[3], out[4], out[5]]
+
+
+def sort_idx_by_value(arr, idx):
+    """``idx[argsort(arr[idx])]`` with ties kept in the order of ``idx`` (cb_prep_sort_idx_by_value).
+
+    numpy's default argsort (utils.py:703, introsort, SIMD-dispatched) orders equal keys in a way that depends on the
+    numpy build, and the reference's split of the lowest-degree sixth into "isolated" and "small" halves inherits
+    that; the stable order gives the same node set with the same degrees on each side (tests/test_graph_prep.py
+    checks exactly that against the reference's output)."""
+    a, i = _int_array(arr, 'arr'), _int_array(idx, 'idx')
+    out = torch.empty_like(i)
+    with torch.cuda.device(a.device):
+        C.call('cb_prep_sort_idx_by_value', C.ptr(a), a.numel(), C.ptr(i), i.numel(), C.ptr(out), C.stream_ptr(a.device))
+    return out
+
+
+def mask_of(idx, N_nodes, device=None):
+    """bool [N_nodes], True at ``idx`` (utils.py:694-697, 711-717; cb_prep_mask_from_idx)."""
+    i = _int_array(idx, 'idx')
+    m = torch.empty(int(N_nodes), dtype=torch.bool, device=i.device)
+    with torch.cuda.device(i.device):
+        C.call('cb_prep_mask_from_idx', C.ptr(i), i.numel(), int(N_nodes), C.ptr(m), C.stream_ptr(i.device))
+    return m if device is None else m.to(device)
 
 
 def craft_isolation_v2(data):
     """Removes every non-self-loop edge touching a ``zero_deg_mask`` node, keeping the edge order
-    (utils.py:732-752); sets ``data.edge_index_bkup`` and ``data.edge_index``."""
-    ei = data.edge_index
-    z = data.zero_deg_mask.to(ei.device)
-    ori, dst = ei[0].long(), ei[1].long()
-    drop = (ori != dst) & (z[ori] | z[dst])
-    data.edge_index_bkup = ei
-    data.edge_index = ei[:, ~drop]
-    return int(drop.sum())
+    (utils.py:732-752); sets ``data.edge_index_bkup`` and ``data.edge_index`` (cb_prep_drop_edges).  Returns the
+    number of removed edges."""
+    ei = _edges(data.edge_index, 'data.edge_index')
+    z = data.zero_deg_mask.to(ei.device).to(torch.bool).contiguous()
+    e = ei.shape[1]
+    out = torch.empty((2, e), dtype=torch.int64, device=ei.device)
+    kept = ctypes.c_int64()
+    with torch.cuda.device(ei.device):
+        C.call('cb_prep_drop_edges', C.ptr(ei), e, C.ptr(z), z.numel(), C.ptr(out), ctypes.byref(kept),
+               C.stream_ptr(ei.device))
+    data.edge_index_bkup = data.edge_index
+    data.edge_index = out[:, :kept.value].contiguous()
+    return e - kept.value
 
 
 def save_graph_analyze(N_nodes, data, use_special_split):
@@ -65,35 +130,20 @@ def save_graph_analyze(N_nodes, data, use_special_split):
     its ``np.save`` side effect); returns the Table-1 statistics record."""
     data.N_nodes = N_nodes
     degs_ori, degs_dst = graph_analyze(N_nodes, data.edge_index)
-    d = degs_ori.double()
-    stats = [N_nodes, int(degs_ori.sum()), int(degs_ori.max()), float(d.mean()), float(_np_median(d)),
-             float((degs_ori == 0).sum()) / N_nodes * 100]
+    stats = degree_stats(degs_ori)
     dev = data.x.device
-
-    def mask_of(idx):
-        m = torch.zeros(N_nodes, dtype=torch.bool, device=dev)
-        m[idx.to(dev)] = True
-        return m
-
     if not use_special_split:
         data.small_deg_idx = get_partial_sorted_idx(degs_dst, 'top3')
         data.large_deg_idx = get_partial_sorted_idx(degs_dst, 'bottom3')
-        data.small_deg_mask, data.large_deg_mask = mask_of(data.small_deg_idx), mask_of(data.large_deg_idx)
+        data.small_deg_mask = mask_of(data.small_deg_idx, N_nodes, dev)
+        data.large_deg_mask = mask_of(data.large_deg_idx, N_nodes, dev)
     else:
-        idx = get_partial_sorted_idx(degs_dst, 'top6')
-        idx = idx[_np_argsort(degs_dst[idx])]
+        idx = sort_idx_by_value(degs_dst, get_partial_sorted_idx(degs_dst, 'top6'))
         half = idx.numel() // 2
         data.zero_deg_idx, data.small_deg_idx = idx[:half], idx[half:]
         data.large_deg_idx = get_partial_sorted_idx(degs_dst, 'bottom3')
-        data.zero_deg_mask, data.small_deg_mask = mask_of(data.zero_deg_idx), mask_of(data.small_deg_idx)
-        data.large_deg_mask = mask_of(data.large_deg_idx)
+        data.zero_deg_mask = mask_of(data.zero_deg_idx, N_nodes, dev)
+        data.small_deg_mask = mask_of(data.small_deg_idx, N_nodes, dev)
+        data.large_deg_mask = mask_of(data.large_deg_idx, N_nodes, dev)
         craft_isolation_v2(data)
     return stats
-
-
-def _np_argsort(v):
-    """numpy's default argsort (introsort, not stable, SIMD-dispatched) orders equal keys in a way that depends on
-    the numpy build, and the reference's split of the lowest-degree sixth into "isolated" and "small" halves
-    (utils.py:702-706) inherits that.  A stable sort is used here: same node set, same degrees on each side, ties
-    resolved by node id (tests/test_graph_prep.py checks exactly that against the reference's output)."""
-    return torch.sort(v, stable=True).indices

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 5   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid; 5: source panels */
+#define CB_ABI_VERSION 6   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid; 5: source panels; 6: graph preparation */
 
 enum {
     CB_OK = 0,
@@ -430,6 +430,40 @@ int cb_topk_merge(const float* scores, int64_t B, int64_t width, int64_t ld, int
                   int32_t* top_idx, int first, void* stream);
 int cb_topk_softmax_mix(const float* top_val, const int32_t* top_idx, int64_t B, int K, const float* table, int64_t d,
                         int64_t ld_table, float* out, void* stream);
+
+/*
+ * Graph preparation either side of the path: the reference's host loops over .tolist()-ed edge lists as
+ * integer kernels, same values and the same ORDER.  Setup-time calls: they allocate their own scratch and synchronise
+ * the stream once (a count goes back to the host).  All pointers are device pointers unless marked host.
+ *
+ *   cb_prep_degrees            utils.py:300-334 graph_analyze: edges per node as origin / as destination, int64 [N]
+ *                              (ids >= N are ignored like the reference's range(N_nodes) read-out; negative: CB_E_RANGE)
+ *   cb_prep_symmetrize         utils.py:667-674 ensure_symmetric: the coalesced indices of A + A^T, N = max id + 1,
+ *                              sorted by (row, col).  out: [2, 2 * num_edges] (row pitch 2 * num_edges), *count (host)
+ *                              columns are valid
+ *   cb_prep_partial_sorted_idx utils.py:910-943 get_partial_sorted_idx on an int64 array: `levels` rounds (1..5 = the
+ *                              50 / 25 / 12 / 6 / 3 modes) of "keep what is <= (top != 0) or >= (top == 0) the numpy
+ *                              median of what was kept", then the indices in ascending order: idx_out [n], *count (host)
+ *   cb_prep_degree_stats       utils.py:676-678 gen_rec_for_table1_stats: stats (host, 6 doubles) = N, sum, max, mean,
+ *                              numpy median, percentage of zeros
+ *   cb_prep_sort_idx_by_value  idx[np.argsort(arr[idx], kind='stable')] (utils.py:703-704; numpy's default sort there
+ *                              is not stable, ties are resolved by position in idx here)
+ *   cb_prep_mask_from_idx      mask[N] bytes: 1 at the listed ids, 0 elsewhere (utils.py:694-697, 711-717)
+ *   cb_prep_drop_edges         utils.py:732-752 craft_isolation_v2: drops every edge that is not a self loop and touches
+ *                              a node with node_mask != 0, keeping the order.  out: [2, num_edges] (row pitch num_edges),
+ *                              *kept (host) columns are valid
+ */
+int cb_prep_degrees(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int64_t* degs_ori,
+                    int64_t* degs_dst, void* stream);
+int cb_prep_symmetrize(const int64_t* edge_index, int64_t num_edges, int64_t* out, int64_t* count, void* stream);
+int cb_prep_partial_sorted_idx(const int64_t* arr, int64_t n, int top, int levels, int64_t* idx_out, int64_t* count,
+                               void* stream);
+int cb_prep_degree_stats(const int64_t* degs, int64_t n, double* stats, void* stream);
+int cb_prep_sort_idx_by_value(const int64_t* arr, int64_t n, const int64_t* idx, int64_t m, int64_t* idx_sorted,
+                              void* stream);
+int cb_prep_mask_from_idx(const int64_t* idx, int64_t m, int64_t num_nodes, uint8_t* mask, void* stream);
+int cb_prep_drop_edges(const int64_t* edge_index, int64_t num_edges, const uint8_t* node_mask, int64_t num_nodes,
+                       int64_t* out, int64_t* kept, void* stream);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
 int64_t cb_launch_count(void);

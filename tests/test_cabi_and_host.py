@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(lib, name), name
     lib.cb_abi_version.restype = ctypes.c_int
     from gnn_tail_generalization_b200 import _cabi
-    assert lib.cb_abi_version() == _cabi.ABI_VERSION == 5
+    assert lib.cb_abi_version() == _cabi.ABI_VERSION == 6
     lib.cb_last_error.restype = ctypes.c_char_p
     assert lib.cb_last_error() == b''
     lib.cb_launch_count.restype = ctypes.c_int64

@@ -16,6 +16,8 @@ ABI_VERSION = 6
 CB_ACT_NONE, CB_ACT_RELU = 0, 1
 CB_BY_DST, CB_BY_SRC = 0, 1
 CB_F32, CB_BF16 = 0, 1
+PREP_DEGREES, PREP_SYMMETRIZE, PREP_PARTIAL_SORTED_IDX, PREP_DEGREE_STATS, PREP_SORT_IDX_BY_VALUE, PREP_MASK_FROM_IDX, \
+    PREP_DROP_EDGES = range(7)
 CB_PANEL_SHIFT = 7      # source-panel blocks are 128 rows (include/coldbrew_b200.h)
 
 Q_NUM_NODES, Q_NUM_EDGES, Q_ROW_BEGIN, Q_ROW_END, Q_HAS_ZERO_IN_DEG, Q_HUB_CHUNK, Q_SRC_PANELS = 0, 1, 2, 3, 4, 5, 6
@@ -93,13 +95,14 @@ SYMBOLS = {
     'cb_gemm_tn_supported_bf16': (_int, [_i64, _i64, _i64]),
     'cb_gemm_tn_workspace_bytes_bf16': (_i64, [_i64, _i64, _i64]),
     'cb_gemm_tn_bf16': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
-    'cb_prep_degrees': (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
-    'cb_prep_symmetrize': (_int, [_vp, _i64, _vp, ctypes.POINTER(_i64), _vp]),
-    'cb_prep_partial_sorted_idx': (_int, [_vp, _i64, _int, _int, _vp, ctypes.POINTER(_i64), _vp]),
-    'cb_prep_degree_stats': (_int, [_vp, _i64, ctypes.POINTER(_dbl), _vp]),
-    'cb_prep_sort_idx_by_value': (_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
-    'cb_prep_mask_from_idx': (_int, [_vp, _i64, _i64, _vp, _vp]),
-    'cb_prep_drop_edges': (_int, [_vp, _i64, _vp, _i64, _vp, ctypes.POINTER(_i64), _vp]),
+    'cb_prep_graph_workspace_bytes': (_i64, [_int, _i64]),
+    'cb_prep_degrees': (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    'cb_prep_symmetrize': (_int, [_vp, _i64, _vp, ctypes.POINTER(_i64), _vp, _i64, _vp]),
+    'cb_prep_partial_sorted_idx': (_int, [_vp, _i64, _int, _int, _vp, ctypes.POINTER(_i64), _vp, _i64, _vp]),
+    'cb_prep_degree_stats': (_int, [_vp, _i64, ctypes.POINTER(_dbl), _vp, _i64, _vp]),
+    'cb_prep_sort_idx_by_value': (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp]),
+    'cb_prep_mask_from_idx': (_int, [_vp, _i64, _i64, _vp, _vp, _i64, _vp]),
+    'cb_prep_drop_edges': (_int, [_vp, _i64, _vp, _i64, _vp, ctypes.POINTER(_i64), _vp, _i64, _vp]),
     'cb_topk_merge': (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _int, _vp]),
     'cb_topk_softmax_mix': (_int, [_vp, _vp, _i64, _int, _vp, _i64, _i64, _vp, _vp]),
     'cb_launch_count': (_i64, []),

@@ -62,6 +62,7 @@ struct AggArgs {
     int n_panels, panel;
     float* carry;
     const int2* row_be;         // compacted plain gather: (begin, end) per row with hub rows emptied, else null
+    int prefetch_x0;            // pull the row of x0 into L2 before the neighbour walk (CB_AGG_PREFETCH=0: A/B switch)
 };
 
 template <int VEC>
@@ -276,6 +277,13 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
         for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
     }
     const bool pass_row = a.rowptr_exp != nullptr && !is_chunk;
+    if (a.prefetch_x0 && a.x0 && !is_chunk) {
+        // the epilogue's x0 row is the last dependent DRAM access of a row: request it now, read it from L2 later
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            if (cval[ch])
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const S*>(a.x0) + row * a.o_ld + cofs[ch]));
+    }
     if (pass_row && a.panel > 0) {       // continue the in-order sum of the earlier panels
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch)
@@ -415,7 +423,8 @@ __global__ void __launch_bounds__(256) k_combine(const AggArgs a) {
 template <typename S, int VEC, int LPR, int NCH>
 static int launch_cfg(const AggArgs& a_in, cudaStream_t st) {
     constexpr int GROUPS = 32 / LPR;
-    constexpr int WARPS = 8;
+    static const int warps_env = getenv("CB_AGG_WARPS") ? atoi(getenv("CB_AGG_WARPS")) : 0;    // A/B switch
+    const int WARPS = (warps_env == 1 || warps_env == 2 || warps_env == 4) ? warps_env : 8;
     constexpr int UNROLL = NCH >= 2 ? 4 : 8;   // >= 128 bytes of gathered rows in flight per lane
     constexpr int U = UNROLL < LPR ? UNROLL : LPR;
     AggArgs a = a_in;
@@ -447,8 +456,173 @@ static int launch_cfg(const AggArgs& a_in, cudaStream_t st) {
     return CB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Experiment (round-1 verdict 3d, the north_star's wording): gathered rows staged through shared memory by the bulk-copy
+// engine.  One warp per task as in k_agg; an elected lane issues one cp.async.bulk (global -> shared, a whole feature
+// row, completion counted on an mbarrier) per neighbour into a per-warp ring of R row slots, the warp adds the slots in
+// stored order -- the same in-order fp32 sums, bit-identical outputs.  R rows of a task are in flight without holding
+// them in registers.  Selected with CB_AGG_BULK=R (4 or 8) for full-width fp32 / bf16 rows; measured, see DESIGN.md 9.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > (1u << 24)) __trap();      // a pipeline bug traps instead of hanging the device
+    }
+}
+
+template <typename S, int VEC, int NCH, int R>
+__global__ void __launch_bounds__(256) k_agg_bulk(const AggArgs a) {
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    constexpr int LPR = 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const uint32_t row_bytes = (uint32_t)(a.d * sizeof(S));
+    unsigned char* ring = bulk_smem + (size_t)w * R * row_bytes;
+    const uint32_t bars = smem_addr(bulk_smem + (size_t)W * R * row_bytes) + (uint32_t)w * R * 8u;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8u * r), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int64_t task = a.task0 + (int64_t)blockIdx.x * W + w;
+    if (task >= a.n_rows + a.n_chunks) return;
+    const bool is_chunk = task >= a.n_rows;
+    int64_t row, beg, end;
+    if (!is_chunk) {
+        row = task;
+        beg = __ldg(a.rowptr + row);
+        end = __ldg(a.rowptr + row + 1);
+        if (end - beg > a.hub_chunk) return;      // hub row: its chunks and k_combine produce it
+    } else {
+        const int64_t c = task - a.n_rows;
+        row = __ldg(a.chunk_row + c);
+        beg = __ldg(a.chunk_beg + c);
+        const int64_t rend = __ldg(a.rowptr + row + 1);
+        end = beg + a.hub_chunk < rend ? beg + a.hub_chunk : rend;
+    }
+    float acc[NCH][VEC];
+    int64_t cofs[NCH];
+    bool cval[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        cofs[ch] = (int64_t)(ch * LPR + lane) * VEC;
+        cval[ch] = cofs[ch] < a.d;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[ch][i] = 0.f;
+    }
+    if (a.prefetch_x0 && a.x0 && !is_chunk) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            if (cval[ch])
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const S*>(a.x0) + row * a.o_ld + cofs[ch]));
+    }
+    uint32_t phases = 0;      // bit r: parity the next wait on slot r expects
+    uint32_t head = 0;        // slot of the next row to consume
+    for (int64_t base = beg; base < end; base += 32) {
+        const int nb = (int)(end - base < 32 ? end - base : 32);
+        const int my = lane < nb ? __ldg(a.col + base + lane) : 0;
+        int issued = 0;
+        auto issue = [&](int j) {
+            const int s = __shfl_sync(0xffffffffu, my, j);
+            if (lane == 0) {
+                const uint32_t slot = (head + (uint32_t)j) % R;      // consumption k of this batch uses (head + k) % R
+                const uint32_t bar = bars + 8u * slot;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        smem_addr(ring + (size_t)slot * row_bytes)),
+                    "l"(reinterpret_cast<const S*>(a.X) + (int64_t)s * a.x_ld), "r"(row_bytes), "r"(bar)
+                    : "memory");
+            }
+        };
+        for (; issued < nb && issued < R; ++issued) issue(issued);
+        for (int k = 0; k < nb; ++k) {
+            const uint32_t slot = (head + (uint32_t)k) % R;
+            bulk_wait(bars + 8u * slot, (phases >> slot) & 1u);
+            phases ^= 1u << slot;
+            const S* src = reinterpret_cast<const S*>(ring + (size_t)slot * row_bytes);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                if (cval[ch]) {
+                    float v[VEC];
+                    if constexpr (sizeof(S) == 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(src + cofs[ch]);
+                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                    } else {
+                        Elem<S, VEC>::widen(v, *reinterpret_cast<const uint4*>(src + cofs[ch]));
+                    }
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[ch][i] += v[i];
+                }
+            }
+            __syncwarp();      // every lane has read the slot before the copy engine may overwrite it
+            if (issued < nb) {
+                issue(issued);
+                ++issued;
+            }
+        }
+        head = (head + (uint32_t)nb) % R;
+    }
+    if (is_chunk) {
+        float* pr = a.partial + (task - a.n_rows) * a.d;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            if (cval[ch]) Vec<VEC>::store(pr + cofs[ch], acc[ch]);
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            if (cval[ch]) epilogue_store<S, VEC>(a, row, cofs[ch], acc[ch]);
+    }
+}
+
+template <typename S, int VEC, int NCH, int R>
+static int launch_bulk(const AggArgs& a, cudaStream_t st) {
+    constexpr int WARPS = 8;
+    const size_t smem = (size_t)WARPS * R * (size_t)a.d * sizeof(S) + (size_t)WARPS * R * 8;
+    CB_CUDA(cudaFuncSetAttribute(k_agg_bulk<S, VEC, NCH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t tasks = a.n_rows + a.n_chunks;
+    const int64_t blocks = ceil_div(tasks, (int64_t)WARPS);
+    CB_REQUIRE(blocks < (int64_t)INT32_MAX, CB_E_UNSUPPORTED, "aggregation grid too large");
+    k_agg_bulk<S, VEC, NCH, R><<<(unsigned)blocks, WARPS * 32, smem, st>>>(a);
+    CB_LAUNCH_CHECK();
+    if (a.n_chunks > 0) {
+        k_combine<S, VEC, 32, NCH><<<(unsigned)ceil_div(a.n_chunks, (int64_t)WARPS), WARPS * 32, 0, st>>>(a);
+        CB_LAUNCH_CHECK();
+    }
+    return CB_OK;
+}
+
+// the bulk-copy experiment covers: full-width rows of 128..256 (fp32) / 256..512 (bf16) elements, a contiguous 16-byte
+// aligned source, the plain walk (no live flags, no compacted lists, no source-panel pass)
+template <typename S, int VEC>
+static bool try_bulk(const AggArgs& a, cudaStream_t st, int* rc) {
+    static const int ring = getenv("CB_AGG_BULK") ? atoi(getenv("CB_AGG_BULK")) : 0;
+    if (ring != 4 && ring != 8) return false;
+    const int64_t units = ceil_div(a.d, VEC);
+    if (a.live || a.row_be || a.rowptr_exp || a.hub_rowptr || a.chunk_end || a.col0 != 0 || a.task0 != 0) return false;
+    if (units <= 32 || units > 64 || a.d % VEC != 0 || (a.x_ld * (int64_t)sizeof(S)) % 16 != 0) return false;
+    if ((size_t)8 * ring * a.d * sizeof(S) > 200 * 1024) return false;
+    *rc = ring == 4 ? launch_bulk<S, VEC, 2, 4>(a, st) : launch_bulk<S, VEC, 2, 8>(a, st);
+    return true;
+}
+
 template <typename S, int VEC>
 static int launch_vec(AggArgs a, cudaStream_t st) {
+    if constexpr (VEC > 1) {
+        int rc = CB_OK;
+        if (try_bulk<S, VEC>(a, st, &rc)) return rc;
+    }
     const int64_t units = ceil_div(a.d, VEC);
     if (units <= 1) return launch_cfg<S, VEC, 1, 1>(a, st);
     if (units <= 2) return launch_cfg<S, VEC, 2, 1>(a, st);
@@ -485,6 +659,9 @@ static int run_agg(const cb_graph* g, int side_id, int dtype, AggArgs a, void* w
         a.panel = panel;
         a.carry = carry;
     }
+    // measured at the bench shape: 21.5 -> 20.6 ms per fused forward aggregation (profiles/r02x_*)
+    static const int prefetch_x0 = (getenv("CB_AGG_PREFETCH") && atoi(getenv("CB_AGG_PREFETCH")) == 0) ? 0 : 1;
+    a.prefetch_x0 = prefetch_x0;
     a.rowptr = s.rowptr;
     a.col = s.col;
     a.n_rows = g->rows;

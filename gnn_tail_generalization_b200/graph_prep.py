@@ -35,6 +35,13 @@ def _int_array(arr, what):
     return arr.reshape(-1).to(torch.int64).contiguous()
 
 
+def _ws(what, n, device):
+    """Scratch of one cb_prep_* call, from torch's caching allocator (cudaMalloc / cudaFree of the sort buffers would
+    cost more than the kernels)."""
+    nbytes = int(C.lib().cb_prep_graph_workspace_bytes(what, int(n)))
+    return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device), nbytes
+
+
 def graph_analyze(N_nodes, edge_index):
     """(degs_ori, degs_dst): edges per node as origin / as destination (utils.py:300-334), int64 tensors on the
     device of ``edge_index`` (cb_prep_degrees)."""
@@ -43,7 +50,9 @@ def graph_analyze(N_nodes, edge_index):
     ori = torch.empty(n, dtype=torch.int64, device=ei.device)
     dst = torch.empty(n, dtype=torch.int64, device=ei.device)
     with torch.cuda.device(ei.device):
-        C.call('cb_prep_degrees', C.ptr(ei), ei.shape[1], n, C.ptr(ori), C.ptr(dst), C.stream_ptr(ei.device))
+        ws, nb = _ws(C.PREP_DEGREES, n, ei.device)
+        C.call('cb_prep_degrees', C.ptr(ei), ei.shape[1], n, C.ptr(ori), C.ptr(dst), C.ptr(ws), nb,
+               C.stream_ptr(ei.device))
     return ori, dst
 
 
@@ -57,7 +66,9 @@ def ensure_symmetric(edge_index):
     out = torch.empty((2, 2 * e), dtype=torch.int64, device=ei.device)
     count = ctypes.c_int64()
     with torch.cuda.device(ei.device):
-        C.call('cb_prep_symmetrize', C.ptr(ei), e, C.ptr(out), ctypes.byref(count), C.stream_ptr(ei.device))
+        ws, nb = _ws(C.PREP_SYMMETRIZE, e, ei.device)
+        C.call('cb_prep_symmetrize', C.ptr(ei), e, C.ptr(out), ctypes.byref(count), C.ptr(ws), nb,
+               C.stream_ptr(ei.device))
     return out[:, :count.value].contiguous()
 
 
@@ -70,8 +81,9 @@ def get_partial_sorted_idx(arr, mode='top25'):
     idx = torch.empty(a.numel(), dtype=torch.int64, device=a.device)
     count = ctypes.c_int64()
     with torch.cuda.device(a.device):
+        ws, nb = _ws(C.PREP_PARTIAL_SORTED_IDX, a.numel(), a.device)
         C.call('cb_prep_partial_sorted_idx', C.ptr(a), a.numel(), int(top), levels, C.ptr(idx), ctypes.byref(count),
-               C.stream_ptr(a.device))
+               C.ptr(ws), nb, C.stream_ptr(a.device))
     return idx[:count.value]
 
 
@@ -81,7 +93,8 @@ def degree_stats(degs):
     d = _int_array(degs, 'degs')
     out = (ctypes.c_double * 6)()
     with torch.cuda.device(d.device):
-        C.call('cb_prep_degree_stats', C.ptr(d), d.numel(), out, C.stream_ptr(d.device))
+        ws, nb = _ws(C.PREP_DEGREE_STATS, d.numel(), d.device)
+        C.call('cb_prep_degree_stats', C.ptr(d), d.numel(), out, C.ptr(ws), nb, C.stream_ptr(d.device))
     return [int(out[0]), int(out[1]), int(out[2]), out[3], out[4], out[5]]
 
 
@@ -95,7 +108,9 @@ def sort_idx_by_value(arr, idx):
     a, i = _int_array(arr, 'arr'), _int_array(idx, 'idx')
     out = torch.empty_like(i)
     with torch.cuda.device(a.device):
-        C.call('cb_prep_sort_idx_by_value', C.ptr(a), a.numel(), C.ptr(i), i.numel(), C.ptr(out), C.stream_ptr(a.device))
+        ws, nb = _ws(C.PREP_SORT_IDX_BY_VALUE, i.numel(), a.device)
+        C.call('cb_prep_sort_idx_by_value', C.ptr(a), a.numel(), C.ptr(i), i.numel(), C.ptr(out), C.ptr(ws), nb,
+               C.stream_ptr(a.device))
     return out
 
 
@@ -104,7 +119,9 @@ def mask_of(idx, N_nodes, device=None):
     i = _int_array(idx, 'idx')
     m = torch.empty(int(N_nodes), dtype=torch.bool, device=i.device)
     with torch.cuda.device(i.device):
-        C.call('cb_prep_mask_from_idx', C.ptr(i), i.numel(), int(N_nodes), C.ptr(m), C.stream_ptr(i.device))
+        ws, nb = _ws(C.PREP_MASK_FROM_IDX, 0, i.device)
+        C.call('cb_prep_mask_from_idx', C.ptr(i), i.numel(), int(N_nodes), C.ptr(m), C.ptr(ws), nb,
+               C.stream_ptr(i.device))
     return m if device is None else m.to(device)
 
 
@@ -118,7 +135,8 @@ def craft_isolation_v2(data):
     out = torch.empty((2, e), dtype=torch.int64, device=ei.device)
     kept = ctypes.c_int64()
     with torch.cuda.device(ei.device):
-        C.call('cb_prep_drop_edges', C.ptr(ei), e, C.ptr(z), z.numel(), C.ptr(out), ctypes.byref(kept),
+        ws, nb = _ws(C.PREP_DROP_EDGES, e, ei.device)
+        C.call('cb_prep_drop_edges', C.ptr(ei), e, C.ptr(z), z.numel(), C.ptr(out), ctypes.byref(kept), C.ptr(ws), nb,
                C.stream_ptr(ei.device))
     data.edge_index_bkup = data.edge_index
     data.edge_index = out[:, :kept.value].contiguous()

@@ -433,8 +433,9 @@ int cb_topk_softmax_mix(const float* top_val, const int32_t* top_idx, int64_t B,
 
 /*
  * Graph preparation either side of the path: the reference's host loops over .tolist()-ed edge lists as
- * integer kernels, same values and the same ORDER.  Setup-time calls: they allocate their own scratch and synchronise
- * the stream once (a count goes back to the host).  All pointers are device pointers unless marked host.
+ * integer kernels, same values and the same ORDER.  Setup-time calls: scratch is the caller's
+ * (workspace of cb_prep_graph_workspace_bytes(what, n) bytes, device memory), the stream is synchronised once or twice (a count,
+ * or the key range that sizes the radix sort, goes back to the host).  Device pointers unless marked host.
  *
  *   cb_prep_degrees            utils.py:300-334 graph_analyze: edges per node as origin / as destination, int64 [N]
  *                              (ids >= N are ignored like the reference's range(N_nodes) read-out; negative: CB_E_RANGE)
@@ -453,17 +454,30 @@ int cb_topk_softmax_mix(const float* top_val, const int32_t* top_idx, int64_t B,
  *                              a node with node_mask != 0, keeping the order.  out: [2, num_edges] (row pitch num_edges),
  *                              *kept (host) columns are valid
  */
+enum {  /* `what` of cb_prep_graph_workspace_bytes; n = the size named beside it */
+    CB_PREP_DEGREES = 0,            /* n = num_nodes */
+    CB_PREP_SYMMETRIZE = 1,         /* n = num_edges */
+    CB_PREP_PARTIAL_SORTED_IDX = 2, /* n = length of arr */
+    CB_PREP_DEGREE_STATS = 3,       /* n = length of degs */
+    CB_PREP_SORT_IDX_BY_VALUE = 4,  /* n = m (length of idx) */
+    CB_PREP_MASK_FROM_IDX = 5,      /* n ignored */
+    CB_PREP_DROP_EDGES = 6          /* n = num_edges */
+};
+int64_t cb_prep_graph_workspace_bytes(int what, int64_t n);
 int cb_prep_degrees(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int64_t* degs_ori,
-                    int64_t* degs_dst, void* stream);
-int cb_prep_symmetrize(const int64_t* edge_index, int64_t num_edges, int64_t* out, int64_t* count, void* stream);
+                    int64_t* degs_dst, void* workspace, int64_t workspace_bytes, void* stream);
+int cb_prep_symmetrize(const int64_t* edge_index, int64_t num_edges, int64_t* out, int64_t* count, void* workspace,
+                       int64_t workspace_bytes, void* stream);
 int cb_prep_partial_sorted_idx(const int64_t* arr, int64_t n, int top, int levels, int64_t* idx_out, int64_t* count,
-                               void* stream);
-int cb_prep_degree_stats(const int64_t* degs, int64_t n, double* stats, void* stream);
+                               void* workspace, int64_t workspace_bytes, void* stream);
+int cb_prep_degree_stats(const int64_t* degs, int64_t n, double* stats, void* workspace, int64_t workspace_bytes,
+                         void* stream);
 int cb_prep_sort_idx_by_value(const int64_t* arr, int64_t n, const int64_t* idx, int64_t m, int64_t* idx_sorted,
-                              void* stream);
-int cb_prep_mask_from_idx(const int64_t* idx, int64_t m, int64_t num_nodes, uint8_t* mask, void* stream);
+                              void* workspace, int64_t workspace_bytes, void* stream);
+int cb_prep_mask_from_idx(const int64_t* idx, int64_t m, int64_t num_nodes, uint8_t* mask, void* workspace,
+                          int64_t workspace_bytes, void* stream);
 int cb_prep_drop_edges(const int64_t* edge_index, int64_t num_edges, const uint8_t* node_mask, int64_t num_nodes,
-                       int64_t* out, int64_t* kept, void* stream);
+                       int64_t* out, int64_t* kept, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
 int64_t cb_launch_count(void);

@@ -423,8 +423,12 @@ __global__ void __launch_bounds__(256) k_combine(const AggArgs a) {
 template <typename S, int VEC, int LPR, int NCH>
 static int launch_cfg(const AggArgs& a_in, cudaStream_t st) {
     constexpr int GROUPS = 32 / LPR;
-    static const int warps_env = getenv("CB_AGG_WARPS") ? atoi(getenv("CB_AGG_WARPS")) : 0;    // A/B switch
-    const int WARPS = (warps_env == 1 || warps_env == 2 || warps_env == 4) ? warps_env : 8;
+    // Warps per block.  A block keeps its slot until its longest row is done, and on a power-law graph the longest of
+    // 8 rows is several times the mean: with 8-warp blocks sm__warps_active was 35 % of a 50 % limit.  Measured at the
+    // bench shape (profiles/r02y_*): fused forward 20.4 / 18.9 / 18.6 ms and transposed gather 17.5 / 16.6 / 16.4 ms
+    // with 8 / 4 / 2 warps per block.  CB_AGG_WARPS overrides (A/B switch).
+    static const int warps_env = getenv("CB_AGG_WARPS") ? atoi(getenv("CB_AGG_WARPS")) : 0;
+    const int WARPS = (warps_env == 1 || warps_env == 2 || warps_env == 4 || warps_env == 8) ? warps_env : 2;
     constexpr int UNROLL = NCH >= 2 ? 4 : 8;   // >= 128 bytes of gathered rows in flight per lane
     constexpr int U = UNROLL < LPR ? UNROLL : LPR;
     AggArgs a = a_in;

@@ -170,7 +170,7 @@ class GraphHandle:
         """Per-row byte flags of every rank's rows (identity on a whole graph)."""
         return local_flags
 
-    def push_slot(self, side, d, dtype=torch.float32):
+    def push_slot(self, side, d, dtype=torch.float32, passes=True):
         """Exchange buffer the producing kernel should write into (node-sliced graphs with peer pushes)."""
         return None
 

@@ -110,7 +110,8 @@ class GCNConv(nn.Module):
         return h, (fused.norm(graph) if fused is not None else _ops.frob_norm(self.le, graph))
 
     def fused(self, graph, feat, prescaled=False, relu=False, x0=None, alpha=0.0, want_out=True,
-              want_scaled=False, weight=None, x0_sink=None, dx_sink=None, my_plan=None, dx_plan=None):
+              want_scaled=False, weight=None, x0_sink=None, dx_sink=None, my_plan=None, dx_plan=None,
+              row_sparse_hint=False, dropout_p=0.0):
         """The whole layer plus what follows it in TricksComb, norm='both' only.
 
         feat        layer input; if ``prescaled`` it already carries the D_out^-1/2 factor
@@ -118,6 +119,7 @@ class GCNConv(nn.Module):
         want_scaled also return D_out^-1/2 * out (the next layer's pre-scaled input)
         my_plan     BwdPlan for this layer's backward prologue (run by the consumer of its output)
         dx_plan     BwdPlan of the op that produced ``feat`` (run by this layer's dX GEMM)
+        dropout_p   > 0: ``out`` comes back already dropped (the F.dropout in front of its consumer, same mask)
         Returns (out, out_scaled, se_reg).
         """
         assert self._norm == 'both'
@@ -125,7 +127,7 @@ class GCNConv(nn.Module):
         h, se_reg = self._transform(graph, feat, weight, None if prescaled else graph.dout_inv_sqrt, dx_sink,
                                     dx_plan)
         out, out_scaled = _ops.fused_aggregate(h, graph, self.bias, x0, alpha, relu, want_out, want_scaled,
-                                               x0_sink, my_plan)
+                                               x0_sink, my_plan, row_sparse_hint, dropout_p)
         return out, out_scaled, se_reg
 
     def forward(self, graph, feat, weight=None, edge_weight=None):
@@ -254,11 +256,12 @@ class TricksComb(nn.Module):
 
         no_drop = (not self.training) or self.dropout == 0
         xs_next = None   # D_out^-1/2-scaled copy of x produced by the previous layer's epilogue
+        dropped = False  # x already went through the dropout that stands in front of its consumer (the layer owned it)
 
         for i in range(L):
             x_in = None
             if xs_next is None:
-                x_in = x if no_drop else F.dropout(x, p=self.dropout, training=self.training)
+                x_in = x if (no_drop or dropped) else F.dropout(x, p=self.dropout, training=self.training)
             layer = self.layers_GCN[i]
             want_relu = self.has_residual_MLP or i < L - 1
             # the epilogue (relu, Initial mix) can ride on the aggregation kernel unless a norm layer
@@ -278,6 +281,12 @@ class TricksComb(nn.Module):
             my_plan = _ops.new_plan() if single_consumer else None
             if my_plan is not None and last:
                 my_plan.row_sparse_hint = True     # the layer under the output head (see ops.BwdPlan)
+            # Training with dropout (the reference's defaults): where the aggregation's output goes straight into the
+            # dropout in front of its consumer, the layer draws that dropout itself (same torch call, same mask) and
+            # runs its backward inside its own backward prologue.
+            p_next = self.args.dropout if last else self.dropout
+            owns_dropout = (self.training and 0 < p_next < 1 and fuse_tail and not keeps_history and
+                            (mix_fused or not mixes) and _ops.dropout_fusion())
             dx_plan = prev_plan if (xs_next is not None or (x_in is not None and x_in is x)) else None
             out, out_scaled, se_reg = layer.fused(
                 graph, xs_next if xs_next is not None else x_in, prescaled=xs_next is not None,
@@ -285,7 +294,12 @@ class TricksComb(nn.Module):
                 want_out=need_plain, want_scaled=feeds_conv, x0_sink=x0_sink if mix_fused else None,
                 # layer 0 reads x0 itself: its dX GEMM adds the parked residual gradients in its epilogue
                 dx_sink=x0_sink if (x0_sink is not None and x_in is not None and x_in is x_list[0]) else None,
-                my_plan=my_plan, dx_plan=dx_plan)
+                my_plan=my_plan, dx_plan=dx_plan,
+                # without the hand-off plan (dropout in front of the head: the reference's training defaults) the
+                # last layer still looks for the all-zero rows of its gradient itself
+                row_sparse_hint=last and my_plan is None and self.training,
+                dropout_p=p_next if owns_dropout else 0.0)
+            dropped = owns_dropout
             prev_plan = my_plan
             if se_reg is not None:
                 se_reg_all = se_reg if se_reg_all is None else se_reg_all + se_reg
@@ -301,7 +315,8 @@ class TricksComb(nn.Module):
                 x = self.layers_res[i](x_list)
             xs_next = out_scaled if feeds_conv else None
 
-        x = F.dropout(x, p=self.args.dropout, training=self.training)
+        if not dropped:
+            x = F.dropout(x, p=self.args.dropout, training=self.training)
         if self.has_residual_MLP:
             if AcontainsB(trick, ['Jumping']):
                 x = self.layers_res[0](x_list)

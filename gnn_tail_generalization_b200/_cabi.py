@@ -66,6 +66,8 @@ SYMBOLS = {
                                     _i64, _vp]),
     'cb_agg_backward_prep_bf16': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _dbl, _vp, _vp, _vp, _int, _vp,
                                          _i64, _vp]),
+    'cb_agg_backward_prep_ex': (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp, _int, _int, _dbl, _vp, _dbl, _vp, _vp, _vp,
+                                       _int, _vp, _vp, _i64, _vp]),
     'cb_se_adam_step': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _i64, _vp, _dbl, _vp]),
     'cb_to_bf16': (_int, [_vp, _i64, _vp, _vp]),
     'cb_row_scale': (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),

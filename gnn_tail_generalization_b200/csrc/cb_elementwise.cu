@@ -162,6 +162,11 @@ struct PrepArgs {
     float* bias_partial;   // [gridDim.x, d] or null
     int64_t rows, d;
     int64_t rows_per_block;
+    // cb_agg_backward_prep_ex: d_out is the gradient of dropout(out): dt = keep ? drop_scale * d_out : 0 first
+    // (native_dropout_backward's grad * mask * scale), and the rows of G holding a non-zero are flagged
+    const uint8_t* drop_keep;  // [rows, d] bytes (a bool tensor), or null
+    float drop_scale;
+    uint8_t* row_live;         // [rows] zeroed by the caller, or null
 };
 
 // Block layout: CU = min(units, 256) column slots side by side, RL = 256 / CU row lanes.  Every thread
@@ -198,6 +203,17 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs a) {
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) dt[i] = 0.f;
                 if (a.d_out) IO::ld(dt, p_out + off);
+                if (a.drop_keep) {
+                    bool k[VEC];
+                    if (VEC == 4) {
+                        const uchar4 kk = *reinterpret_cast<const uchar4*>(a.drop_keep + off);
+                        k[0] = kk.x; k[1 % VEC] = kk.y; k[2 % VEC] = kk.z; k[3 % VEC] = kk.w;
+                    } else {
+                        k[0] = a.drop_keep[off] != 0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) dt[i] = k[i] ? __fmul_rn(dt[i], a.drop_scale) : 0.f;
+                }
                 if (a.d_out2) {
                     const float s2 = __ldg(a.s2 + r);
                     float t[VEC];
@@ -244,6 +260,12 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs a) {
                     g[i] = __fmul_rn(rs, dz);
                 }
                 IO::st(p_G + off, g);
+                if (a.row_live) {
+                    bool nz = false;
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) nz |= g[i] != 0.f;
+                    if (nz) a.row_live[r] = 1;       // every writer stores the same byte
+                }
             }
         }
         if (a.bias_partial) {
@@ -515,7 +537,8 @@ int64_t cb_prep_workspace_bytes(int64_t rows, int64_t d) {
 static int backward_prep_impl(const cb_graph_t* g, int dtype, const void* d_out, const void* d_out_scaled, int64_t d,
                               const uint8_t* mask, const void* relu_out, int act, int mixed, double alpha,
                               void* G, float* d_bias, void* d_x0, int accumulate_x0, void* workspace,
-                              int64_t workspace_bytes, void* stream) {
+                              int64_t workspace_bytes, void* stream, const uint8_t* drop_keep = nullptr,
+                              double drop_scale = 1.0, uint8_t* row_live = nullptr) {
     using namespace cb;
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_backward_prep: graph is NULL");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_backward_prep: d must be positive");
@@ -548,13 +571,18 @@ static int backward_prep_impl(const cb_graph_t* g, int dtype, const void* d_out,
     a.d_x0 = d_x0;
     a.accumulate_x0 = accumulate_x0;
     a.bias_partial = d_bias ? (float*)workspace : nullptr;
+    CB_REQUIRE(drop_keep == nullptr || (d_out != nullptr && d_out_scaled == nullptr), CB_E_INVALID,
+               "cb_agg_backward_prep_ex: the dropout mask applies to the plain output's gradient only");
+    a.drop_keep = drop_keep;
+    a.drop_scale = (float)drop_scale;
+    a.row_live = row_live;
     a.rows = rows;
     a.d = d;
     a.rows_per_block = ceil_div(rows > 0 ? rows : 1, blocks);
     auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & m) == 0; };
     const uintptr_t am = dtype == CB_BF16 ? 7 : 15;    // 4 elements per access
     const bool vec = d % 4 == 0 && al(d_out, am) && al(d_out_scaled, am) && al(G, am) && al(d_x0, am) &&
-                     al(relu_out, am) && al(mask, 3);
+                     al(relu_out, am) && al(mask, 3) && al(drop_keep, 3);
     const int64_t units = vec ? d / 4 : d;
     const int cu = (int)(units < 256 ? units : 256);
     const int rl = 256 / cu;
@@ -581,6 +609,15 @@ int cb_agg_backward_prep(const cb_graph_t* g, const float* d_out, const float* d
                          int64_t workspace_bytes, void* stream) {
     return backward_prep_impl(g, CB_F32, d_out, d_out_scaled, d, mask, relu_out, act, mixed, alpha, G, d_bias, d_x0,
                               accumulate_x0, workspace, workspace_bytes, stream);
+}
+
+int cb_agg_backward_prep_ex(const cb_graph_t* g, int dtype, const void* d_out, const void* d_out_scaled, int64_t d,
+                            const uint8_t* mask, const void* relu_out, int act, int mixed, double alpha,
+                            const uint8_t* drop_keep, double drop_scale, void* G, float* d_bias, void* d_x0,
+                            int accumulate_x0, uint8_t* row_live, void* workspace, int64_t workspace_bytes, void* stream) {
+    CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_agg_backward_prep_ex: unknown dtype");
+    return backward_prep_impl(g, dtype, d_out, d_out_scaled, d, mask, relu_out, act, mixed, alpha, G, d_bias, d_x0,
+                              accumulate_x0, workspace, workspace_bytes, stream, drop_keep, drop_scale, row_live);
 }
 
 int cb_agg_backward_prep_bf16(const cb_graph_t* g, const uint16_t* d_out, const uint16_t* d_out_scaled, int64_t d,

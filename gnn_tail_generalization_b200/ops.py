@@ -221,8 +221,11 @@ def agg_gather_raw(graph, side, X, row_scale=None, out=None, panel=None, live=No
 
 
 def backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, relu, mixed, alpha, want_bias, want_x0,
-                      d_x0_accum=None):
-    """d_x0_accum: an existing [rows, d] buffer that receives ``+= alpha * dtot`` instead of a fresh d_x0."""
+                      d_x0_accum=None, drop_keep=None, drop_scale=1.0, want_live=False):
+    """d_x0_accum: an existing [rows, d] buffer that receives ``+= alpha * dtot`` instead of a fresh d_x0.
+    drop_keep / drop_scale: ``d_out`` is the gradient of dropout(out); the boolean keep mask of torch.native_dropout
+    and 1 / (1 - p) fold its backward into this pass (cb_agg_backward_prep_ex).  want_live: also return uint8 [rows]
+    flags of the rows of G that hold a non-zero (returned as a 4th value)."""
     ref = d_out if d_out is not None else d_out_scaled
     _need_cuda(ref)
     st = ref.dtype
@@ -240,6 +243,19 @@ def backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, relu, mixed, a
     mats = int(d_out is not None) + int(d_out_scaled is not None) + 1 + int(want_x0) + accumulate + \
         int(relu_out is not None)
     alg = mats * rows * d * ref.element_size() + (rows * d if mask is not None else 0) + 2 * rows * 4
+    if drop_keep is not None or want_live:
+        if drop_keep is not None:
+            if drop_keep.dtype != torch.bool or drop_keep.shape != ref.shape or d_out is None or d_out_scaled is not None:
+                raise ValueError('drop_keep: a bool mask of the plain output, whose gradient d_out must be the only one')
+            drop_keep = drop_keep.contiguous()
+            alg += rows * d
+        live = torch.zeros(rows, dtype=torch.uint8, device=ref.device) if want_live else None
+        with torch.cuda.device(ref.device), _Timed('backward_prep' + _sfx(st), alg, ref.device):
+            C.call('cb_agg_backward_prep_ex', graph.handle, C.CB_F32 if st == torch.float32 else C.CB_BF16, C.ptr(d_out),
+                   C.ptr(d_out_scaled), d, C.ptr(mask), C.ptr(relu_out), C.CB_ACT_RELU if relu else C.CB_ACT_NONE,
+                   int(bool(mixed)), float(alpha), C.ptr(drop_keep), float(drop_scale), C.ptr(G), C.ptr(d_bias),
+                   C.ptr(d_x0), accumulate, C.ptr(live), C.ptr(ws), ws_bytes, C.stream_ptr(ref.device))
+        return (G, d_bias, d_x0, live) if want_live else (G, d_bias, d_x0)
     with torch.cuda.device(ref.device), _Timed('backward_prep' + _sfx(st), alg, ref.device):
         C.call('cb_agg_backward_prep' + _sfx(st), graph.handle, C.ptr(d_out), C.ptr(d_out_scaled), d, C.ptr(mask),
                C.ptr(relu_out), C.CB_ACT_RELU if relu else C.CB_ACT_NONE, int(bool(mixed)), float(alpha),
@@ -602,6 +618,20 @@ def set_backward_fusion(on):
     backward) instead of inside the neighbouring dX GEMM -- the A/B switch of tests and bench."""
     global _backward_fusion
     _backward_fusion = bool(on)
+
+
+_dropout_fusion = True
+
+
+def set_dropout_fusion(on):
+    """False: the dropouts between the layers stay separate F.dropout autograd nodes (the A/B partner of the layers
+    that own their output's dropout, see fused_aggregate(dropout_p=...)); same masks, same gradients."""
+    global _dropout_fusion
+    _dropout_fusion = bool(on)
+
+
+def dropout_fusion():
+    return _dropout_fusion
 
 
 def new_plan():
@@ -989,11 +1019,16 @@ class _FusedAggregate(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, H, bias, x0, graph, alpha, relu, want_out, want_scaled, x0_sink, my_plan):
+    def forward(ctx, H, bias, x0, graph, alpha, relu, want_out, want_scaled, x0_sink, my_plan, row_sparse_hint,
+                dropout_p):
         ctx.x0_sink = x0_sink
         ctx.my_plan = my_plan
+        ctx.row_sparse_hint = row_sparse_hint
         mixed = x0 is not None
         need_grad = any(ctx.needs_input_grad[:3])
+        owns_dropout = dropout_p > 0.0
+        if owns_dropout and (want_scaled or not want_out):
+            raise ValueError('fused_aggregate: the dropout applies to the plain output only')
         # relu mask source for backward: the plain relu output doubles as the mask when nothing was
         # mixed into it, otherwise a byte mask is written by the kernel
         use_out_as_mask = relu and not mixed and want_out
@@ -1002,11 +1037,19 @@ class _FusedAggregate(torch.autograd.Function):
         ctx.h_shape = H.shape
         ctx.graph, ctx.alpha, ctx.relu, ctx.mixed = graph, alpha, relu, mixed
         ctx.has_bias, ctx.use_out_as_mask = bias is not None, use_out_as_mask
-        ctx.save_for_backward(mask if want_mask else None, out if (use_out_as_mask and need_grad) else None)
+        ctx.drop_scale, keep = 1.0, None
+        pre_drop = out
+        if owns_dropout:
+            # The dropout that follows the layer (GCN.py:104,110,133) is drawn HERE with the same call F.dropout makes,
+            # so the Philox stream and the mask are the reference's; the layer keeps the mask and folds the dropout's
+            # backward into its own prologue (cb_agg_backward_prep_ex) instead of a separate pass over [N, d].
+            out, keep = torch.native_dropout(out, dropout_p, True)
+            ctx.drop_scale = 1.0 / (1.0 - dropout_p)
+        ctx.save_for_backward(mask if want_mask else None, pre_drop if (use_out_as_mask and need_grad) else None, keep)
         ctx.set_materialize_grads(False)
         if my_plan is not None:
             my_plan.kind = None
-            if need_grad and (want_out != want_scaled):
+            if need_grad and (want_out != want_scaled) and not owns_dropout:
                 p = my_plan
                 p.kind, p.graph, p.slot = 'prep', graph, 'out' if want_out else 'out_scaled'
                 p.gate_u8 = mask if want_mask else None
@@ -1023,14 +1066,14 @@ class _FusedAggregate(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out, d_out_scaled):
-        mask, relu_out = ctx.saved_tensors
+        mask, relu_out, drop_keep = ctx.saved_tensors
         graph = ctx.graph
         if d_out is not None and d_out.dim() == 1:          # 1-D empty placeholder of the unused slot
             d_out = None
         if d_out_scaled is not None and d_out_scaled.dim() == 1:
             d_out_scaled = None
         if d_out is None and d_out_scaled is None:
-            return (None,) * 10
+            return (None,) * 12
         done = ctx.my_plan.take_result() if ctx.my_plan is not None else None
         if done is not None:
             # the consumer's dX GEMM ran the prologue in its epilogue: what arrived is G itself
@@ -1043,24 +1086,36 @@ class _FusedAggregate(torch.autograd.Function):
             want_bias = ctx.has_bias and ctx.needs_input_grad[1]
             want_x0 = ctx.mixed and ctx.needs_input_grad[2]
             sink = ctx.x0_sink if want_x0 else None
-            G, d_bias, d_x0 = backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, ctx.relu, ctx.mixed,
-                                                ctx.alpha, want_bias, want_x0,
-                                                d_x0_accum=sink.dense() if sink is not None else None)
+            # The layer under the output head, reached without the fused hand-off (dropout in between, training with the
+            # reference's defaults): under a loss over the train rows only most rows of G are zero.  The prologue flags
+            # the others while it writes G; the gather then walks the compacted lists (same sums).
+            want_live = ctx.row_sparse_hint and ctx.needs_input_grad[0] and graph.rows > 0
+            res = backward_prep_raw(graph, d_out, d_out_scaled, mask, relu_out, ctx.relu, ctx.mixed,
+                                    ctx.alpha, want_bias, want_x0,
+                                    d_x0_accum=sink.dense() if sink is not None else None,
+                                    drop_keep=drop_keep, drop_scale=ctx.drop_scale, want_live=want_live)
+            G, d_bias, d_x0 = res[:3]
+            live = res[3] if want_live else None
             if sink is not None:   # parked for the hub / the last consumer's GEMM epilogue
                 sink.buf, d_x0 = d_x0, None
         dH = None
         if ctx.needs_input_grad[0]:
             dH = aggregate_gather(graph, C.CB_BY_SRC, G, live=live, live_full=live_full).view(ctx.h_shape)
-        return dH, d_bias, d_x0, None, None, None, None, None, None, None
+        return dH, d_bias, d_x0, None, None, None, None, None, None, None, None, None
 
 
 def fused_aggregate(H, graph, bias=None, x0=None, alpha=0.0, relu=False, want_out=True, want_scaled=False,
-                    x0_sink=None, my_plan=None):
-    """Returns (out, out_scaled); the one not asked for is None."""
+                    x0_sink=None, my_plan=None, row_sparse_hint=False, dropout_p=0.0):
+    """Returns (out, out_scaled); the one not asked for is None.
+    row_sparse_hint: the gradient of this output is expected to be zero on most rows (the layer under an output head
+    whose loss reads the train rows only): the backward pass then looks for all-zero rows and gathers over the
+    compacted lists.  A hint only -- the rows are found from the data, the sums are the same.
+    dropout_p > 0: the returned ``out`` is F.dropout(out, dropout_p, training=True) -- the same torch call, hence the
+    same mask -- and the dropout's backward runs inside this op's own backward prologue."""
     if not (want_out or want_scaled):
         raise ValueError('fused_aggregate: nothing requested')
     out, out_scaled = _FusedAggregate.apply(H, bias, x0, graph, float(alpha), bool(relu), bool(want_out),
-                                            bool(want_scaled), x0_sink, my_plan)
+                                            bool(want_scaled), x0_sink, my_plan, bool(row_sparse_hint), float(dropout_p))
     return (out if want_out else None), (out_scaled if want_scaled else None)
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 6   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid; 5: source panels; 6: graph preparation */
+#define CB_ABI_VERSION 6   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid; 5: source panels; 6: graph preparation, cb_agg_backward_prep_ex */
 
 enum {
     CB_OK = 0,
@@ -255,6 +255,20 @@ int cb_agg_backward_prep_bf16(const cb_graph_t* g, const uint16_t* d_out, const 
                               const uint8_t* mask, const uint16_t* relu_out, int act, int mixed, double alpha,
                               uint16_t* G, float* d_bias, uint16_t* d_x0, int accumulate_x0, void* workspace,
                               int64_t workspace_bytes, void* stream);
+
+/*
+ * The same prologue when a dropout sat between the aggregation's output and its consumer (GCN.py:104,110,133 with the
+ * reference's training defaults, base_options.py:190-220): d_out is the gradient of dropout(out) and
+ * drop_keep [rows, d] (bytes of the boolean mask torch.native_dropout returned) / drop_scale = 1 / (1 - p) turn it into
+ * the gradient of out first -- keep ? drop_scale * d_out : 0, what native_dropout_backward computes -- in the same pass
+ * (d_out_scaled must be NULL then).  row_live [rows] (zeroed by the caller) or NULL: receives 1 for every row of G that
+ * holds a non-zero, so that the transposed gather can run over the compacted lists (cb_graph_compact_live) without a
+ * separate pass over G.  dtype CB_F32 / CB_BF16 of d_out, d_out_scaled, relu_out, G, d_x0.
+ */
+int cb_agg_backward_prep_ex(const cb_graph_t* g, int dtype, const void* d_out, const void* d_out_scaled, int64_t d,
+                            const uint8_t* mask, const void* relu_out, int act, int mixed, double alpha,
+                            const uint8_t* drop_keep, double drop_scale, void* G, float* d_bias, void* d_x0,
+                            int accumulate_x0, uint8_t* row_live, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Optimizer step of one Structural-Embedding table (GCN.py:181-182 `self.le`; trainer_node_classification.py:310

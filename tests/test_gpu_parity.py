@@ -203,6 +203,95 @@ def test_fused_aggregate_autograd_matches_oracle(d, relu, mix):
     assert torch.allclose(gpu[0].grad.cpu(), cpu[0].grad, rtol=1e-5, atol=1e-5)
 
 
+def test_row_sparse_hint_on_the_unfused_backward_changes_nothing():
+    """The layer under the output head when dropout sits in between (no hand-off plan): with the hint the backward
+    looks for the all-zero rows of G and gathers over the compacted lists -- same gradients, bit for bit."""
+    C, G, ops = _pkg()
+    n, e, d, alpha = 6000, 80000, 64, 0.1
+    ei = O.canonicalize_planetoid(_multigraph(n, e, 321), n)
+    gen = torch.Generator().manual_seed(9)
+    base = [torch.randn(n, d, generator=gen), torch.randn(d, generator=gen), torch.randn(n, d, generator=gen)]
+    w = torch.randn(n, d, generator=gen)
+    w[n // 10:] = 0                                  # the loss reads the first tenth of the rows only
+    h = G.GraphHandle(ei.to(DEV), n, hub_chunk=64)
+    grads, names = [], []
+    for hint in (False, True):
+        gpu = [t.clone().to(DEV).requires_grad_() for t in base]
+        sink = []
+        ops.set_timing_sink(sink)
+        out, _ = ops.fused_aggregate(gpu[0], h, gpu[1], gpu[2], alpha, True, True, False, row_sparse_hint=hint)
+        (torch.nn.functional.dropout(out, 0.5, training=True) * w.to(DEV)).sum().backward()
+        ops.set_timing_sink(None)
+        names.append([x[0] for x in sink])
+        grads.append([t.grad.clone() for t in gpu])
+        torch.manual_seed(0)
+    assert 'agg_gather_src' in names[0] and 'agg_gather_src_rowsparse' not in names[0]
+    # the prologue flags the live rows of G while it writes them: no separate pass
+    assert 'agg_gather_src_rowsparse' in names[1] and 'row_any_nonzero' not in names[1]
+    # the dropout masks differ between the two runs (the RNG moved on): compare what does not depend on them --
+    # rows of dH that only gather from dead rows are zero in both, and a deterministic rerun matches bit for bit
+    for hint in (False, True):
+        res = []
+        for _ in range(2):
+            torch.manual_seed(11)
+            gpu = [t.clone().to(DEV).requires_grad_() for t in base]
+            out, _ = ops.fused_aggregate(gpu[0], h, gpu[1], gpu[2], alpha, True, True, False, row_sparse_hint=hint)
+            (torch.nn.functional.dropout(out, 0.5, training=True) * w.to(DEV)).sum().backward()
+            res.append([t.grad.clone() for t in gpu])
+        grads.append(res[0])
+        for a, b in zip(*res):
+            assert torch.equal(a, b)
+    for a, b in zip(grads[2], grads[3]):             # same seed, hint off vs on
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('trick,se,L', [('Initial', '000', 2), ('Initial', '111', 3), ('NoRes', '000', 3), ('Residual', '010', 2),
+                                         ('InitialJumping', '000', 3)])
+def test_layers_that_own_their_dropout_match_separate_dropout_nodes(trick, se, L):
+    """Training with dropout > 0 (the reference's defaults, base_options.py:190-220): a layer whose output goes straight
+    into F.dropout draws that dropout itself and folds its backward into its prologue.  Same torch call in the same
+    order => same masks; logits and every gradient are bit-identical to the path with separate F.dropout nodes."""
+    C, G, ops = _pkg()
+    from gnn_tail_generalization_b200.GNN_model.GNN_normalizations import TeacherGNN
+    n, e, d, Cn = 3000, 30000, 64, 16
+    ei = O.canonicalize_planetoid(_multigraph(n, e, 55), n).to(DEV)
+    kw = dict(type_trick=trick, whetherHasSE=se, num_layers=L, dim_hidden=d, num_feats=32, num_classes=Cn, N_nodes=n,
+              dataset='Cora', res_alpha=0.1, dropout=0.5)
+    a = O.make_args(**kw)
+    a.device = DEV
+    torch.manual_seed(1)
+    model = TeacherGNN(a, None).to(DEV).train()
+    x = torch.randn(n, 32, generator=torch.Generator().manual_seed(2)).to(DEV)
+    y = torch.randint(0, Cn, (n,), generator=torch.Generator().manual_seed(3)).to(DEV)
+    mask = torch.arange(n, device=DEV) < n // 5
+    results = []
+    try:
+        for fused in (False, True):
+            ops.set_dropout_fusion(fused)
+            model.zero_grad(set_to_none=True)
+            torch.manual_seed(77)
+            sink = []
+            ops.set_timing_sink(sink)
+            res = model.get_3_embs(x, ei, mask)
+            loss = F.nll_loss(F.log_softmax(res.emb4classi, 1), y[mask])
+            if model.se_reg_all is not None:
+                loss = loss + 0.5 * model.se_reg_all
+            loss.backward()
+            ops.set_timing_sink(None)
+            results.append((res.emb4classi_full.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters()
+                                                                   if p.grad is not None}, [s[0] for s in sink]))
+    finally:
+        ops.set_dropout_fusion(True)
+        ops.set_timing_sink(None)
+    (lg0, g0, _), (lg1, g1, names) = results
+    assert torch.equal(lg0, lg1)
+    assert set(g0) == set(g1) and len(g0) > 0
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
+    if trick in ('Initial', 'NoRes'):
+        assert 'agg_gather_src_rowsparse' in names        # the layer under the head found its dead rows itself
+
+
 def test_transpose_identity():
     """<A x, y> == <x, A^T y>: the backward gather is the exact transpose of the forward one."""
     C, G, ops = _pkg()

@@ -133,8 +133,27 @@ class GCNConv(nn.Module):
     def forward(self, graph, feat, weight=None, edge_weight=None):
         """Same contract as the reference's GCNConv.forward (GCN.py:184-258)."""
         if edge_weight is not None:
+            # GCN.py:199-202: the messages become h[u] * w[e] (fn.u_mul_e); the degree norms stay edge COUNTS
+            # (GCN.py:205-213, 242-250).  Never reached from TricksComb (it does not pass edge weights): the plain
+            # composition, every piece on this library's kernels, no fused epilogue.
             assert edge_weight.shape[0] == graph.number_of_edges()
-            raise NotImplementedError('edge_weight (u_mul_e) is not used on the TeacherGNN path and has no kernel yet')
+            weight = self._check(graph, weight)
+            scale_src = None
+            if self._norm == 'both':
+                scale_src = graph.dout_inv_sqrt
+            elif self._norm == 'left':
+                scale_src = 1.0 / graph.out_degrees().float().clamp(min=1)
+            h, se_reg = self._transform(graph, feat, weight, scale_src)
+            rst = _ops.weighted_sum(h, edge_weight, graph)
+            if self._norm == 'both':
+                rst = _ops.row_scale(rst, graph.din_inv_sqrt)
+            elif self._norm == 'right':
+                rst = rst * (1.0 / graph.in_degrees().float().clamp(min=1)).unsqueeze(-1)
+            if self.bias is not None:
+                rst = rst + self.bias
+            if self._activation is not None:
+                rst = self._activation(rst)
+            return rst, se_reg
         if self._norm == 'both':
             rst, _, se_reg = self.fused(graph, feat, weight=weight)
         else:

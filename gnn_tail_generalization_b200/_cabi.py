@@ -57,6 +57,9 @@ SYMBOLS = {
     'cb_agg_forward_pass': (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _i64, _int, _vp, _vp,
                                    _i64, _vp]),
     'cb_agg_gather_pass': (_int, [_vp, _int, _int, _vp, _i64, _i64, _vp, _vp, _i64, _int, _vp, _vp, _i64, _vp]),
+    'cb_graph_sort_edge_values': (_int, [_vp, _int, _vp, _i64, _vp, _vp]),
+    'cb_agg_gather_weighted': (_int, [_vp, _int, _int, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    'cb_agg_edge_dot': (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
     'cb_agg_propagate': (_int, [_vp, _int, _vp, _i64, _vp, _vp, _dbl, _dbl, _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _i64, _vp]),
     'cb_graph_live_workspace_bytes': (_i64, [_vp, _int]),
     'cb_graph_compact_live': (_int, [_vp, _int, _vp, _vp, _i64, _vp]),

@@ -47,6 +47,7 @@ struct AggArgs {
     void* out2;               // [rows, d] or null (storage type S)
     uint8_t* mask;            // [rows, d] or null
     const uint8_t* live;      // [n_src] or null: rows of X with live[s] == 0 are all-zero and are not gathered
+    const float* ew;          // [n_edges] or null: weight of every stored edge (GCN.py:199-202 u_mul_e): sum of x * w
     // live-column compacted lists (cb_graph_compact_live): rowptr / col / chunk_beg point into the compacted CSR,
     // hub_rowptr is the ORIGINAL rowptr (a row is a hub by its original degree, so that every partial sum keeps
     // the association of the uncompacted walk) and chunk_end bounds each chunk explicitly
@@ -132,6 +133,11 @@ struct Elem<float, VEC> {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] += r.f[i];
     }
+    // u_mul_e: the product is rounded before it is added (no FMA), like DGL's `out += lhs * rhs` on the CPU
+    static __device__ __forceinline__ void add_scaled(float (&acc)[VEC], const Raw& r, float w) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = __fadd_rn(acc[i], __fmul_rn(r.f[i], w));
+    }
     static __device__ __forceinline__ void load(float (&v)[VEC], const void* base, int64_t off) {
         Vec<VEC>::load(v, reinterpret_cast<const float*>(base) + off);
     }
@@ -161,6 +167,12 @@ struct Elem<__nv_bfloat16, 8> {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += v[i];
     }
+    static __device__ __forceinline__ void add_scaled(float (&acc)[8], const Raw& r, float w) {
+        float v[8];
+        widen(v, r.u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], __fmul_rn(v[i], w));
+    }
     static __device__ __forceinline__ void load(float (&v)[8], const void* base, int64_t off) {
         widen(v, __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off)));
     }
@@ -181,6 +193,9 @@ struct Elem<__nv_bfloat16, 1> {
         r.f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]);
     }
     static __device__ __forceinline__ void add(float (&acc)[1], const Raw& r) { acc[0] += r.f; }
+    static __device__ __forceinline__ void add_scaled(float (&acc)[1], const Raw& r, float w) {
+        acc[0] = __fadd_rn(acc[0], __fmul_rn(r.f, w));
+    }
     static __device__ __forceinline__ void load(float (&v)[1], const void* base, int64_t off) {
         v[0] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]);
     }
@@ -223,8 +238,11 @@ __device__ __forceinline__ void epilogue_store(const AggArgs& a, int64_t row, in
 
 // LIVE: X is row-sparse (e.g. the gradient arriving from a loss over the train rows only); a.live says which
 // source rows can be non-zero.  Skipping an all-zero row leaves every fp32 sum unchanged (x + 0 = x).
-template <typename S, int VEC, int LPR, int NCH, int UNROLL, bool LIVE>
+// MODE 0: plain walk.  MODE 1 (LIVE): X is row-sparse, see above.  MODE 2 (EW): every stored edge carries a weight
+// (a.ew, in stored order): out = sum of x * w, the product rounded before the in-order add.
+template <typename S, int VEC, int LPR, int NCH, int UNROLL, int MODE>
 __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
+    constexpr bool LIVE = MODE == 1, EW = MODE == 2;
     constexpr int GROUPS = 32 / LPR;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
@@ -294,12 +312,16 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
         const int n = (int)(end - base < LPR ? end - base : LPR);
         int my = sub < n ? __ldg(a.col + base + sub) : 0;
         if (LIVE && sub < n && __ldg(a.live + my) == 0) my |= (int)0x80000000;   // N < 2^31: the sign bit is free
+        float myw = 0.f;
+        if (EW && sub < n) myw = __ldg(a.ew + base + sub);
         for (int k = 0; k < n; k += UNROLL) {
             typename Elem<S, VEC>::Raw v[UNROLL][NCH];
             bool on[UNROLL];
+            float wv[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int s = __shfl_sync(gmask, my, (k + u) & (LPR - 1), LPR);
+                if (EW) wv[u] = __shfl_sync(gmask, myw, (k + u) & (LPR - 1), LPR);
                 on[u] = (k + u < n) && (!LIVE || s >= 0);
                 if (on[u]) {
                     const int64_t xr = (int64_t)s * a.x_ld;
@@ -312,8 +334,12 @@ __global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
             for (int u = 0; u < UNROLL; ++u) {
                 if (on[u]) {
 #pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch)
-                        if (cval[ch]) Elem<S, VEC>::add(acc[ch], v[u][ch]);
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        if (cval[ch]) {
+                            if constexpr (EW) Elem<S, VEC>::add_scaled(acc[ch], v[u][ch], wv[u]);
+                            else Elem<S, VEC>::add(acc[ch], v[u][ch]);
+                        }
+                    }
                 }
             }
         }
@@ -447,9 +473,11 @@ static int launch_cfg(const AggArgs& a_in, cudaStream_t st) {
         const int64_t blocks = ceil_div(tasks, (int64_t)WARPS * GROUPS);
         CB_REQUIRE(blocks < (int64_t)INT32_MAX, CB_E_UNSUPPORTED, "aggregation grid too large");
         if (a.live)
-            k_agg<S, VEC, LPR, NCH, U, true><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+            k_agg<S, VEC, LPR, NCH, U, 1><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+        else if (a.ew)
+            k_agg<S, VEC, LPR, NCH, U, 2><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
         else
-            k_agg<S, VEC, LPR, NCH, U, false><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
+            k_agg<S, VEC, LPR, NCH, U, 0><<<(unsigned)blocks, WARPS * 32, 0, st>>>(a);
         CB_LAUNCH_CHECK();
     }
     if (a.n_chunks > 0) {
@@ -614,7 +642,7 @@ static bool try_bulk(const AggArgs& a, cudaStream_t st, int* rc) {
     static const int ring = getenv("CB_AGG_BULK") ? atoi(getenv("CB_AGG_BULK")) : 0;
     if (ring != 4 && ring != 8) return false;
     const int64_t units = ceil_div(a.d, VEC);
-    if (a.live || a.row_be || a.rowptr_exp || a.hub_rowptr || a.chunk_end || a.col0 != 0 || a.task0 != 0) return false;
+    if (a.live || a.ew || a.row_be || a.rowptr_exp || a.hub_rowptr || a.chunk_end || a.col0 != 0 || a.task0 != 0) return false;
     if (units <= 32 || units > 64 || a.d % VEC != 0 || (a.x_ld * (int64_t)sizeof(S)) % 16 != 0) return false;
     if ((size_t)8 * ring * a.d * sizeof(S) > 200 * 1024) return false;
     *rc = ring == 4 ? launch_bulk<S, VEC, 2, 4>(a, st) : launch_bulk<S, VEC, 2, 8>(a, st);
@@ -658,6 +686,7 @@ static int run_agg(const cb_graph* g, int side_id, int dtype, AggArgs a, void* w
         CB_REQUIRE(panel < g->src_panels, CB_E_INVALID, "aggregation pass: panel out of range");
         CB_REQUIRE(carry != nullptr || g->rows == 0, CB_E_INVALID, "aggregation pass: carry buffer is NULL");
         CB_REQUIRE(live_ws == nullptr, CB_E_UNSUPPORTED, "aggregation pass over compacted lists is not supported");
+        CB_REQUIRE(a.ew == nullptr, CB_E_UNSUPPORTED, "edge-weighted aggregation passes are not supported");
         a.rowptr_exp = s.rowptr_exp;
         a.n_panels = g->src_panels;
         a.panel = panel;
@@ -672,6 +701,7 @@ static int run_agg(const cb_graph* g, int side_id, int dtype, AggArgs a, void* w
     a.chunk_row = s.chunk_row;
     a.chunk_beg = s.chunk_beg;
     a.n_chunks = s.n_chunks;
+    CB_REQUIRE(!(a.ew && (live_ws || a.live)), CB_E_UNSUPPORTED, "edge weights on a row-sparse gather are not supported");
     if (live_ws) {
         const LiveView v = live_view(g, side_id, const_cast<void*>(live_ws));
         a.hub_rowptr = s.rowptr;
@@ -733,7 +763,7 @@ static int agg_forward_impl(const cb_graph* g, int dtype, const void* H, int64_t
 static int agg_gather_impl(const cb_graph* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
                            const float* row_scale, const uint8_t* row_live, void* out, int64_t ld_out, void* workspace,
                            int64_t workspace_bytes, void* stream, const void* live_ws = nullptr, int panel = -1,
-                           float* carry = nullptr) {
+                           float* carry = nullptr, const float* edge_val = nullptr) {
     CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_gather: graph is NULL");
     CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_agg_gather: unknown side");
     CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_gather: d must be positive");
@@ -750,7 +780,58 @@ static int agg_gather_impl(const cb_graph* g, int side, int dtype, const void* X
     a.act = CB_ACT_NONE;
     a.out = out;
     a.live = row_live;
+    a.ew = edge_val;
     return run_agg(g, side, dtype, a, workspace, workspace_bytes, (cudaStream_t)stream, live_ws, panel, carry);
+}
+
+// ---- edge-weighted aggregation (GCN.py:199-202): weights into stored order, per-edge dot products for dL/dw -------
+__global__ void k_sort_edge_values(const float* __restrict__ values, const int32_t* __restrict__ perm, int64_t n,
+                                   float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) out[j] = values[perm[j]];
+}
+
+template <typename S>
+__device__ __forceinline__ float ld_elem(const S* p);
+template <>
+__device__ __forceinline__ float ld_elem<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_elem<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// out[perm[j]] = <X[col[j], :], Y[row, :]> for every stored edge j of the side: one warp per task (a row, or one
+// hub_chunk-long piece of a hub row), lanes stride over the columns, a fixed butterfly adds the 32 partials.
+template <typename S>
+__global__ void __launch_bounds__(256) k_edge_dot(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                  const int32_t* __restrict__ perm, const int32_t* __restrict__ chunk_row,
+                                                  const int64_t* __restrict__ chunk_beg, int64_t n_rows, int64_t n_chunks,
+                                                  int hub_chunk, const S* __restrict__ X, int64_t ld_x,
+                                                  const S* __restrict__ Y, int64_t ld_y, int64_t d,
+                                                  float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t task = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (task >= n_rows + n_chunks) return;
+    int64_t row, beg, end;
+    if (task < n_rows) {
+        row = task;
+        beg = rowptr[row];
+        end = rowptr[row + 1];
+        if (end - beg > hub_chunk) return;
+    } else {
+        const int64_t c = task - n_rows;
+        row = chunk_row[c];
+        beg = chunk_beg[c];
+        const int64_t rend = rowptr[row + 1];
+        end = beg + hub_chunk < rend ? beg + hub_chunk : rend;
+    }
+    const S* y = Y + row * ld_y;
+    for (int64_t j = beg; j < end; ++j) {
+        const S* x = X + (int64_t)col[j] * ld_x;
+        float t = 0.f;
+        for (int64_t k = lane; k < d; k += 32) t = __fadd_rn(t, __fmul_rn(ld_elem<S>(x + k), ld_elem<S>(y + k)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) out[perm[j]] = t;
+    }
 }
 
 }  // namespace cb
@@ -782,6 +863,58 @@ int cb_agg_gather(const cb_graph_t* g, int side, const float* X, int64_t ld_x, i
                   void* stream) {
     return cb::agg_gather_impl(g, side, CB_F32, X, ld_x, d, row_scale, row_live, out, ld_out, workspace,
                                workspace_bytes, stream);
+}
+
+int cb_graph_sort_edge_values(const cb_graph_t* g, int side, const float* values, int64_t num_values, float* out,
+                              void* stream) {
+    CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_graph_sort_edge_values: graph is NULL");
+    CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_graph_sort_edge_values: unknown side");
+    const cb::Side& s = side == CB_BY_DST ? g->by_dst : g->by_src;
+    if (s.n_edges == 0) return CB_OK;
+    CB_REQUIRE(values != nullptr && out != nullptr, CB_E_INVALID, "cb_graph_sort_edge_values: NULL buffer");
+    CB_REQUIRE(num_values >= s.n_edges, CB_E_INVALID,
+               "cb_graph_sort_edge_values: fewer values than edges in the list the graph was built from");
+    const int64_t blocks = cb::ceil_div(s.n_edges, 256);
+    cb::k_sort_edge_values<<<(unsigned)(blocks < 65535 * 16 ? blocks : 65535 * 16), 256, 0, (cudaStream_t)stream>>>(
+        values, s.perm, s.n_edges, out);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_agg_gather_weighted(const cb_graph_t* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
+                           const float* edge_val, const float* row_scale, void* out, int64_t ld_out, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+    CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_agg_gather_weighted: unknown dtype");
+    CB_REQUIRE(g == nullptr || edge_val != nullptr || (side == CB_BY_DST ? g->by_dst : g->by_src).n_edges == 0,
+               CB_E_INVALID, "cb_agg_gather_weighted: edge_val is NULL");
+    return cb::agg_gather_impl(g, side, dtype, X, ld_x, d, row_scale, nullptr, out, ld_out, workspace, workspace_bytes,
+                               stream, nullptr, -1, nullptr, edge_val);
+}
+
+int cb_agg_edge_dot(const cb_graph_t* g, int side, int dtype, const void* X, int64_t ld_x, const void* Y, int64_t ld_y,
+                    int64_t d, float* out, void* stream) {
+    CB_REQUIRE(g != nullptr, CB_E_INVALID, "cb_agg_edge_dot: graph is NULL");
+    CB_REQUIRE(side == CB_BY_DST || side == CB_BY_SRC, CB_E_INVALID, "cb_agg_edge_dot: unknown side");
+    CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_agg_edge_dot: unknown dtype");
+    CB_REQUIRE(d > 0, CB_E_INVALID, "cb_agg_edge_dot: d must be positive");
+    const cb::Side& s = side == CB_BY_DST ? g->by_dst : g->by_src;
+    if (g->rows == 0 || s.n_edges == 0) return CB_OK;
+    CB_REQUIRE(X && Y && out, CB_E_INVALID, "cb_agg_edge_dot: NULL buffer");
+    ld_x = ld_x ? ld_x : d;
+    ld_y = ld_y ? ld_y : d;
+    const int64_t tasks = g->rows + s.n_chunks;
+    const int64_t blocks = cb::ceil_div(tasks, 8);
+    CB_REQUIRE(blocks < (int64_t)INT32_MAX, CB_E_UNSUPPORTED, "cb_agg_edge_dot: grid too large");
+    if (dtype == CB_F32)
+        cb::k_edge_dot<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            s.rowptr, s.col, s.perm, s.chunk_row, s.chunk_beg, g->rows, s.n_chunks, g->hub_chunk, (const float*)X, ld_x,
+            (const float*)Y, ld_y, d, out);
+    else
+        cb::k_edge_dot<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            s.rowptr, s.col, s.perm, s.chunk_row, s.chunk_beg, g->rows, s.n_chunks, g->hub_chunk,
+            (const __nv_bfloat16*)X, ld_x, (const __nv_bfloat16*)Y, ld_y, d, out);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
 }
 
 int cb_agg_gather_compacted(const cb_graph_t* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,

@@ -1134,3 +1134,82 @@ class _CopySum(torch.autograd.Function):
 
 def copy_sum(H, graph):
     return _CopySum.apply(H, graph)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge-weighted aggregation: graph.update_all(fn.u_mul_e('h', '_edge_weight', 'm'), fn.sum('m', 'h')), GCN.py:199-202
+# ---------------------------------------------------------------------------------------------
+def sort_edge_values_raw(graph, side, values):
+    """Per-edge fp32 values in the order of the caller's edge list -> the stored order of one CSR side."""
+    _need_cuda(values)
+    v = values.reshape(-1).to(torch.float32).contiguous()
+    e = graph.num_edges if side == C.CB_BY_DST else graph.num_edges_by_src
+    out = torch.empty(e, dtype=torch.float32, device=v.device)
+    with torch.cuda.device(v.device):
+        C.call('cb_graph_sort_edge_values', graph.handle, side, C.ptr(v), v.numel(), C.ptr(out), C.stream_ptr(v.device))
+    return out
+
+
+def agg_gather_weighted_raw(graph, side, X, edge_val, row_scale=None):
+    """out[r] = row_scale[r] * sum_j X[col[j]] * edge_val[j] (edge_val in stored order, cb_agg_gather_weighted)."""
+    _need_cuda(X, edge_val, row_scale)
+    if X.dtype not in _STORAGE:
+        raise TypeError(f'X must be float32 or bfloat16, got {X.dtype}')
+    X, row_scale = X.contiguous(), _f32c(row_scale)
+    d = X.shape[1]
+    if X.shape[0] != graph.num_nodes:
+        raise ValueError(f'X has {X.shape[0]} rows, the graph has {graph.num_nodes} nodes')
+    out = torch.empty((graph.rows, d), dtype=X.dtype, device=X.device)
+    ws, ws_bytes = graph.workspace(side, d)
+    alg = gather_alg_bytes(graph, side, d, 1, 1, False, int(row_scale is not None), X.element_size()) + 4 * edge_val.numel()
+    with torch.cuda.device(X.device), _Timed('agg_gather_weighted', alg, X.device):
+        C.call('cb_agg_gather_weighted', graph.handle, side, C.CB_F32 if X.dtype == torch.float32 else C.CB_BF16,
+               C.ptr(X), d, d, C.ptr(edge_val), C.ptr(row_scale), C.ptr(out), d, C.ptr(ws), ws_bytes,
+               C.stream_ptr(X.device))
+    return out
+
+
+def edge_dot_raw(graph, side, X, Y, num_values):
+    """fp32 [num_values]: <X[col[j]], Y[row]> at the caller's position of every stored edge of ``side`` (cb_agg_edge_dot)."""
+    _need_cuda(X, Y)
+    if X.dtype not in _STORAGE or Y.dtype != X.dtype or X.shape[1] != Y.shape[1]:
+        raise TypeError('edge_dot: X and Y must share a float32 / bfloat16 type and their width')
+    X, Y = X.contiguous(), Y.contiguous()
+    out = torch.zeros(int(num_values), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        C.call('cb_agg_edge_dot', graph.handle, side, C.CB_F32 if X.dtype == torch.float32 else C.CB_BF16, C.ptr(X),
+               X.shape[1], C.ptr(Y), Y.shape[1], X.shape[1], C.ptr(out), C.stream_ptr(X.device))
+    return out
+
+
+class _WeightedSum(torch.autograd.Function):
+    """rst[v] = sum_{e = (u->v)} w[e] * h[u]; backward: dh[u] = sum_{e = (u->v)} w[e] * drst[v], dw[e] = <h[u], drst[v]>."""
+
+    @staticmethod
+    def forward(ctx, H, w, graph):
+        if graph.world != 1:
+            raise NotImplementedError('edge_weight on a node-sliced graph: the per-edge gradient is not assembled '
+                                      'across ranks (the TeacherGNN path never passes edge weights)')
+        w32 = w.detach().reshape(-1).to(torch.float32).contiguous()
+        ctx.graph, ctx.w_shape, ctx.w_dtype = graph, w.shape, w.dtype
+        ctx.save_for_backward(H, w32)
+        return agg_gather_weighted_raw(graph, C.CB_BY_DST, H, sort_edge_values_raw(graph, C.CB_BY_DST, w32))
+
+    @staticmethod
+    def backward(ctx, d):
+        H, w32 = ctx.saved_tensors
+        g = ctx.graph
+        d = d.contiguous()
+        dH = dw = None
+        if ctx.needs_input_grad[0]:
+            dH = agg_gather_weighted_raw(g, C.CB_BY_SRC, d, sort_edge_values_raw(g, C.CB_BY_SRC, w32))
+        if ctx.needs_input_grad[1]:
+            dw = edge_dot_raw(g, C.CB_BY_DST, H, d, w32.numel()).to(ctx.w_dtype).view(ctx.w_shape)
+        return dH, dw, None
+
+
+def weighted_sum(H, edge_weight, graph):
+    """The bare ``update_all(u_mul_e, sum)`` of GCN.py:199-202,238 with autograd in H and in the edge weights."""
+    if edge_weight.reshape(-1).shape[0] != graph.num_edges or (edge_weight.dim() > 1 and edge_weight.numel() != graph.num_edges):
+        raise ValueError(f'edge_weight must hold one value per edge ({graph.num_edges}), got {tuple(edge_weight.shape)}')
+    return _WeightedSum.apply(H, edge_weight, graph)

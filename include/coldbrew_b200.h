@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 6   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid; 5: source panels; 6: graph preparation, cb_agg_backward_prep_ex */
+#define CB_ABI_VERSION 6   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid; 5: source panels; 6: graph preparation, cb_agg_backward_prep_ex, edge weights */
 
 enum {
     CB_OK = 0,
@@ -201,6 +201,25 @@ int cb_agg_forward_pass(const cb_graph_t* g, int dtype, const void* H, int64_t l
 int cb_agg_gather_pass(const cb_graph_t* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
                        const float* row_scale, void* out, int64_t ld_out, int panel, float* carry, void* workspace,
                        int64_t workspace_bytes, void* stream);
+
+/*
+ * Edge-weighted aggregation (GCN.py:199-202: graph.edata['_edge_weight'] = edge_weight; fn.u_mul_e('h', '_edge_weight',
+ * 'm') then fn.sum): out[r] = row_scale[r] * sum_j X[col[j]] * w[j], every product rounded before the in-order add.
+ *   cb_graph_sort_edge_values  the caller's per-edge values [num_values] (positions of the edge list the graph was built
+ *                              from) -> the stored order of `side`: out[j] = values[perm[j]], out [E_side]
+ *   cb_agg_gather_weighted     the gather with edge_val in stored order (by destination: the forward sum; by source:
+ *                              its autograd transpose on the same weights sorted for that side)
+ *   cb_agg_edge_dot            dL/dw: out[perm[j]] = <X[col[j], :], Y[row, :]> for every stored edge of `side` (X holds
+ *                              every gathered row, Y the owned rows; out in the caller's edge positions, fp32)
+ * dtype CB_F32 / CB_BF16 of X, Y and the gathered output; weights and dot products are fp32.
+ */
+int cb_graph_sort_edge_values(const cb_graph_t* g, int side, const float* values, int64_t num_values, float* out,
+                              void* stream);
+int cb_agg_gather_weighted(const cb_graph_t* g, int side, int dtype, const void* X, int64_t ld_x, int64_t d,
+                           const float* edge_val, const float* row_scale, void* out, int64_t ld_out, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+int cb_agg_edge_dot(const cb_graph_t* g, int side, int dtype, const void* X, int64_t ld_x, const void* Y, int64_t ld_y,
+                    int64_t d, float* out, void* stream);
 
 /*
  * One label-propagation / outcome-correlation iteration in one kernel (Label_propagation_model/

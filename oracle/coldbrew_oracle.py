@@ -132,6 +132,10 @@ def _c_oracle():
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
             ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
         lib.cb_oracle_num_threads.restype = ctypes.c_int
+        lib.cb_oracle_spmm_mul_sum_csr.restype = ctypes.c_int
+        lib.cb_oracle_spmm_mul_sum_csr.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+            ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
         _CLIB = lib
     return _CLIB
 
@@ -156,6 +160,31 @@ def aggregate_sum_csr_ordered(h: np.ndarray, rowptr: np.ndarray, cols: np.ndarra
     if rc != 0:
         raise RuntimeError(f'cb_oracle_spmm_sum_csr failed rc={rc}')
     return out
+
+
+def aggregate_mul_sum_csr_ordered(h: np.ndarray, rowptr: np.ndarray, cols: np.ndarray, vals: np.ndarray,
+                                  hub_chunk: int = 0, threads: int = 0) -> np.ndarray:
+    """Edge-weighted in-order CSR row sums (GCN.py:199-202 ``u_mul_e`` + ``sum``): ``vals[j]`` is the weight of the
+    stored edge j; every product is rounded to fp32 before it is added, chunks as in aggregate_sum_csr_ordered."""
+    lib = _c_oracle()
+    h = np.ascontiguousarray(h, dtype=np.float32)
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    cols = np.ascontiguousarray(cols, dtype=np.int64)
+    vals = np.ascontiguousarray(vals, dtype=np.float32)
+    nrows = rowptr.shape[0] - 1
+    out = np.zeros((nrows, h.shape[1]), dtype=np.float32)
+    rc = lib.cb_oracle_spmm_mul_sum_csr(rowptr.ctypes.data, cols.ctypes.data, vals.ctypes.data, h.ctypes.data,
+                                        h.shape[0], h.shape[1], out.ctypes.data, nrows, int(hub_chunk), int(threads))
+    if rc != 0:
+        raise RuntimeError(f'cb_oracle_spmm_mul_sum_csr failed rc={rc}')
+    return out
+
+
+def aggregate_mul_sum(h: torch.Tensor, edge_index: torch.Tensor, edge_weight: torch.Tensor, num_dst: int) -> torch.Tensor:
+    """rst[v] = sum over edges e = (u->v) of h[u] * w[e] (GCN.py:199-202).  Differentiable in h and w."""
+    w = edge_weight.reshape(-1, *([1] * (h.dim() - 1)))
+    out = torch.zeros((num_dst,) + tuple(h.shape[1:]), dtype=h.dtype, device=h.device)
+    return out.index_add_(0, edge_index[1], h[edge_index[0]] * w)
 
 
 def c_oracle_threads() -> int:
@@ -197,7 +226,8 @@ def aggregate_sum_planned(h: torch.Tensor, plan: CsrPlan) -> torch.Tensor:
 # one GCNConv layer (GCN.py:184-258)
 # --------------------------------------------------------------------------------------
 
-def gcn_conv(feat, edge_index, num_nodes, weight, bias=None, le=None, allow_zero_in_degree=False, plan=None):
+def gcn_conv(feat, edge_index, num_nodes, weight, bias=None, le=None, allow_zero_in_degree=False, plan=None,
+             edge_weight=None):
     """Returns (rst, se_reg).  Order of operations is the reference's:
 
     scale source rows by dout^-1/2  ->  @ W  ->  + E (unscaled)  ->  sum over in-edges  ->
@@ -217,7 +247,11 @@ def gcn_conv(feat, edge_index, num_nodes, weight, bias=None, le=None, allow_zero
         # Pubmed size (19 717 x 256), which is the accumulation error of that one kernel, not reference
         # semantics; the small golden fixtures still agree with the reference's fp32 value to 1e-6.
         se_reg = torch.linalg.vector_norm(le, dtype=torch.float64).to(le.dtype)
-    rst = aggregate_sum(h, edge_index, num_nodes) if plan is None else aggregate_sum_planned(h, plan)  # GCN.py:238
+    if edge_weight is not None:                                                # GCN.py:199-202 (degrees stay counts)
+        assert edge_weight.shape[0] == edge_index.shape[1]
+        rst = aggregate_mul_sum(h, edge_index, edge_weight, num_nodes)
+    else:
+        rst = aggregate_sum(h, edge_index, num_nodes) if plan is None else aggregate_sum_planned(h, plan)  # GCN.py:238
     rst = rst * din_is.reshape(-1, 1)                                          # GCN.py:242-250
     if bias is not None:
         rst = rst + bias                                                       # GCN.py:252-253

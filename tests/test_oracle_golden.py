@@ -100,3 +100,25 @@ def test_powerlaw_graph_is_canonical():
     assert set((dst * n + src).tolist()) == set(key.tolist())        # symmetric
     assert ei.shape[1] == 2 * 9000 + n
     assert not O.has_zero_in_degree(ei, n)
+
+
+def test_edge_weighted_oracle_forms_agree():
+    """GCN.py:199-202 (u_mul_e): unit weights give the unweighted layer; the in-order C restatement and the
+    index_add_ restatement agree (to fp32 reassociation); the toy graph by hand."""
+    import numpy as np
+    rst, _ = O.gcn_conv(torch.eye(3), TOY, 3, torch.eye(3), torch.zeros(3))
+    rst_w, _ = O.gcn_conv(torch.eye(3), TOY, 3, torch.eye(3), torch.zeros(3), edge_weight=torch.ones(TOY.shape[1]))
+    assert torch.equal(rst, rst_w)
+    g = torch.Generator().manual_seed(0)
+    n, e, d = 300, 4000, 16
+    ei = torch.randint(0, n, (2, e), generator=g)
+    x, w = torch.randn(n, d, generator=g), torch.randn(e, generator=g)
+    rp, cl, pm = O.build_csr(ei[1].numpy(), ei[0].numpy(), n)
+    a = O.aggregate_mul_sum_csr_ordered(x.numpy(), rp, cl, w.numpy()[pm])
+    b = O.aggregate_mul_sum(x, ei, w, n).numpy()
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(O.aggregate_mul_sum_csr_ordered(x.numpy(), rp, cl, np.ones(e, np.float32)),
+                          O.aggregate_sum_csr_ordered(x.numpy(), rp, cl))
+    tiny = O.aggregate_mul_sum_csr_ordered(np.array([[1., 2.], [3., 4.]], np.float32), np.array([0, 2, 3]), np.array([1, 0, 1]),
+                                           np.array([0.5, 2., 3.], np.float32))
+    assert tiny.tolist() == [[3.5, 6.0], [9.0, 12.0]]

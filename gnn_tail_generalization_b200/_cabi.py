@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcoldbrew_b200.so')
+# CB_LIB: another build of the same ABI (A/B measurements of a kernel change); default: the in-tree library
+LIB_PATH = os.environ.get('CB_LIB') or os.path.join(_HERE, 'libcoldbrew_b200.so')
 
 CB_OK = 0
 ABI_VERSION = 6

@@ -86,6 +86,8 @@ SYMBOLS = {
     'cb_peer_close': (_int, [_vp]),
     'cb_peer_free': (_int, [_vp]),
     'cb_gemm_rows_grad_workspace_bytes': (_i64, [_i64, _i64]),
+    'cb_gemm_rows_masked': (_int, [_int, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _int, _vp, _i64, _vp, _vp,
+                                   _i64, _vp, _i64, _vp, _vp]),
     'cb_gemm_rows_grad': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _int, _dbl,
                                  _vp, _i64, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'cb_row_any_nonzero': (_int, [_vp, _int, _i64, _i64, _i64, _vp, _vp]),

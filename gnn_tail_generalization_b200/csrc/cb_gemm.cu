@@ -94,6 +94,8 @@ struct GemmArgs {
     void* out2;              // [M, ld_out2] or null (S)
     int64_t ld_out2;
     int64_t n_tiles_m;
+    uint8_t* relu_mask;      // forward: [M, ld_mask] bytes, 1 where the relu output is positive, or null
+    int64_t ld_mask;
     int tile_first, tile_step;   // this launch's 128-row tiles: tile_first, tile_first + tile_step, ... (0, 1 = all)
     // ---- gradient epilogue (k_gemm_rows<S, BN, true>): the backward prologue of the layer below ----
     const uint8_t* gate_u8;   // [M, ld_gate] relu mask bytes, or null
@@ -695,6 +697,18 @@ k_gemm_rows(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                             if (itr < nval) st4_cs(p + (int64_t)itr * 4 * g.ld_out, v[itr]);
                         if (g.push.n_peers) push_to_peers<S>(g.push, rbase, col, nval, v);
                     }
+                    if (g.relu_mask) {
+                        // the backward's relu gate as bytes: a quarter (fp32) of what re-reading the activations costs
+                        uint8_t* p = g.relu_mask + rbase * g.ld_mask + col;
+                        // "positive as STORED": a bf16 store rounds fp32 values up to 2^-134 to zero
+                        const float z = sizeof(S) == 2 ? __uint_as_float(0x00008000u) : 0.f;
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr) {
+                            const uint32_t m = (v[itr].x > z ? 1u : 0u) | (v[itr].y > z ? 0x100u : 0u) |
+                                               (v[itr].z > z ? 0x10000u : 0u) | (v[itr].w > z ? 0x1000000u : 0u);
+                            if (itr < nval) *reinterpret_cast<uint32_t*>(p + (int64_t)itr * 4 * g.ld_mask) = m;
+                        }
+                    }
                     if (g.out2) {
                         S* p = reinterpret_cast<S*>(g.out2) + rbase * g.ld_out2 + col;
 #pragma unroll
@@ -850,7 +864,9 @@ template <typename S>
 static int gemm_rows_impl(const S* A, int64_t M, int64_t K, int64_t lda, const S* Bt_hi, const S* Bt_lo, int64_t N,
                           const float* row_scale, const float* bias, const S* add, int64_t ld_add, int act, S* out,
                           int64_t ld_out, const float* out2_scale, S* out2, int64_t ld_out2, const cb_peer_push_t* push,
-                          void* stream) {
+                          void* stream, uint8_t* relu_mask = nullptr, int64_t ld_mask = 0) {
+    CB_REQUIRE(!relu_mask || (ld_mask >= N && ld_mask % 4 == 0 && (reinterpret_cast<uintptr_t>(relu_mask) & 3u) == 0),
+               CB_E_INVALID, "cb_gemm_rows_masked: the mask needs a 4-byte aligned base and pitch >= N");
     CB_REQUIRE(!push || (push->n_peers >= 0 && push->n_peers <= CB_MAX_PEERS && (push->n_peers == 0 ||
                          (out && push->need && push->ld >= N && push->ld % 4 == 0))), CB_E_INVALID,
                "cb_gemm_rows: bad cb_peer_push_t");
@@ -883,6 +899,7 @@ static int gemm_rows_impl(const S* A, int64_t M, int64_t K, int64_t lda, const S
     g.M = M; g.N = (int)N; g.K = (int)K;
     g.row_scale = row_scale; g.bias = bias; g.add = add; g.ld_add = ld_add; g.act = act;
     g.out = out; g.ld_out = ld_out; g.out2_scale = out2_scale; g.out2 = out2; g.ld_out2 = ld_out2;
+    g.relu_mask = relu_mask; g.ld_mask = ld_mask;
     if (push) g.push = *push;
     g.n_tiles_m = ceil_div(M, BM);
     g.tile_first = (push && push->tile_step > 0) ? push->tile_first : 0;
@@ -1321,6 +1338,21 @@ int cb_gemm_rows_bf16(const uint16_t* A, int64_t M, int64_t K, int64_t lda, cons
     using B = __nv_bfloat16;
     return cb::tc::gemm_rows_impl<B>((const B*)A, M, K, lda, (const B*)Bt, nullptr, N, row_scale, bias, (const B*)add,
                                      ld_add, act, (B*)out, ld_out, out2_scale, (B*)out2, ld_out2, push, stream);
+}
+
+int cb_gemm_rows_masked(int dtype, const void* A, int64_t M, int64_t K, int64_t lda, const void* Bt_hi, const void* Bt_lo,
+                        int64_t N, const float* row_scale, const float* bias, const void* add, int64_t ld_add, int act,
+                        void* out, int64_t ld_out, const float* out2_scale, void* out2, int64_t ld_out2,
+                        uint8_t* relu_mask, int64_t ld_mask, const cb_peer_push_t* push, void* stream) {
+    using B = __nv_bfloat16;
+    CB_REQUIRE(dtype == CB_F32 || dtype == CB_BF16, CB_E_INVALID, "cb_gemm_rows_masked: unknown dtype");
+    if (dtype == CB_F32)
+        return cb::tc::gemm_rows_impl<float>((const float*)A, M, K, lda, (const float*)Bt_hi, (const float*)Bt_lo, N,
+                                             row_scale, bias, (const float*)add, ld_add, act, (float*)out, ld_out,
+                                             out2_scale, (float*)out2, ld_out2, push, stream, relu_mask, ld_mask);
+    return cb::tc::gemm_rows_impl<B>((const B*)A, M, K, lda, (const B*)Bt_hi, nullptr, N, row_scale, bias, (const B*)add,
+                                     ld_add, act, (B*)out, ld_out, out2_scale, (B*)out2, ld_out2, push, stream,
+                                     relu_mask, ld_mask);
 }
 
 int cb_gemm_weight_to_bf16(const float* W, int64_t n_rows, int64_t k_cols, int transpose, uint16_t* out, void* stream) {

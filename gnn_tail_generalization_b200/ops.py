@@ -335,14 +335,16 @@ def _weight_args(wt, c0, K):
 
 
 def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_scale=None, want_out=True,
-                  want_out2=False, push=None):
+                  want_out2=False, push=None, want_relu_mask=False):
     """act(row_scale * (A @ W^T) + bias + add) on the tcgen05 tensor cores: fp32 A -> 3xTF32 (fp32-class accuracy),
     bf16 A -> kind::f16 on the operands as stored (add / out / out2 then bf16 too, epilogue in fp32).
     Returns out, or (out, out2) when want_out2 (out2 = out2_scale[:,None] * out).
 
     push (dist.PushSlot, multi-GPU): ``out`` is written into the exchange buffer -- one launch per column
     panel of the slot, each storing its rows also into the peers that gather them and followed by the
-    slot's stream barrier -- and the slot's local view is returned ([M, N], or [M, panels, N/panels])."""
+    slot's stream barrier -- and the slot's local view is returned ([M, N], or [M, panels, N/panels]).
+    want_relu_mask (no push): also returns, last, uint8 [M, N] with 1 where the activated output is positive
+    (cb_gemm_rows_masked): the byte gate of the backward pass."""
     _need_cuda(A, row_scale, bias, add, out2_scale)
     st = A.dtype
     if st not in _STORAGE or wt.dtype != st:
@@ -380,6 +382,17 @@ def gemm_rows_raw(A, wt, row_scale=None, bias=None, add=None, relu=False, out2_s
                        C.stream_ptr(A.device))
             push.pushed(p)
         return (push.local, out2) if want_out2 else push.local
+    if want_relu_mask:
+        if push is not None or M == 0:
+            raise ValueError('want_relu_mask: a plain launch on a non-empty matrix only')
+        rmask = torch.empty((M, N), dtype=torch.uint8, device=A.device)
+        alg = es * (M * K + M * N * (int(want_out) + int(want_out2) + int(add is not None))) + wbytes * N * K + M * N
+        wa = _weight_args(wt, 0, K)
+        with torch.cuda.device(A.device), _Timed('gemm_rows' + _sfx(st), alg, A.device, flops=mma * M * N * K):
+            C.call('cb_gemm_rows_masked', C.CB_F32 if st == torch.float32 else C.CB_BF16, C.ptr(A), M, K, K, wa[0],
+                   wa[1] if len(wa) > 1 else None, N, C.ptr(row_scale), C.ptr(bias), C.ptr(add), N, act, C.ptr(out), N,
+                   C.ptr(out2_scale), C.ptr(out2), N, C.ptr(rmask), N, None, C.stream_ptr(A.device))
+        return (out, out2, rmask) if want_out2 else (out, rmask)
     if push is None:
         alg = es * (M * K + M * N * (int(want_out) + int(want_out2) + int(add is not None))) + wbytes * N * K
         with torch.cuda.device(A.device), _Timed('gemm_rows' + _sfx(st), alg, A.device, flops=mma * M * N * K):
@@ -649,7 +662,7 @@ class BwdPlan:
     already done.  The caller (TricksComb) creates a plan only where the single-consumer condition holds by
     construction."""
     __slots__ = ('kind', 'graph', 'gate_u8', 'gate_f32', 'relu', 'mixed', 'alpha', 'want_bias', 'want_x0',
-                 'x0_sink', 'slot', 'result', 'row_sparse_hint')
+                 'x0_sink', 'slot', 'result', 'row_sparse_hint', 'dy_live')
 
     def __init__(self):
         self.kind = None       # 'relu_bias' (Linear + relu) | 'prep' (fused aggregation)
@@ -661,13 +674,14 @@ class BwdPlan:
         # set by the caller for the layer under the output head: its gradient is row-sparse when the loss reads
         # the train rows only, so the GEMM also records which rows of G are non-zero and the gather skips the rest
         self.row_sparse_hint = False
+        self.dy_live = None    # left by run(): uint8 [M] flags of the non-zero rows of the consumer's incoming gradient
 
     def run(self, dtot_in, wb, row_scale, add):
         """Called from the consumer's backward: dX GEMM + this plan's prologue.  ``row_scale``/``add`` are
         the consumer's own epilogue terms (its out-degree scale, parked residual gradients)."""
         if self.kind == 'relu_bias':
-            out, col, _ = gemm_rows_grad_raw(dtot_in, wb, row_scale=row_scale, add=add, gate_f32=self.gate_f32,
-                                             want_col_sum=self.want_bias)
+            out, col, _ = gemm_rows_grad_raw(dtot_in, wb, row_scale=row_scale, add=add, gate_u8=self.gate_u8,
+                                             gate_f32=self.gate_f32, want_col_sum=self.want_bias)
             self.result = {'d_bias': col}
             return out
         g = self.graph
@@ -691,6 +705,7 @@ class BwdPlan:
             # Measured at the bench shape (scripts/grad_sparse_bench.py): 7.48 -> 5.75 + 0.90 ms for this GEMM and
             # 12.2 -> 10.2 ms for the next one, which no longer reads the 90 % of d_x0 that would have been zeros.
             a_live = row_any_nonzero_raw(dtot_in)
+            self.dy_live = a_live          # the consumer's weight gradient skips the same rows (_Dense.backward)
             if slot is not None:
                 # multi-GPU: the flags of every rank are all-gathered HERE, ahead of the first panel's GEMM: the
                 # side-stream gathers wait only for their panel's event, which is recorded after this point, so
@@ -797,11 +812,21 @@ class _Dense(torch.autograd.Function):
         # multi-GPU: the output is what the next aggregation gathers -> write it into the exchange buffer and
         # into the peers from the epilogue (graph.exchange() then only has to wait for everyone's pushes)
         slot = push_graph.push_slot(C.CB_BY_DST, wt.n, x.dtype) if (push_graph is not None and want_out) else None
-        res = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2, push=slot)
-        out, out2 = res if want_out2 else (res, None)
+        need = any(ctx.needs_input_grad[:4]) or add_sink is not None
+        # the relu/bias backward of this op will ride on its consumer's dX GEMM (see below): that GEMM then gates with
+        # a byte mask written here instead of re-reading the activations
+        hands_off_relu = (my_plan is not None and relu and want_out and not want_out2 and add is None and need and
+                          slot is None and x.shape[0] > 0)
+        rmask = None
+        if hands_off_relu:
+            out, rmask = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2,
+                                       want_relu_mask=True)
+            out2 = None
+        else:
+            res = gemm_rows_raw(x, wt, row_scale, bias, add, relu, out2_scale, want_out, want_out2, push=slot)
+            out, out2 = res if want_out2 else (res, None)
         ctx.layout, ctx.relu = layout, relu
         ctx.has_bias, ctx.has_add = bias is not None, add is not None
-        need = any(ctx.needs_input_grad[:4]) or add_sink is not None
         keep_y = (out if out is not None else out2) if (relu and need) else None
         ctx.save_for_backward(x if need else None, weight if need else None, row_scale, out2_scale, keep_y)
         ctx.set_materialize_grads(False)
@@ -809,7 +834,8 @@ class _Dense(torch.autograd.Function):
             my_plan.kind = None
             if relu and want_out and not want_out2 and add is None and need:
                 # detached alias: a plan must not keep the autograd graph alive (the graph owns the plan)
-                my_plan.kind, my_plan.gate_f32 = 'relu_bias', out.detach()
+                my_plan.kind = 'relu_bias'
+                my_plan.gate_u8, my_plan.gate_f32 = (rmask, None) if rmask is not None else (None, out.detach())
                 my_plan.want_bias = bias is not None and ctx.needs_input_grad[2]
         empty = x.new_empty(0)
         return (out if out is not None else empty), (out2 if out2 is not None else empty)
@@ -862,7 +888,27 @@ class _Dense(torch.autograd.Function):
                     dx = (dx * row_scale[:, None]).to(st)
                 if parked is not None:
                     dx = dx + parked
+        dy_live = None
+        if ctx.dx_plan is not None:
+            dy_live, ctx.dx_plan.dy_live = ctx.dx_plan.dy_live, None
+        rows_kept = None
+        if (ctx.needs_input_grad[1] and dy_live is not None and M >= _COMPACT_DW_MIN_ROWS and
+                not torch.cuda.is_current_stream_capturing()):
+            # Row-sparse incoming gradient (the head under a loss over the train rows): dW = X^T dY only has terms from
+            # the live rows, wherever they sit.  Their indices are read back once (the one host sync of the step) and
+            # the weight-gradient GEMM runs on the compacted operands -- unless most rows are live anyway.
+            rows_kept = torch.nonzero(dy_live).squeeze(1)
+            if rows_kept.numel() * 2 > M:
+                rows_kept = None
+        if rows_kept is not None:
+            x = x.index_select(0, rows_kept)
+            dtot_w = dtot.index_select(0, rows_kept)
+            row_scale = row_scale.index_select(0, rows_kept) if row_scale is not None else None
+            M = int(rows_kept.numel())
+        else:
+            dtot_w = dtot
         if ctx.needs_input_grad[1]:
+            dtot = dtot_w       # (dx above is done with the full gradient)
             if gemm_tn_supported(M, K, N, st):
                 if st != torch.float32 and row_scale is not None:
                     # the bf16 kernel takes operands as stored: one extra [M, K] pass for the layer that reads an
@@ -883,6 +929,10 @@ class _Dense(torch.autograd.Function):
                 else:
                     dw = (xs.t() @ dtot if ctx.layout == 'kn' else dtot.t() @ xs).float()
         return dx, dw, d_bias, d_add, None, None, None, None, None, None, None, None, None, None, None
+
+
+# a row-sparse weight gradient is compacted (one host sync) only where the GEMM it saves is worth it
+_COMPACT_DW_MIN_ROWS = 1 << 18
 
 
 class GradSlot:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 6   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid; 5: source panels; 6: graph preparation, cb_agg_backward_prep_ex, edge weights */
+#define CB_ABI_VERSION 6   /* 3: live-column compaction, bf16 transform, SE optimizer step, local-edge graph build; 4: a_live / x0_valid; 5: source panels; 6: graph preparation, cb_agg_backward_prep_ex, edge weights, cb_gemm_rows_masked */
 
 enum {
     CB_OK = 0,
@@ -420,6 +420,17 @@ int cb_gemm_rows_bf16(const uint16_t* A, int64_t M, int64_t K, int64_t lda, cons
                       const float* row_scale, const float* bias, const uint16_t* add, int64_t ld_add, int act,
                       uint16_t* out, int64_t ld_out, const float* out2_scale, uint16_t* out2, int64_t ld_out2,
                       const cb_peer_push_t* push, void* stream);
+
+/*
+ * The same transform (dtype CB_F32: Bt_hi / Bt_lo from cb_gemm_split_weight; CB_BF16: Bt_hi from cb_gemm_weight_to_bf16,
+ * Bt_lo NULL) that also writes relu_mask [M, ld_mask] bytes: 1 where the activated output is positive.  The backward's
+ * relu gate (cb_gemm_rows_grad gate_u8) then reads a byte per element instead of re-reading the activations
+ * (GCN.py:104-106: the input Linear + relu, whose gate the first layer's adjoint GEMM applies).
+ */
+int cb_gemm_rows_masked(int dtype, const void* A, int64_t M, int64_t K, int64_t lda, const void* Bt_hi, const void* Bt_lo,
+                        int64_t N, const float* row_scale, const float* bias, const void* add, int64_t ld_add, int act,
+                        void* out, int64_t ld_out, const float* out2_scale, void* out2, int64_t ld_out2,
+                        uint8_t* relu_mask, int64_t ld_mask, const cb_peer_push_t* push, void* stream);
 int cb_gemm_rows_grad_bf16(const uint16_t* A, int64_t M, int64_t K, int64_t lda, const uint16_t* Bt, int64_t N,
                            const float* row_scale, const uint16_t* add, int64_t ld_add, const uint8_t* gate_u8,
                            const uint16_t* gate_val, int64_t ld_gate, int mixed, double alpha, uint16_t* d_x0,

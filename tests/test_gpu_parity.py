@@ -292,6 +292,44 @@ def test_layers_that_own_their_dropout_match_separate_dropout_nodes(trick, se, L
         assert 'agg_gather_src_rowsparse' in names        # the layer under the head found its dead rows itself
 
 
+def test_head_weight_gradient_on_compacted_rows(monkeypatch):
+    """Under a loss over the train rows the head's dW = X^T dY has terms from those rows only: the weight-gradient GEMM
+    runs on the compacted operands (one host sync per step, large graphs only).  Same gradient up to the reassociation
+    of the fp32 sums; every other gradient bit-identical."""
+    C, G, ops = _pkg()
+    from gnn_tail_generalization_b200.GNN_model.GNN_normalizations import TeacherGNN
+    n, e, d, Cn = 6000, 60000, 64, 32
+    ei = O.canonicalize_planetoid(_multigraph(n, e, 91), n).to(DEV)
+    a = O.make_args(type_trick='Initial', whetherHasSE='000', num_layers=2, dim_hidden=d, num_feats=d, num_classes=Cn,
+                    N_nodes=n, dataset='Cora', res_alpha=0.1, dropout=0.0)
+    a.device = DEV
+    torch.manual_seed(4)
+    model = TeacherGNN(a, None).to(DEV).train()
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(5)).to(DEV)
+    y = torch.randint(0, Cn, (n,), generator=torch.Generator().manual_seed(6)).to(DEV)
+    mask = torch.zeros(n, dtype=torch.bool, device=DEV)
+    mask[torch.randperm(n, generator=torch.Generator().manual_seed(7))[:n // 8].to(DEV)] = True     # scattered train rows
+    grads = []
+    for min_rows in (1 << 30, 1000):
+        monkeypatch.setattr(ops, '_COMPACT_DW_MIN_ROWS', min_rows)
+        model.zero_grad(set_to_none=True)
+        sink = []
+        ops.set_timing_sink(sink)
+        res = model.get_3_embs(x, ei, mask)
+        F.nll_loss(F.log_softmax(res.emb4classi, 1), y[mask]).backward()
+        ops.set_timing_sink(None)
+        grads.append(({k: p.grad.clone() for k, p in model.named_parameters()}, [s[2] for s in sink if s[0] == 'gemm_tn']))
+    (g0, _), (g1, _) = grads
+    head = 'model.model.layers_MLP.1.weight'
+    assert head in g0
+    for k in g0:
+        if k == head:
+            scale = float(g0[k].abs().max())
+            assert 0 < float((g0[k] - g1[k]).abs().max()) <= 2e-6 * scale or torch.equal(g0[k], g1[k])
+        else:
+            assert torch.equal(g0[k], g1[k]), k
+
+
 def test_transpose_identity():
     """<A x, y> == <x, A^T y>: the backward gather is the exact transpose of the forward one."""
     C, G, ops = _pkg()

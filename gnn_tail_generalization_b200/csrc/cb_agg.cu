@@ -240,8 +240,11 @@ __device__ __forceinline__ void epilogue_store(const AggArgs& a, int64_t row, in
 // source rows can be non-zero.  Skipping an all-zero row leaves every fp32 sum unchanged (x + 0 = x).
 // MODE 0: plain walk.  MODE 1 (LIVE): X is row-sparse, see above.  MODE 2 (EW): every stored edge carries a weight
 // (a.ew, in stored order): out = sum of x * w, the product rounded before the in-order add.
+// Register budget: 64 per thread (32 resident warps per SM) for everything up to two column slots per lane.  Without
+// the bound the bf16 instantiations drifted from 64 to 76 registers as the argument block grew, which cost a quarter of
+// the resident warps and 35 % of their throughput (caught by scripts/agg_bf16_bench.py against its round-1 numbers).
 template <typename S, int VEC, int LPR, int NCH, int UNROLL, int MODE>
-__global__ void __launch_bounds__(256) k_agg(const AggArgs a) {
+__global__ void __launch_bounds__(256, (NCH >= 4 ? 2 : 4)) k_agg(const AggArgs a) {
     constexpr bool LIVE = MODE == 1, EW = MODE == 2;
     constexpr int GROUPS = 32 / LPR;
     const int lane = threadIdx.x & 31;

@@ -399,6 +399,7 @@ int cb_prep_degrees(const int64_t* edge_index, int64_t num_edges, int64_t num_no
     CB_REQUIRE(num_edges == 0 || edge_index, CB_E_INVALID, "cb_prep_degrees: edge_index is NULL");
     CB_REQUIRE(num_nodes == 0 || (degs_ori && degs_dst), CB_E_INVALID, "cb_prep_degrees: an output is NULL");
     CB_REQUIRE(num_edges < (int64_t)UINT32_MAX, CB_E_UNSUPPORTED, "cb_prep_degrees: 2^32 edges or more");
+    CB_REQUIRE(num_nodes < (int64_t)INT32_MAX / 2, CB_E_UNSUPPORTED, "cb_prep_degrees: 2^30 nodes or more");
     CB_PREP_WS(CB_PREP_DEGREES, num_nodes);
     const DegWs w = carve_deg(carver, num_nodes);
     cudaStream_t st = (cudaStream_t)stream;
@@ -583,6 +584,7 @@ int cb_prep_mask_from_idx(const int64_t* idx, int64_t m, int64_t num_nodes, uint
 int cb_prep_drop_edges(const int64_t* edge_index, int64_t num_edges, const uint8_t* node_mask, int64_t num_nodes,
                        int64_t* out, int64_t* kept, void* workspace, int64_t workspace_bytes, void* stream) {
     CB_REQUIRE(num_edges >= 0 && num_nodes >= 0, CB_E_INVALID, "cb_prep_drop_edges: negative size");
+    CB_REQUIRE(num_edges < (int64_t)INT32_MAX / 2, CB_E_UNSUPPORTED, "cb_prep_drop_edges: 2^30 edges or more");
     CB_REQUIRE(kept != nullptr, CB_E_INVALID, "cb_prep_drop_edges: kept is NULL");
     *kept = 0;
     if (num_edges == 0) return CB_OK;

@@ -138,3 +138,30 @@ def test_sharded_generator_builds_one_canonical_graph(tmp_path, world, n, und):
     assert abs(ei.shape[1] - (2 * und + n)) <= 2 * world
     deg = torch.bincount(dst, minlength=n)
     assert int(deg.max()) > 20 * int(deg.median())                           # power law: hubs exist
+
+
+def test_slice_bounds_with_block_alignment():
+    """Slices of whole 128-row blocks (source-panelled graphs: a row tile of the producing GEMM must lie in one panel):
+    every node owned exactly once, every boundary but the last on a block edge, trailing ranks may be empty."""
+    from gnn_tail_generalization_b200 import dist as cbdist
+    for n, world in ((30011, 2), (30011, 8), (1000, 8), (127, 4), (10_000_000, 8), (0, 3)):
+        per = cbdist.rows_per_rank(n, world, cbdist.PANEL_ROWS)
+        assert per % cbdist.PANEL_ROWS == 0 and per * world >= n
+        spans = [cbdist.slice_bounds(n, world, r, cbdist.PANEL_ROWS) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for (a, b), (c, d) in zip(spans, spans[1:]):
+            assert b == c and a <= b
+        for a, b in spans:
+            assert a % cbdist.PANEL_ROWS == 0 or a == n
+        # the panel of local tile t on a rank that starts at `lo` is ((lo >> 7) + t) % S: the producer launch of panel p
+        # starts at tile (p - (lo >> 7)) % S and steps by S (dist.PeerExchange.slot)
+        for S in (2, 4):
+            for lo, hi in spans:
+                tiles = -(-(hi - lo) // cbdist.PANEL_ROWS)
+                covered = sorted(t for p in range(S) for t in range((p - (lo >> 7)) % S, tiles, S))
+                assert covered == list(range(tiles))
+                for p in range(S):
+                    for t in range((p - (lo >> 7)) % S, tiles, S):
+                        assert ((lo >> 7) + t) % S == p
+    # alignment 1 is the plain ceil(N / P) slicing
+    assert cbdist.rows_per_rank(10, 4) == 3 and cbdist.slice_bounds(10, 4, 3) == (9, 10)

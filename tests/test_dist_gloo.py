@@ -74,7 +74,7 @@ def test_slice_bounds_cover_everything():
             assert cbdist.is_row_sharded('model.model.layers_GCN.0.le') and not cbdist.is_row_sharded('x.weight')
 
 
-def _need_worker(rank, world, port, n, out_dir):
+def _need_worker(rank, world, port, n, out_dir, align=1):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
@@ -82,12 +82,15 @@ def _need_worker(rank, world, port, n, out_dir):
         # drop some edges so that not every row is needed everywhere
         ei = ei[:, torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(0))[: 2 * n]]
         src, dst = ei
-        per = cbdist.rows_per_rank(n, world)
-        lo, hi = cbdist.slice_bounds(n, world, rank)
+        per = cbdist.rows_per_rank(n, world, align)
+        lo, hi = cbdist.slice_bounds(n, world, rank, align)
+        # the row exchange with the same (possibly block-aligned) slicing: trailing ranks may own fewer or no rows
+        H = torch.randn(n, 4, generator=torch.Generator().manual_seed(2))
+        assert torch.equal(cbdist.exchange_rows(H[lo:hi].clone(), n, world, per=per), H)
         # forward: this rank gathers the sources of the in-edges of its rows
         needed = torch.zeros(per * world, dtype=torch.uint8)
         needed[src[(dst >= lo) & (dst < hi)]] = 1
-        mask, peers = cbdist.need_masks(needed, n, world, rank)
+        mask, peers = cbdist.need_masks(needed, n, world, rank, per=per)
         assert peers == [r for r in range(world) if r != rank] and mask.shape == (per,)
         # brute force: bit j of mask[m] <=> some edge (lo+m -> v) has v owned by peers[j]
         owner = torch.div(dst, per, rounding_mode='floor')
@@ -101,10 +104,11 @@ def _need_worker(rank, world, port, n, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,n', [(2, 501), (3, 1000)])
-def test_need_masks_match_brute_force(tmp_path, world, n):
-    """Host logic of the fused exchange: which local rows each peer gathers (dist.need_masks)."""
-    mp.spawn(_need_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize('world,n,align', [(2, 501, 1), (3, 1000, 1), (3, 700, 128), (2, 100, 128)])
+def test_need_masks_match_brute_force(tmp_path, world, n, align):
+    """Host logic of the fused exchange: which local rows each peer gathers (dist.need_masks), also with the
+    block-aligned slicing of source-panelled graphs (a trailing rank then owns few or no rows)."""
+    mp.spawn(_need_worker, args=(world, _free_port(), n, str(tmp_path), align), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f'need{r}') for r in range(world))
 
 
